@@ -1,0 +1,255 @@
+"""Generate the golden fixtures in tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE
+(/root/reference, CPU, `load_custom_cuda_lib=False`) in this container.
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors or tests with assertions, so these fixtures -
+reference outputs and reference-autograd gradients on seeded inputs, in fp64 (truth) and fp32 (the
+reference's own noise floor) - are what pins both the oracle (tests/test_oracle_golden.py) and the
+CUDA path (tests/test_gpu_*.py).  The GPU box has no /root/reference; it only reads the .npz files.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_reference  # noqa: E402
+
+warnings.filterwarnings("ignore")
+ref_emb, ref_conv = load_reference()
+FSW_embedding = ref_emb.FSW_embedding
+FSW_conv = ref_conv.FSW_conv
+FSW_readout = ref_conv.FSW_readout
+
+
+def npy(t):
+    if t is None:
+        return None
+    return t.detach().cpu().numpy().copy()
+
+
+def save(name, **arrays):
+    arrays = {k: v for k, v in arrays.items() if v is not None}
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %-40s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
+def emb_params(mod):
+    return {("param_" + k): npy(v) for k, v in mod.state_dict().items()}
+
+
+def run_both_dtypes(build, run):
+    """build(dtype)->module (seeded identically), run(module, dtype)->dict of outputs."""
+    out = {}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        mod = build(dtype)
+        res = run(mod, dtype)
+        for k, v in res.items():
+            out["%s_%s" % (k, tag)] = v
+        if dtype == torch.float64:
+            out.update(emb_params(mod))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. dense FSW_embedding: batched weighted point clouds (demo_fsw_embedding.py shape, shrunk)
+# ------------------------------------------------------------------------------------------------
+def case_dense(name, batch_dims, n, d, d_out, Wmode, seed, **kw):
+    g = torch.Generator().manual_seed(seed)
+    X64 = torch.randn(batch_dims + (n, d), generator=g, dtype=torch.float64)
+    if Wmode == "rand":
+        W64 = torch.rand(batch_dims + (n,), generator=g, dtype=torch.float64)
+        W64[..., 0] = 0.0  # an explicit zero weight
+    elif Wmode == "deficient":  # total mass below the pad threshold for some multisets
+        W64 = torch.rand(batch_dims + (n,), generator=g, dtype=torch.float64) * (1.5 / n)
+    else:
+        W64 = Wmode
+    gout = torch.randn(batch_dims + (d_out,), generator=g, dtype=torch.float64)
+
+    def build(dtype):
+        torch.manual_seed(seed)
+        return FSW_embedding(d_in=d, d_out=d_out, device="cpu", dtype=dtype, load_custom_cuda_lib=False,
+                             learnable_slices=True, learnable_freqs=True, **kw)
+
+    def run(mod, dtype):
+        X = X64.clone().to(dtype).requires_grad_(True)
+        W = W64 if isinstance(W64, str) else W64.clone().to(dtype).requires_grad_(True)
+        out = mod(X, W)
+        (out * gout.to(dtype)).sum().backward()
+        r = dict(out=npy(out), dX=npy(X.grad), dprojVecs=npy(mod.projVecs.grad), dfreqs=npy(mod.freqs.grad))
+        if not isinstance(W, str):
+            r["dW"] = npy(W.grad)
+        if getattr(mod, "bias", None) is not None and mod.bias.grad is not None:
+            r["dbias"] = npy(mod.bias.grad)
+        return r
+
+    res = run_both_dtypes(build, run)
+    save(name, X=npy(X64), W=(None if isinstance(W64, str) else npy(W64)), gout=npy(gout),
+         Wmode=np.array(Wmode if isinstance(W64, str) else "tensor"), **res)
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. sparse graph-mode FSW_embedding (the path FSW_conv drives), incl. empty and deficient rows
+# ------------------------------------------------------------------------------------------------
+def case_sparse_graph(name, S, N, d, d_out, nnz, seed, weighted, **kw):
+    g = torch.Generator().manual_seed(seed)
+    X64 = torch.randn(N, d, generator=g, dtype=torch.float64)
+    rows = torch.randint(0, S, (nnz,), generator=g)
+    rows[rows == 1] = 0  # row 1 is left empty
+    cols = torch.randint(0, N, (nnz,), generator=g)
+    vals = torch.rand(nnz, generator=g, dtype=torch.float64) + 0.05 if weighted else torch.ones(nnz, dtype=torch.float64)
+    if weighted:
+        vals[rows == 2] *= 0.05  # row 2 gets total mass < 1 (deficit padding)
+    A64 = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (S, N)).coalesce()
+    gout = torch.randn(S, d_out, generator=g, dtype=torch.float64)
+
+    def build(dtype):
+        torch.manual_seed(seed)
+        return FSW_embedding(d_in=d, d_out=d_out, device="cpu", dtype=dtype, load_custom_cuda_lib=False,
+                             learnable_slices=True, learnable_freqs=True, **kw)
+
+    def run(mod, dtype):
+        X = X64.clone().to(dtype).requires_grad_(True)
+        A = torch.sparse_coo_tensor(A64.indices(), A64.values().to(dtype), (S, N)).coalesce()
+        out = mod(X, A, graph_mode=True)
+        (out * gout.to(dtype)).sum().backward()
+        r = dict(out=npy(out), dX=npy(X.grad), dprojVecs=npy(mod.projVecs.grad), dfreqs=npy(mod.freqs.grad))
+        if getattr(mod, "total_mass_encoding_scale", None) is not None and mod.total_mass_encoding_scale.grad is not None:
+            r["dscale"] = npy(mod.total_mass_encoding_scale.grad)
+        if getattr(mod, "bias", None) is not None and mod.bias.grad is not None:
+            r["dbias"] = npy(mod.bias.grad)
+        return r
+
+    res = run_both_dtypes(build, run)
+    save(name, X=npy(X64), A_indices=npy(A64.indices()), A_values=npy(A64.values()), A_shape=np.array([S, N]),
+         gout=npy(gout), **res)
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. FSW_conv / FSW_readout
+# ------------------------------------------------------------------------------------------------
+def conv_params(mod):
+    return {("param_" + k): npy(v) for k, v in mod.state_dict().items()}
+
+
+def case_conv(name, N, E, d_in, d_out, seed, edgefeat_dim=0, with_dups=True, **kw):
+    g = torch.Generator().manual_seed(seed)
+    x64 = torch.randn(N, d_in, generator=g, dtype=torch.float64)
+    ei = torch.randint(0, N, (2, E), generator=g)
+    ei[1][ei[1] == 3] = 4  # vertex 3 receives no message (empty neighbourhood)
+    if with_dups:
+        ei[:, -3:] = ei[:, :3]  # duplicate edges: `coalesce` sums their weights
+    ef64 = torch.randn(E, edgefeat_dim, generator=g, dtype=torch.float64) if edgefeat_dim > 0 else None
+    gout = torch.randn(N, d_out, generator=g, dtype=torch.float64)
+
+    def build(dtype):
+        torch.manual_seed(seed)
+        return FSW_conv(d_in, d_out, edgefeat_dim=edgefeat_dim, device="cpu", dtype=dtype, **kw)
+
+    out_all = {}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        mod = build(dtype)
+        mod.fsw_embed  # noqa
+        ref_emb.libfsw_embedding = None  # pure-torch segcumsum on CPU
+        x = x64.clone().to(dtype).requires_grad_(True)
+        ef = ef64.clone().to(dtype).requires_grad_(True) if ef64 is not None else None
+        out = mod(x, ei, edge_features=ef)
+        (out * gout.to(dtype)).sum().backward()
+        out_all["out_" + tag] = npy(out)
+        out_all["dx_" + tag] = npy(x.grad)
+        if ef is not None:
+            out_all["def_" + tag] = npy(ef.grad)
+        for pn, p in mod.named_parameters():
+            if p.grad is not None:
+                out_all["grad_%s_%s" % (pn, tag)] = npy(p.grad)
+        if dtype == torch.float64:
+            out_all.update(conv_params(mod))
+    save(name, x=npy(x64), edge_index=npy(ei), edge_features=npy(ef64), gout=npy(gout), **out_all)
+
+
+def case_readout(name, sizes, d_in, d_out, seed, **kw):
+    g = torch.Generator().manual_seed(seed)
+    N = int(sum(sizes))
+    x64 = torch.randn(N, d_in, generator=g, dtype=torch.float64)
+    gi = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    gout = torch.randn(len(sizes), d_out, generator=g, dtype=torch.float64)
+    out_all = {}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        torch.manual_seed(seed)
+        mod = FSW_readout(d_in, d_out, concat_self=False, device="cpu", dtype=dtype, **kw)
+        x = x64.clone().to(dtype).requires_grad_(True)
+        out = mod(x, graph_index=gi, batch_size=len(sizes))
+        (out * gout.to(dtype)).sum().backward()
+        out_all["out_" + tag] = npy(out)
+        out_all["dx_" + tag] = npy(x.grad)
+        for pn, p in mod.named_parameters():
+            if p.grad is not None:
+                out_all["grad_%s_%s" % (pn, tag)] = npy(p.grad)
+        if dtype == torch.float64:
+            out_all.update(conv_params(mod))
+    save(name, x=npy(x64), graph_index=npy(gi), gout=npy(gout), **out_all)
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. segcumsum (fsw_embedding.py:2795) vs its own slow checker (:3016)
+# ------------------------------------------------------------------------------------------------
+def case_segcumsum(name, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, 40, (n,), generator=g)
+    lens[5] = 700  # one long segment spanning several 256-element blocks
+    ids = torch.repeat_interleave(torch.arange(n) * 3 + 7, lens)  # arbitrary distinct ids
+    out = {}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        v = torch.randn(ids.numel(), generator=torch.Generator().manual_seed(seed + 1), dtype=torch.float64).to(dtype)
+        slow = ref_emb.segcumsum_slow(v, ids)
+        fast = ref_emb.segcumsum(v, ids, always_use_pure_torch=True)
+        assert torch.allclose(slow, fast, rtol=1e-4 if dtype == torch.float32 else 1e-12, atol=1e-5 if dtype == torch.float32 else 1e-12)
+        out["values_" + tag] = npy(v)
+        out["out_slow_" + tag] = npy(slow)
+        out["out_torch_" + tag] = npy(fast)
+    save(name, segment_ids=npy(ids), **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. Cartesian mode (nSlices x nFreqs), small
+# ------------------------------------------------------------------------------------------------
+def case_cartesian(name, seed, collapse):
+    g = torch.Generator().manual_seed(seed)
+    X64 = torch.randn(3, 9, 4, generator=g, dtype=torch.float64)
+    W64 = torch.rand(3, 9, generator=g, dtype=torch.float64)
+    torch.manual_seed(seed)
+    mod = FSW_embedding(d_in=4, nSlices=5, nFreqs=3, collapse_freqs=collapse, device="cpu", dtype=torch.float64,
+                        load_custom_cuda_lib=False)
+    out = mod(X64, W64)
+    save(name, X=npy(X64), W=npy(W64), out_f64=npy(out), **emb_params(mod))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    case_dense("emb_dense_weighted", (2, 3), 11, 4, 9, "rand", seed=1)
+    case_dense("emb_dense_unit", (4,), 33, 3, 16, "unit", seed=2)
+    case_dense("emb_dense_uniform", (2,), 8, 3, 6, "uniform", seed=3)
+    case_dense("emb_dense_deficient_tm", (5,), 6, 2, 7, "deficient", seed=4, encode_total_mass=True,
+               total_mass_encoding_function="sqrt", learnable_total_mass_encoding_scale=True)
+    case_dense("emb_dense_n1", (3,), 1, 5, 8, "unit", seed=5)  # single point: closed-form known answer
+    case_dense("emb_dense_big", (2,), 300, 3, 32, "unit", seed=6, freqs_init="spread")
+    case_sparse_graph("emb_graph_unit", 12, 20, 5, 10, 60, seed=11, weighted=False)
+    case_sparse_graph("emb_graph_weighted", 12, 20, 5, 10, 70, seed=12, weighted=True,
+                      encode_total_mass=True, total_mass_encoding_function="log", learnable_total_mass_encoding_scale=True)
+    case_sparse_graph("emb_graph_homog", 9, 15, 4, 8, 40, seed=13, weighted=True, encode_total_mass=True,
+                      total_mass_encoding_method="homog", enable_bias=False)
+    case_conv("conv_default", 40, 240, 6, 5, seed=21)
+    case_conv("conv_selfloop_gcn", 30, 150, 5, 7, seed=22, self_loop_weight=0.2, edge_weighting="gcn",
+              vertex_degree_encoding_function="log", learnable_vertex_degree_encoding_scale=True, mlp_layers=2)
+    case_conv("conv_edgefeat", 25, 120, 5, 6, seed=23, edgefeat_dim=3, mlp_layers=3, with_dups=True)
+    case_conv("conv_homog_nomlp", 25, 100, 4, 6, seed=24, mlp_layers=0, bias=False, homog_degree_encoding=True)
+    case_conv("conv_wide", 60, 900, 8, 8, seed=25, embed_dim=40)  # mean degree 15, some degrees > 32
+    case_readout("readout_default", [5, 1, 40, 17, 30], 6, 4, seed=31)  # NB total >= 64: the reference torch segcumsum breaks when stride > n (fsw_embedding.py:2872)
+    case_segcumsum("segcumsum", 60, seed=41)
+    case_cartesian("emb_cartesian", seed=51, collapse=False)
+    case_cartesian("emb_cartesian_collapse", seed=52, collapse=True)
