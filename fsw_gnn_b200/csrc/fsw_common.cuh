@@ -1,0 +1,123 @@
+// Shared declarations for the libfsw_embedding.so kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fsw_embedding.h"
+
+// ---- host-side error plumbing (fsw_api.cu) -------------------------------------------------------
+int fsw_fail(int code, const char* fmt, ...);
+void fsw_count_launch(int n = 1);
+
+#define FSW_CHECK_LAUNCH(name)                                                                      \
+    do {                                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess)                                                                     \
+            return fsw_fail(FSW_ERR_CUDA, "%s: kernel launch failed: %s", name, cudaGetErrorString(e__)); \
+        fsw_count_launch();                                                                         \
+    } while (0)
+
+#define FSW_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fsw_fail(FSW_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));         \
+    } while (0)
+
+static inline int64_t fsw_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- info word of the segment plan ----------------------------------------------------------------
+#define FSW_INFO_UNIFORM (1 << 30)
+#define FSW_INFO_NMASK ((1 << 30) - 1)
+
+// plan bucket of a segment of n_eff elements (0..64 exact, then power-of-two ranges)
+__host__ __device__ static inline int fsw_size_bucket(int n_eff) {
+    if (n_eff < FSW_PLAN_EXACT) return n_eff;
+    if (n_eff <= 128) return 65;
+    if (n_eff <= 256) return 66;
+    if (n_eff <= 512) return 67;
+    if (n_eff <= 1024) return 68;
+    if (n_eff <= 2048) return 69;
+    if (n_eff <= 4096) return 70;
+    return 71;
+}
+
+// ---- numeric helpers --------------------------------------------------------------------------------
+template <typename T>
+struct Num;
+
+template <>
+struct Num<float> {
+    static __device__ __forceinline__ float big() { return FLT_MAX; }
+    static __device__ __forceinline__ float cospi_(float x) { return cospif(x); }
+    static __device__ __forceinline__ float sinpi_(float x) { return sinpif(x); }
+    // phase given in units of pi, in double; reduce to [-1, 1] before dropping to fp32 so that the
+    // large-frequency phases (xi up to ~2K, SURVEY.md 7 hard part 2) keep full fp32 accuracy.
+    static __device__ __forceinline__ float reduce(double phi) { return (float)(phi - 2.0 * rint(0.5 * phi)); }
+};
+
+template <>
+struct Num<double> {
+    static __device__ __forceinline__ double big() { return DBL_MAX; }
+    static __device__ __forceinline__ double cospi_(double x) { return cospi(x); }
+    static __device__ __forceinline__ double sinpi_(double x) { return sinpi(x); }
+    static __device__ __forceinline__ double reduce(double phi) { return phi; }
+};
+
+// sinc(x) = sin(pi x)/(pi x)   (torch.sinc, fsw_embedding.py:1002, :1767)
+template <typename T>
+__device__ __forceinline__ T fsw_sinc(T x) {
+    T ax = fabs(x);
+    if (ax < (T)1e-3) {
+        T y = (T)M_PI * x;
+        T y2 = y * y;
+        return (T)1 - y2 * ((T)(1.0 / 6.0) - y2 * (T)(1.0 / 120.0));
+    }
+    return Num<T>::sinpi_(x) / ((T)M_PI * x);
+}
+
+// d/dx sinc(x) = (cos(pi x) - sinc(x)) / x   (what autograd of torch.sinc gives, sp.dsinc :2763-2774)
+template <typename T>
+__device__ __forceinline__ T fsw_dsinc(T x) {
+    T ax = fabs(x);
+    if (ax < (T)0.25) {
+        // -pi^2 x/3 + pi^4 x^3/30 - pi^6 x^5/840 + pi^8 x^7/45360 - pi^10 x^9/3991680
+        T y = (T)M_PI * x;
+        T y2 = y * y;
+        T s = (T)(1.0 / 3.0) - y2 * ((T)(1.0 / 30.0) - y2 * ((T)(1.0 / 840.0) - y2 * ((T)(1.0 / 45360.0) - y2 * (T)(1.0 / 3991680.0))));
+        return -(T)M_PI * y * s;
+    }
+    return (Num<T>::cospi_(x) - fsw_sinc(x)) / x;
+}
+
+// Arguments shared by the forward and backward embedding kernels.
+template <typename T>
+struct SegArgs {
+    const T* Xp;            // [Nrows, ldp]
+    const T* Ep;            // [E, ldp] or nullptr
+    const int32_t* rowptr;  // [S+1] or nullptr
+    const int32_t* col;     // [E] or nullptr
+    const T* W;             // [E] or nullptr
+    const double* mass;     // [S]
+    const int32_t* info;    // [S]
+    const int32_t* order;   // [S] or nullptr (identity)
+    const T* freqs;         // [K]
+    int64_t ldp;
+    int64_t n_fixed;
+    int K;
+    double thresh;
+};
+
+template <typename T>
+__device__ __forceinline__ void fsw_seg_range(const SegArgs<T>& a, int s, int64_t& e0, int& n) {
+    if (a.rowptr) {
+        e0 = a.rowptr[s];
+        n = a.rowptr[s + 1] - (int)e0;
+    } else {
+        e0 = (int64_t)s * a.n_fixed;
+        n = (int)a.n_fixed;
+    }
+}

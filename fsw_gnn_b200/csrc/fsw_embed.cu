@@ -1,0 +1,940 @@
+// K2 / K3: fused FSW embedding forward and backward over CSR segments.
+//
+// Replaces FSW_embedding.forward_helper (fsw_embedding.py:894-1112) and the autograd functions it
+// drives (class ag, :1232-2258; helpers sp, :2266-2775).  One launch family per size class:
+//
+//   small  (n_eff <= 64 fp32 / 32 fp64): one THREAD owns one (segment, slice).  Lanes of a warp are 32
+//          consecutive slices, so the gather Xp[col[e], k0..k0+31] is one coalesced 128-byte line per
+//          element.  Keys live in registers and are sorted with a data-oblivious Batcher odd-even
+//          merge network (no shuffles, no divergence).  Segments are visited in plan order (sorted by
+//          size) so that, with uniform weights, the per-(n, slice) Fourier coefficient table
+//          cos(pi xi (2j+1)/n) is built once and reused for a run of segments.
+//   generic (anything larger): one CTA owns a tile [n_pad][32 slices] in shared memory (or in an
+//          L2-resident global scratch when it does not fit) and runs a block-wide bitonic network
+//          with rows as elements and lanes as slices (bank = lane, conflict free).
+//
+// Numerics (SURVEY.md 7 hard part 2): the phase xi*(2C - w) is formed in fp64 from fp64 cumulative
+// weights and reduced mod 2 before it is rounded to fp32; everything else is fp32 for fp32 inputs.
+// The sparse product form D_j = 2 w sinc(xi w) cos(pi xi (2C - w)) (fsw_embedding.py:1047-1075) is
+// used for both value and gradient; it is well conditioned for every xi >= 0.
+#include <utility>
+
+#include "fsw_common.cuh"
+
+#define FSW_FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------------
+// Batcher odd-even merge sort network over NP compile-time indexed slots (NP power of two).
+// ---------------------------------------------------------------------------------------------------
+// The comparator list is produced at compile time and applied through a fold expression, so every
+// index is a constant and the arrays stay in registers whatever NP is.
+template <int NP>
+struct FswNet {
+    static constexpr int kMax = (NP <= 4) ? 8 : NP * 10;  // >= number of comparators (543 for NP = 64)
+    struct Pairs {
+        int a[kMax];
+        int b[kMax];
+        int n;
+    };
+    static constexpr Pairs make() {
+        Pairs P{};
+        int c = 0;
+        for (int p = 1; p < NP; p <<= 1)
+            for (int k = p; k >= 1; k >>= 1)
+                for (int j = k % p; j <= NP - 1 - k; j += 2 * k)
+                    for (int i = 0; i <= ((k - 1) < (NP - j - k - 1) ? (k - 1) : (NP - j - k - 1)); ++i)
+                        if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                            P.a[c] = i + j;
+                            P.b[c] = i + j + k;
+                            ++c;
+                        }
+        P.n = c;
+        return P;
+    }
+    static constexpr int count = make().n;
+};
+
+// scalar compile-time constants are usable from device code (aggregate constexpr members are not)
+template <int NP, int I>
+struct FswPair {
+    static constexpr int a = FswNet<NP>::make().a[I];
+    static constexpr int b = FswNet<NP>::make().b[I];
+};
+
+template <int NP, typename CE, int... Is>
+__device__ __forceinline__ void fsw_sort_network_apply(CE&& ce, std::integer_sequence<int, Is...>) {
+    (ce(FswPair<NP, Is>::a, FswPair<NP, Is>::b), ...);
+}
+
+template <int NP, typename CE>
+__device__ __forceinline__ void fsw_sort_network(CE&& ce) {
+    fsw_sort_network_apply<NP>(ce, std::make_integer_sequence<int, FswNet<NP>::count>{});
+}
+
+template <typename T>
+__device__ __forceinline__ T fsw_ldg(const T* p) {
+    return __ldg(p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Small path, forward
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int NP, bool UNIFORM>
+__global__ void __launch_bounds__(128) fsw_fwd_small_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks,
+                                                            T* __restrict__ out, int64_t ld_out, int64_t out_col0,
+                                                            const T* __restrict__ bias) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t item = wglobal / nchunks;
+    const int chunk = (int)(wglobal - item * nchunks);
+    const int64_t first = (int64_t)seg_lo + item * G;
+    if (first >= seg_hi) return;
+    const int last = (int)((first + G < seg_hi) ? first + G : seg_hi);
+    const int k = chunk * 32 + lane;
+    const bool act = k < a.K;
+    const int kk = act ? k : a.K - 1;
+    const T xi = fsw_ldg(a.freqs + kk);
+    const double xid = (double)xi;
+    const T bk = (bias != nullptr) ? fsw_ldg(bias + kk) : (T)0;
+
+    T coef[NP];
+    T A = (T)0;
+    int n_prev = -1;
+    (void)coef;
+    (void)A;
+    (void)n_prev;
+
+    for (int q = (int)first; q < last; ++q) {
+        const int s = a.order ? a.order[q] : q;
+        int64_t e0;
+        int n;
+        fsw_seg_range(a, s, e0, n);
+
+        // ---- gather (column ids and raw weights are loaded coalesced, then broadcast by shuffle) ----
+        int c0 = 0, c1 = 0;
+        if (a.col) {
+            if (lane < n) c0 = a.col[e0 + lane];
+            if (NP > 32 && lane + 32 < n) c1 = a.col[e0 + 32 + lane];
+        }
+        T key[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            int64_t row = e0 + j;
+            if (a.col) row = __shfl_sync(FSW_FULL, (j < 32) ? c0 : c1, j & 31);
+            T v = Num<T>::big();
+            if (j < n) {
+                v = fsw_ldg(a.Xp + row * a.ldp + kk);
+                if (a.Ep) v += fsw_ldg(a.Ep + (e0 + j) * a.ldp + kk);
+            }
+            key[j] = v;
+        }
+
+        T result;
+        if constexpr (UNIFORM) {
+            if (n != n_prev) {
+                const double u = xid / (double)n;
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    coef[j] = (j < n) ? Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * j + 1))) : (T)0;
+                const T wn = (T)(1.0 / (double)n);
+                A = ((T)1 + xi) * (T)2 * wn * fsw_sinc((T)u);
+                n_prev = n;
+            }
+            fsw_sort_network<NP>([&](int i, int l) {
+                T x = key[i], y = key[l];
+                key[i] = fmin(x, y);
+                key[l] = fmax(x, y);
+            });
+            T acc = (T)0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) acc = fma(key[j], coef[j], acc);
+            result = A * acc;
+        } else {
+            const int n_eff = a.info[s] & FSW_INFO_NMASK;
+            const bool padded = n_eff > n;
+            const double Ts = a.mass[s];
+            const double invS = 1.0 / fmax(Ts, a.thresh);
+            const double padw = a.thresh - Ts;  // raw weight of the deficit pad point (x = 0)
+            T w0 = (T)1, w1 = (T)1;
+            if (a.W) {
+                w0 = (lane < n) ? a.W[e0 + lane] : (T)0;
+                if (NP > 32) w1 = (lane + 32 < n) ? a.W[e0 + 32 + lane] : (T)0;
+            }
+            T pay[NP];  // raw weight; -1 flags the pad point, 0 for unused slots
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                T w = __shfl_sync(FSW_FULL, (j < 32) ? w0 : w1, j & 31);
+                if (j >= n) w = (T)0;
+                if (padded && j == n) {
+                    w = (T)-1;
+                    key[j] = (T)0;
+                }
+                pay[j] = w;
+            }
+            fsw_sort_network<NP>([&](int i, int l) {
+                T x = key[i], y = key[l];
+                T px = pay[i], py = pay[l];
+                bool sw = x > y;
+                key[i] = sw ? y : x;
+                key[l] = sw ? x : y;
+                pay[i] = sw ? py : px;
+                pay[l] = sw ? px : py;
+            });
+            double Craw = 0.0;
+            T acc = (T)0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                if (j < n_eff) {
+                    const double wr = (pay[j] < (T)0) ? padw : (double)pay[j];
+                    Craw += wr;
+                    const double wn = wr * invS;
+                    const double phi = xid * (2.0 * Craw * invS - wn);
+                    const T c = Num<T>::cospi_(Num<T>::reduce(phi));
+                    const T wnf = (T)wn;
+                    const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                    acc = fma(key[j], aj * c, acc);
+                }
+            }
+            result = ((T)1 + xi) * acc;
+        }
+        if (act) out[(int64_t)s * ld_out + out_col0 + k] = result + bk;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Small path, backward.  Dynamic shared memory per warp: [3][NP][32] T  (un-permute buffer, cos table,
+// d/dxi table).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int NP, bool UNIFORM, bool NEED_DXI>
+__global__ void __launch_bounds__(128) fsw_bwd_small_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks,
+                                                            const T* __restrict__ g, int64_t ld_g, int64_t g_col0,
+                                                            T* __restrict__ dXp, T* __restrict__ dEp,
+                                                            double* __restrict__ dfreqs) {
+    extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    T* sm_val = reinterpret_cast<T*>(fsw_smem_raw) + (size_t)warp * 3 * NP * 32;
+    T* sm_c = sm_val + NP * 32;
+    T* sm_t = sm_c + NP * 32;
+    (void)sm_c;
+    (void)sm_t;
+
+    const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t item = wglobal / nchunks;
+    const int chunk = (int)(wglobal - item * nchunks);
+    const int64_t first = (int64_t)seg_lo + item * G;
+    if (first >= seg_hi) return;
+    const int last = (int)((first + G < seg_hi) ? first + G : seg_hi);
+    const int k = chunk * 32 + lane;
+    const bool act = k < a.K;
+    const int kk = act ? k : a.K - 1;
+    const T xi = fsw_ldg(a.freqs + kk);
+    const double xid = (double)xi;
+
+    double dxi_acc = 0.0;
+    T A0 = (T)0, A0p = (T)0;
+    int n_prev = -1;
+    (void)A0p;
+    (void)n_prev;
+
+    for (int q = (int)first; q < last; ++q) {
+        const int s = a.order ? a.order[q] : q;
+        int64_t e0;
+        int n;
+        fsw_seg_range(a, s, e0, n);
+        const int n_eff = UNIFORM ? n : (a.info[s] & FSW_INFO_NMASK);
+        const bool padded = n_eff > n;
+
+        int c0 = 0, c1 = 0;
+        if (a.col) {
+            if (lane < n) c0 = a.col[e0 + lane];
+            if (NP > 32 && lane + 32 < n) c1 = a.col[e0 + 32 + lane];
+        }
+        T key[NP];
+        int idx[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            int64_t row = e0 + j;
+            if (a.col) row = __shfl_sync(FSW_FULL, (j < 32) ? c0 : c1, j & 31);
+            T v = Num<T>::big();
+            if (j < n) {
+                v = fsw_ldg(a.Xp + row * a.ldp + kk);
+                if (a.Ep) v += fsw_ldg(a.Ep + (e0 + j) * a.ldp + kk);
+            }
+            if (!UNIFORM && padded && j == n) v = (T)0;
+            key[j] = v;
+            idx[j] = j;
+        }
+        fsw_sort_network<NP>([&](int i, int l) {
+            T x = key[i], y = key[l];
+            int px = idx[i], py = idx[l];
+            bool sw = x > y;
+            key[i] = sw ? y : x;
+            key[l] = sw ? x : y;
+            idx[i] = sw ? py : px;
+            idx[l] = sw ? px : py;
+        });
+
+        const T gk = act ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
+        const T Gk = gk * ((T)1 + xi);
+
+        if constexpr (UNIFORM) {
+            if (n != n_prev) {
+                const double u = xid / (double)n;
+                const T wn = (T)(1.0 / (double)n);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    if (j < n) {
+                        const T r = Num<T>::reduce(u * (double)(2 * j + 1));
+                        sm_c[j * 32 + lane] = Num<T>::cospi_(r);
+                        if (NEED_DXI) sm_t[j * 32 + lane] = (T)M_PI * wn * (T)(2 * j + 1) * Num<T>::sinpi_(r);
+                    }
+                }
+                A0 = (T)2 * wn * fsw_sinc((T)u);
+                if (NEED_DXI) A0p = (T)2 * wn * wn * fsw_dsinc((T)u);
+                n_prev = n;
+            }
+            T Sc = (T)0, Ss = (T)0;
+            const T GA = Gk * A0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                if (j < n) {
+                    const T c = sm_c[j * 32 + lane];
+                    sm_val[idx[j] * 32 + lane] = GA * c;
+                    if (NEED_DXI) {
+                        Sc = fma(key[j], c, Sc);
+                        Ss = fma(key[j], sm_t[j * 32 + lane], Ss);
+                    }
+                }
+            }
+            if (NEED_DXI) dxi_acc += (double)(gk * (A0 * Sc + ((T)1 + xi) * (A0p * Sc - A0 * Ss)));
+        } else {
+            const double Ts = a.mass[s];
+            const double invS = 1.0 / fmax(Ts, a.thresh);
+            const double padw = a.thresh - Ts;
+            T w0 = (T)1, w1 = (T)1;
+            if (a.W) {
+                w0 = (lane < n) ? a.W[e0 + lane] : (T)0;
+                if (NP > 32) w1 = (lane + 32 < n) ? a.W[e0 + 32 + lane] : (T)0;
+            }
+            // raw weights in ORIGINAL order go through shared memory so that they can be fetched by idx
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                T w = __shfl_sync(FSW_FULL, (j < 32) ? w0 : w1, j & 31);
+                sm_c[j * 32 + lane] = (j < n) ? w : (T)0;
+            }
+            __syncwarp();
+            double Craw = 0.0;
+            T sPD = (T)0, sPdD = (T)0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                if (j < n_eff) {
+                    const int id = idx[j];
+                    const double wr = (id >= n) ? padw : (double)sm_c[id * 32 + lane];
+                    Craw += wr;
+                    const double wn = wr * invS;
+                    const double two_c_minus_w = 2.0 * Craw * invS - wn;
+                    const T r = Num<T>::reduce(xid * two_c_minus_w);
+                    const T c = Num<T>::cospi_(r);
+                    const T wnf = (T)wn;
+                    const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                    const T D = aj * c;
+                    sm_val[id * 32 + lane] = Gk * D;
+                    if (NEED_DXI) {
+                        const T sn = Num<T>::sinpi_(r);
+                        const T dD = (T)2 * wnf * wnf * fsw_dsinc(xi * wnf) * c - aj * (T)M_PI * (T)two_c_minus_w * sn;
+                        sPD = fma(key[j], D, sPD);
+                        sPdD = fma(key[j], dD, sPdD);
+                    }
+                }
+            }
+            if (NEED_DXI) dxi_acc += (double)(gk * (sPD + ((T)1 + xi) * sPdD));
+        }
+        __syncwarp();
+        // ---- coalesced scatter in ORIGINAL element order ----
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            int64_t row = e0 + i;
+            if (a.col) row = __shfl_sync(FSW_FULL, (i < 32) ? c0 : c1, i & 31);
+            if (i < n && act) {
+                const T v = sm_val[i * 32 + lane];
+                if (a.col)
+                    atomicAdd(dXp + row * a.ldp + k, v);
+                else
+                    dXp[row * a.ldp + k] = v;
+                if (dEp) dEp[(e0 + i) * a.ldp + k] = v;
+            }
+        }
+        __syncwarp();
+    }
+    if (NEED_DXI && act) atomicAdd(dfreqs + k, dxi_acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Generic path: block-wide bitonic network, rows = elements, lanes = slices.
+// ---------------------------------------------------------------------------------------------------
+template <typename KT, typename PT, bool HAS_PAY>
+__device__ __forceinline__ void fsw_block_bitonic(KT* keys, PT* pay, int n_pad) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = warp; t < (n_pad >> 1); t += nw) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool asc = ((i & k) == 0);
+                KT x = keys[i * 32 + lane], y = keys[l * 32 + lane];
+                if ((x > y) == asc) {
+                    keys[i * 32 + lane] = y;
+                    keys[l * 32 + lane] = x;
+                    if (HAS_PAY) {
+                        PT px = pay[i * 32 + lane], py = pay[l * 32 + lane];
+                        pay[i * 32 + lane] = py;
+                        pay[l * 32 + lane] = px;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int fsw_next_pow2(int n) {
+    int p = 2;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// forward.  MODE 0: uniform weights (keys only).  MODE 1: general (payload = raw weight, -1 = pad point)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) fsw_fwd_generic_kernel(SegArgs<T> a, int seg_lo, int nchunks, int64_t ntiles,
+                                                              T* __restrict__ out, int64_t ld_out, int64_t out_col0,
+                                                              const T* __restrict__ bias, int cap_rows,
+                                                              unsigned char* gscratch) {
+    extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const size_t tile_elems = (size_t)cap_rows * 32;
+    unsigned char* base = gscratch ? gscratch + (size_t)blockIdx.x * tile_elems * sizeof(T) * (MODE == 1 ? 2 : 1) : fsw_smem_raw;
+    T* keys = reinterpret_cast<T*>(base);
+    T* pay = keys + tile_elems;
+    (void)pay;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int q = seg_lo + (int)(tile / nchunks);
+        const int chunk = (int)(tile % nchunks);
+        const int s = a.order ? a.order[q] : q;
+        int64_t e0;
+        int n;
+        fsw_seg_range(a, s, e0, n);
+        const int n_eff = (MODE == 0) ? n : (a.info[s] & FSW_INFO_NMASK);
+        const bool padded = n_eff > n;
+        const int n_pad = fsw_next_pow2(n_eff);
+        const int k = chunk * 32 + lane;
+        const bool act = k < a.K;
+        const int kk = act ? k : a.K - 1;
+        const T xi = fsw_ldg(a.freqs + kk);
+        const double xid = (double)xi;
+
+        for (int r = warp; r < n_pad; r += nw) {
+            T v = Num<T>::big();
+            T w = (T)0;
+            if (r < n) {
+                const int64_t row = a.col ? (int64_t)a.col[e0 + r] : e0 + r;
+                v = fsw_ldg(a.Xp + row * a.ldp + kk);
+                if (a.Ep) v += fsw_ldg(a.Ep + (e0 + r) * a.ldp + kk);
+                if (MODE == 1) w = a.W ? a.W[e0 + r] : (T)1;
+            } else if (MODE == 1 && padded && r == n) {
+                v = (T)0;
+                w = (T)-1;
+            }
+            keys[r * 32 + lane] = v;
+            if (MODE == 1) pay[r * 32 + lane] = w;
+        }
+        __syncthreads();
+        fsw_block_bitonic<T, T, MODE == 1>(keys, pay, n_pad);
+
+        const int rpw = (n_eff + nw - 1) / nw;
+        const int r0 = warp * rpw;
+        const int r1 = (r0 + rpw < n_eff) ? r0 + rpw : n_eff;
+        double acc = 0.0;
+        if (MODE == 0) {
+            const double u = xid / (double)n;
+            for (int r = r0; r < r1; ++r) {
+                const T c = Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * r + 1)));
+                acc += (double)(keys[r * 32 + lane] * c);
+            }
+            const T wn = (T)(1.0 / (double)n);
+            acc *= (double)(((T)1 + xi) * (T)2 * wn * fsw_sinc((T)u));
+        } else {
+            const double Ts = a.mass[s];
+            const double invS = 1.0 / fmax(Ts, a.thresh);
+            const double padw = a.thresh - Ts;
+            double part = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const T w = pay[r * 32 + lane];
+                part += (w < (T)0) ? padw : (double)w;
+            }
+            red[warp][lane] = part;
+            __syncthreads();
+            double Craw = 0.0;
+            for (int w2 = 0; w2 < warp; ++w2) Craw += red[w2][lane];
+            __syncthreads();
+            for (int r = r0; r < r1; ++r) {
+                const T w = pay[r * 32 + lane];
+                const double wr = (w < (T)0) ? padw : (double)w;
+                Craw += wr;
+                const double wn = wr * invS;
+                const T c = Num<T>::cospi_(Num<T>::reduce(xid * (2.0 * Craw * invS - wn)));
+                const T wnf = (T)wn;
+                const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                acc += (double)(keys[r * 32 + lane] * (aj * c));
+            }
+            acc *= (double)((T)1 + xi);
+        }
+        red[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0.0;
+            for (int w2 = 0; w2 < nw; ++w2) tot += red[w2][lane];
+            if (act) out[(int64_t)s * ld_out + out_col0 + k] = (T)tot + ((bias != nullptr) ? bias[k] : (T)0);
+        }
+        __syncthreads();
+    }
+}
+
+// backward generic.  Tiles: keys (T) and idx (int32).  After the key sort and the evaluation the key
+// tile holds dL/dp in SORTED order; a second network sorts by idx to restore the ORIGINAL order so
+// that the scatter to dXp is one coalesced row per element.
+template <typename T, bool UNIFORM, bool NEED_DXI>
+__global__ void __launch_bounds__(256) fsw_bwd_generic_kernel(SegArgs<T> a, int seg_lo, int nchunks, int64_t ntiles,
+                                                              const T* __restrict__ g, int64_t ld_g, int64_t g_col0,
+                                                              T* __restrict__ dXp, T* __restrict__ dEp,
+                                                              double* __restrict__ dfreqs, int cap_rows,
+                                                              unsigned char* gscratch) {
+    extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const size_t tile_elems = (size_t)cap_rows * 32;
+    unsigned char* base = gscratch ? gscratch + (size_t)blockIdx.x * tile_elems * (sizeof(T) + sizeof(int)) : fsw_smem_raw;
+    T* keys = reinterpret_cast<T*>(base);
+    int* idx = reinterpret_cast<int*>(keys + tile_elems);
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int q = seg_lo + (int)(tile / nchunks);
+        const int chunk = (int)(tile % nchunks);
+        const int s = a.order ? a.order[q] : q;
+        int64_t e0;
+        int n;
+        fsw_seg_range(a, s, e0, n);
+        const int n_eff = UNIFORM ? n : (a.info[s] & FSW_INFO_NMASK);
+        const bool padded = n_eff > n;
+        const int n_pad = fsw_next_pow2(n_eff);
+        const int k = chunk * 32 + lane;
+        const bool act = k < a.K;
+        const int kk = act ? k : a.K - 1;
+        const T xi = fsw_ldg(a.freqs + kk);
+        const double xid = (double)xi;
+        const T gk = act ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
+        const T Gk = gk * ((T)1 + xi);
+
+        for (int r = warp; r < n_pad; r += nw) {
+            T v = Num<T>::big();
+            if (r < n) {
+                const int64_t row = a.col ? (int64_t)a.col[e0 + r] : e0 + r;
+                v = fsw_ldg(a.Xp + row * a.ldp + kk);
+                if (a.Ep) v += fsw_ldg(a.Ep + (e0 + r) * a.ldp + kk);
+            } else if (!UNIFORM && padded && r == n) {
+                v = (T)0;
+            }
+            keys[r * 32 + lane] = v;
+            idx[r * 32 + lane] = r;
+        }
+        __syncthreads();
+        fsw_block_bitonic<T, int, true>(keys, idx, n_pad);
+
+        const int rpw = (n_eff + nw - 1) / nw;
+        const int r0 = warp * rpw;
+        const int r1 = (r0 + rpw < n_eff) ? r0 + rpw : n_eff;
+        double dxi_local = 0.0;
+        if (UNIFORM) {
+            const double u = xid / (double)n;
+            const T wn = (T)(1.0 / (double)n);
+            const T A0 = (T)2 * wn * fsw_sinc((T)u);
+            const T A0p = NEED_DXI ? (T)2 * wn * wn * fsw_dsinc((T)u) : (T)0;
+            double Sc = 0.0, Ss = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const T rr = Num<T>::reduce(u * (double)(2 * r + 1));
+                const T c = Num<T>::cospi_(rr);
+                const T p = keys[r * 32 + lane];
+                keys[r * 32 + lane] = Gk * A0 * c;
+                if (NEED_DXI) {
+                    Sc += (double)(p * c);
+                    Ss += (double)(p * ((T)M_PI * wn * (T)(2 * r + 1) * Num<T>::sinpi_(rr)));
+                }
+            }
+            if (NEED_DXI)
+                dxi_local = (double)gk * ((double)A0 * Sc + (1.0 + xid) * ((double)A0p * Sc - (double)A0 * Ss));
+        } else {
+            const double Ts = a.mass[s];
+            const double invS = 1.0 / fmax(Ts, a.thresh);
+            const double padw = a.thresh - Ts;
+            double part = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const int id = idx[r * 32 + lane];
+                part += (id >= n) ? padw : (a.W ? (double)a.W[e0 + id] : 1.0);
+            }
+            red[warp][lane] = part;
+            __syncthreads();
+            double Craw = 0.0;
+            for (int w2 = 0; w2 < warp; ++w2) Craw += red[w2][lane];
+            __syncthreads();
+            double sPD = 0.0, sPdD = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const int id = idx[r * 32 + lane];
+                const double wr = (id >= n) ? padw : (a.W ? (double)a.W[e0 + id] : 1.0);
+                Craw += wr;
+                const double wn = wr * invS;
+                const double tcw = 2.0 * Craw * invS - wn;
+                const T rr = Num<T>::reduce(xid * tcw);
+                const T c = Num<T>::cospi_(rr);
+                const T wnf = (T)wn;
+                const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                const T D = aj * c;
+                const T p = keys[r * 32 + lane];
+                keys[r * 32 + lane] = Gk * D;
+                if (NEED_DXI) {
+                    const T sn = Num<T>::sinpi_(rr);
+                    const T dD = (T)2 * wnf * wnf * fsw_dsinc(xi * wnf) * c - aj * (T)M_PI * (T)tcw * sn;
+                    sPD += (double)(p * D);
+                    sPdD += (double)(p * dD);
+                }
+            }
+            if (NEED_DXI) dxi_local = (double)gk * (sPD + (1.0 + xid) * sPdD);
+        }
+        if (NEED_DXI) {
+            red[warp][lane] = dxi_local;
+            __syncthreads();
+            if (warp == 0 && act) {
+                double tot = 0.0;
+                for (int w2 = 0; w2 < nw; ++w2) tot += red[w2][lane];
+                atomicAdd(dfreqs + k, tot);
+            }
+        }
+        // rows >= n_eff keep idx >= n_eff (they were sorted to the end with +big keys); give them 0 gradient
+        for (int r = n_eff + warp; r < n_pad; r += nw) keys[r * 32 + lane] = (T)0;
+        __syncthreads();
+        fsw_block_bitonic<int, T, true>(idx, keys, n_pad);
+        for (int r = warp; r < n; r += nw) {
+            if (act) {
+                const T v = keys[r * 32 + lane];
+                if (a.col)
+                    atomicAdd(dXp + (int64_t)a.col[e0 + r] * a.ldp + k, v);
+                else
+                    dXp[(e0 + r) * a.ldp + k] = v;
+                if (dEp) dEp[(e0 + r) * a.ldp + k] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host dispatch
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+const int kSmemBudget = 200 * 1024;  // dynamic shared memory we are willing to ask for per CTA
+
+struct ClassRange {
+    int lo, hi;  // bucket range [lo, hi]
+    int np;
+};
+const ClassRange kSmall[] = {{0, 4, 4}, {5, 8, 8}, {9, 16, 16}, {17, 32, 32}, {33, 64, 64}};
+
+template <typename T>
+int max_small_np() {
+    return sizeof(T) == 4 ? 64 : 32;
+}
+
+int bucket_cap(int b, int64_t max_n_eff) {  // upper bound of n_eff in size bucket b (65..71)
+    static const int caps[] = {128, 256, 512, 1024, 2048, 4096};
+    if (b <= 64) return 64;
+    if (b <= 70) return caps[b - 65];
+    int64_t c = 8192;
+    while (c < max_n_eff) c <<= 1;
+    return (int)c;
+}
+
+int pick_G(int64_t cnt, int nchunks) {
+    int64_t g = cnt * nchunks / (148 * 24);
+    if (g < 1) g = 1;
+    if (g > 32) g = 32;
+    return (int)g;
+}
+
+template <typename T, int NP, bool UNIFORM>
+int launch_fwd_small(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
+                     cudaStream_t st) {
+    const int nchunks = (a.K + 31) / 32;
+    const int G = pick_G(hi - lo, nchunks);
+    const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
+    const int64_t blocks = fsw_cdiv(warps, 4);
+    fsw_fwd_small_kernel<T, NP, UNIFORM><<<(unsigned)blocks, 128, 0, st>>>(a, lo, hi, G, nchunks, out, ld_out, out_col0, bias);
+    FSW_CHECK_LAUNCH("fsw_fwd_small_kernel");
+    return FSW_OK;
+}
+
+template <typename T, bool UNIFORM>
+int dispatch_fwd_small(const SegArgs<T>& a, int np, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0,
+                       const T* bias, cudaStream_t st) {
+    switch (np) {
+        case 4: return launch_fwd_small<T, 4, UNIFORM>(a, lo, hi, out, ld_out, out_col0, bias, st);
+        case 8: return launch_fwd_small<T, 8, UNIFORM>(a, lo, hi, out, ld_out, out_col0, bias, st);
+        case 16: return launch_fwd_small<T, 16, UNIFORM>(a, lo, hi, out, ld_out, out_col0, bias, st);
+        case 32: return launch_fwd_small<T, 32, UNIFORM>(a, lo, hi, out, ld_out, out_col0, bias, st);
+        case 64:
+            if constexpr (sizeof(T) == 4) return launch_fwd_small<T, 64, UNIFORM>(a, lo, hi, out, ld_out, out_col0, bias, st);
+            break;
+    }
+    return fsw_fail(FSW_ERR_INVALID, "bad small class %d", np);
+}
+
+template <typename T, int NP, bool UNIFORM, bool NEED_DXI>
+int launch_bwd_small(const SegArgs<T>& a, int lo, int hi, const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp,
+                     double* dfreqs, cudaStream_t st) {
+    const int nchunks = (a.K + 31) / 32;
+    const int G = pick_G(hi - lo, nchunks);
+    const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
+    const int64_t blocks = fsw_cdiv(warps, 4);
+    const size_t smem = (size_t)4 * 3 * NP * 32 * sizeof(T);
+    auto kern = fsw_bwd_small_kernel<T, NP, UNIFORM, NEED_DXI>;
+    if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, 128, smem, st>>>(a, lo, hi, G, nchunks, g, ld_g, g_col0, dXp, dEp, dfreqs);
+    FSW_CHECK_LAUNCH("fsw_bwd_small_kernel");
+    return FSW_OK;
+}
+
+template <typename T, bool UNIFORM, bool NEED_DXI>
+int dispatch_bwd_small(const SegArgs<T>& a, int np, int lo, int hi, const T* g, int64_t ld_g, int64_t g_col0, T* dXp,
+                       T* dEp, double* dfreqs, cudaStream_t st) {
+    switch (np) {
+        case 4: return launch_bwd_small<T, 4, UNIFORM, NEED_DXI>(a, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+        case 8: return launch_bwd_small<T, 8, UNIFORM, NEED_DXI>(a, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+        case 16: return launch_bwd_small<T, 16, UNIFORM, NEED_DXI>(a, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+        case 32: return launch_bwd_small<T, 32, UNIFORM, NEED_DXI>(a, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+        case 64:
+            if constexpr (sizeof(T) == 4) return launch_bwd_small<T, 64, UNIFORM, NEED_DXI>(a, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+            break;
+    }
+    return fsw_fail(FSW_ERR_INVALID, "bad small class %d", np);
+}
+
+// number of resident CTAs we use for the persistent generic kernels
+const int kGenericGrid = 148 * 2;
+
+template <typename T>
+size_t generic_tile_bytes(int cap_rows, bool backward, bool uniform) {
+    const size_t per = backward ? (sizeof(T) + sizeof(int)) : (uniform ? sizeof(T) : 2 * sizeof(T));
+    return (size_t)cap_rows * 32 * per;
+}
+
+template <typename T>
+SegArgs<T> make_args(const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr, int64_t n_fixed,
+                     const int32_t* col, const void* W, const double* mass, const int32_t* info, const int32_t* order,
+                     const void* freqs, int64_t K, double thresh) {
+    SegArgs<T> a;
+    a.Xp = (const T*)Xp;
+    a.Ep = (const T*)Ep;
+    a.rowptr = rowptr;
+    a.col = col;
+    a.W = (const T*)W;
+    a.mass = mass;
+    a.info = info;
+    a.order = order;
+    a.freqs = (const T*)freqs;
+    a.ldp = ldp;
+    a.n_fixed = n_fixed;
+    a.K = (int)K;
+    a.thresh = thresh;
+    return a;
+}
+
+template <typename T>
+int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
+                    int64_t max_n_eff, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    const int nchunks = (a.K + 31) / 32;
+    const int msn = max_small_np<T>();
+    for (int kind = 0; kind < 2; ++kind) {
+        const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
+        for (const ClassRange& c : kSmall) {
+            if (c.np > msn) continue;
+            const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
+            if (hi <= lo) continue;
+            int rc = kind == 0 ? dispatch_fwd_small<T, true>(a, c.np, lo, hi, out, ld_out, out_col0, bias, st)
+                               : dispatch_fwd_small<T, false>(a, c.np, lo, hi, out, ld_out, out_col0, bias, st);
+            if (rc) return rc;
+        }
+        // generic buckets; for fp64 the exact buckets 33..64 are handled here too (cap 64)
+        for (int b = msn + 1; b < FSW_PLAN_BUCKETS_PER_KIND; ++b) {
+            int b_hi = b;
+            if (b <= 64) b_hi = 64;  // fold all exact buckets above the small limit into one launch
+            const int lo = bo[base + b], hi = bo[base + b_hi + 1];
+            const int cap = bucket_cap(b_hi, max_n_eff);
+            b = b_hi;
+            if (hi <= lo) continue;
+            const int64_t ntiles = (int64_t)(hi - lo) * nchunks;
+            const size_t tb = generic_tile_bytes<T>(cap, false, kind == 0);
+            unsigned grid = (unsigned)(ntiles < kGenericGrid ? ntiles : kGenericGrid);
+            unsigned char* gs = nullptr;
+            size_t smem = tb;
+            if (tb > (size_t)kSmemBudget) {
+                if ((size_t)grid * tb > scratch_bytes) {
+                    grid = (unsigned)(scratch_bytes / tb);
+                    if (grid == 0) return fsw_fail(FSW_ERR_WORKSPACE, "embed scratch too small: need >= %zu bytes", tb);
+                }
+                gs = (unsigned char*)scratch;
+                smem = 0;
+            }
+            if (kind == 0) {
+                auto kern = fsw_fwd_generic_kernel<T, 0>;
+                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, out, ld_out, out_col0, bias, cap, gs);
+            } else {
+                auto kern = fsw_fwd_generic_kernel<T, 1>;
+                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, out, ld_out, out_col0, bias, cap, gs);
+            }
+            FSW_CHECK_LAUNCH("fsw_fwd_generic_kernel");
+        }
+    }
+    return FSW_OK;
+}
+
+template <typename T, bool NEED_DXI>
+int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp,
+                     double* dfreqs, int64_t max_n_eff, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    const int nchunks = (a.K + 31) / 32;
+    const int msn = max_small_np<T>();
+    for (int kind = 0; kind < 2; ++kind) {
+        const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
+        for (const ClassRange& c : kSmall) {
+            if (c.np > msn) continue;
+            const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
+            if (hi <= lo) continue;
+            int rc = kind == 0 ? dispatch_bwd_small<T, true, NEED_DXI>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
+                               : dispatch_bwd_small<T, false, NEED_DXI>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+            if (rc) return rc;
+        }
+        for (int b = msn + 1; b < FSW_PLAN_BUCKETS_PER_KIND; ++b) {
+            int b_hi = b;
+            if (b <= 64) b_hi = 64;
+            const int lo = bo[base + b], hi = bo[base + b_hi + 1];
+            const int cap = bucket_cap(b_hi, max_n_eff);
+            b = b_hi;
+            if (hi <= lo) continue;
+            const int64_t ntiles = (int64_t)(hi - lo) * nchunks;
+            const size_t tb = generic_tile_bytes<T>(cap, true, kind == 0);
+            unsigned grid = (unsigned)(ntiles < kGenericGrid ? ntiles : kGenericGrid);
+            unsigned char* gs = nullptr;
+            size_t smem = tb;
+            if (tb > (size_t)kSmemBudget) {
+                if ((size_t)grid * tb > scratch_bytes) {
+                    grid = (unsigned)(scratch_bytes / tb);
+                    if (grid == 0) return fsw_fail(FSW_ERR_WORKSPACE, "embed scratch too small: need >= %zu bytes", tb);
+                }
+                gs = (unsigned char*)scratch;
+                smem = 0;
+            }
+            if (kind == 0) {
+                auto kern = fsw_bwd_generic_kernel<T, true, NEED_DXI>;
+                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);
+            } else {
+                auto kern = fsw_bwd_generic_kernel<T, false, NEED_DXI>;
+                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);
+            }
+            FSW_CHECK_LAUNCH("fsw_bwd_generic_kernel");
+        }
+    }
+    return FSW_OK;
+}
+
+}  // namespace
+
+extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t K, int64_t max_n_eff, int backward) {
+    // worst case over the non-empty generic buckets of grid * tile_bytes, only for tiles beyond the smem budget
+    size_t need = 0;
+    const size_t es = dtype == FSW_F64 ? 8 : 4;
+    const int msn = dtype == FSW_F64 ? 32 : 64;
+    const int nchunks = (int)((K + 31) / 32);
+    for (int kind = 0; kind < 2; ++kind) {
+        const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
+        for (int b = msn + 1; b < FSW_PLAN_BUCKETS_PER_KIND; ++b) {
+            const int cnt = bo[base + b + 1] - bo[base + b];
+            if (cnt <= 0) continue;
+            const int cap = bucket_cap(b, max_n_eff);
+            const size_t per = backward ? (es + 4) : (kind == 0 ? es : 2 * es);
+            const size_t tb = (size_t)cap * 32 * per;
+            if (tb <= (size_t)kSmemBudget) continue;
+            int64_t ntiles = (int64_t)cnt * nchunks;
+            size_t grid = (size_t)(ntiles < kGenericGrid ? ntiles : kGenericGrid);
+            if (grid * tb > need) need = grid * tb;
+        }
+    }
+    return need;
+}
+
+extern "C" int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,
+                                 int64_t n_fixed, const int32_t* col, const void* W, const double* mass,
+                                 const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host,
+                                 int64_t S, int64_t K, const void* freqs, double thresh, void* out, int64_t ld_out,
+                                 int64_t out_col0, const void* bias, int64_t max_n_eff, void* scratch,
+                                 size_t scratch_bytes, void* stream) {
+    if (S == 0 || K == 0) return FSW_OK;
+    if (!Xp || !mass || !info || !bucket_offsets_host || !freqs || !out)
+        return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: null argument");
+    if (!rowptr && n_fixed <= 0) return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: rowptr == NULL needs n_fixed > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FSW_F32) {
+        auto a = make_args<float>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
+        return embed_forward_t<float>(a, bucket_offsets_host, (float*)out, ld_out, out_col0, (const float*)bias, max_n_eff, scratch, scratch_bytes, st);
+    } else if (dtype == FSW_F64) {
+        auto a = make_args<double>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
+        return embed_forward_t<double>(a, bucket_offsets_host, (double*)out, ld_out, out_col0, (const double*)bias, max_n_eff, scratch, scratch_bytes, st);
+    }
+    return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: dtype %d", dtype);
+}
+
+extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,
+                                  int64_t n_fixed, const int32_t* col, const void* W, const double* mass,
+                                  const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host,
+                                  int64_t S, int64_t K, const void* freqs, double thresh, const void* g, int64_t ld_g,
+                                  int64_t g_col0, void* dXp, void* dEp, double* dfreqs_acc, void* dW,
+                                  int64_t max_n_eff, void* scratch, size_t scratch_bytes, void* stream) {
+    if (S == 0 || K == 0) return FSW_OK;
+    if (dW != nullptr)
+        return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_embed_backward: gradient w.r.t. the weights W is not implemented");
+    if (!Xp || !mass || !info || !bucket_offsets_host || !freqs || !g || !dXp)
+        return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: null argument");
+    if (!rowptr && n_fixed <= 0) return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: rowptr == NULL needs n_fixed > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FSW_F32) {
+        auto a = make_args<float>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
+        if (dfreqs_acc)
+            return embed_backward_t<float, true>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, st);
+        return embed_backward_t<float, false>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, st);
+    } else if (dtype == FSW_F64) {
+        auto a = make_args<double>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
+        if (dfreqs_acc)
+            return embed_backward_t<double, true>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, st);
+        return embed_backward_t<double, false>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, st);
+    }
+    return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: dtype %d", dtype);
+}

@@ -1,0 +1,370 @@
+// K0: graph preparation (edge list -> destination-major CSR) and the segment plan.
+//
+// Replaces FSW_conv.edge_index_to_adj (fsw_conv.py:384-447: sparse_coo_tensor + coalesce +
+// get_slice_info + sum_sparseToDense), sp.get_slice_info (fsw_embedding.py:2586-2678) and the
+// total-mass prologue of FSW_embedding.forward (fsw_embedding.py:778-829).
+#include "fsw_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// int32 exclusive scan (three small kernels; N+1 <= 2^31)
+// ---------------------------------------------------------------------------------------------------
+const int SCAN_BLOCK = 1024;  // elements per block (256 threads x 4)
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// block-level exclusive scan of 1024 ints held 4 per thread; returns the block total
+__device__ __forceinline__ int block_excl_scan4(int (&x)[4], int* smem_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int tsum = x[0] + x[1] + x[2] + x[3];
+    int incl = warp_incl_scan(tsum, lane);
+    if (lane == 31) smem_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < (int)(blockDim.x >> 5)) ? smem_warp[lane] : 0;
+        int wi = warp_incl_scan(w, lane);
+        smem_warp[lane] = wi - w;       // exclusive prefix of warps
+        if (lane == 31) smem_warp[32] = wi;  // total
+    }
+    __syncthreads();
+    int run = smem_warp[warp] + incl - tsum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int t = x[i];
+        x[i] = run;
+        run += t;
+    }
+    return smem_warp[32];
+}
+
+__global__ void __launch_bounds__(256) scan_block_sums(const int* __restrict__ in, int64_t n, int* __restrict__ block_sums) {
+    __shared__ int sw[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+    int x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (base + i < n) ? in[base + i] : 0;
+    int tot = block_excl_scan4(x, sw);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) scan_of_block_sums(int* __restrict__ block_sums, int nblocks) {
+    // single block, sequential over chunks of 1024
+    __shared__ int sw[33];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nblocks; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = (i < nblocks) ? block_sums[i] : 0;
+        int incl = warp_incl_scan(v, lane);
+        if (lane == 31) sw[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = sw[lane];
+            int wi = warp_incl_scan(w, lane);
+            sw[lane] = wi - w;
+            if (lane == 31) sw[32] = wi;
+        }
+        __syncthreads();
+        int excl = carry + sw[warp] + incl - v;
+        if (i < nblocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sw[32];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) scan_apply(const int* __restrict__ in, int64_t n, const int* __restrict__ block_offs,
+                                                  int* __restrict__ out) {
+    __shared__ int sw[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+    int x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (base + i < n) ? in[base + i] : 0;
+    block_excl_scan4(x, sw);
+    const int off = block_offs[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (base + i < n) out[base + i] = x[i] + off;
+}
+
+int exclusive_scan_i32(const int* in, int64_t n, int* out, int* block_tmp, cudaStream_t st) {
+    const int nblocks = (int)fsw_cdiv(n, SCAN_BLOCK);
+    scan_block_sums<<<nblocks, 256, 0, st>>>(in, n, block_tmp);
+    FSW_CHECK_LAUNCH("scan_block_sums");
+    scan_of_block_sums<<<1, 1024, 0, st>>>(block_tmp, nblocks);
+    FSW_CHECK_LAUNCH("scan_of_block_sums");
+    scan_apply<<<nblocks, 256, 0, st>>>(in, n, block_tmp, out);
+    FSW_CHECK_LAUNCH("scan_apply");
+    return FSW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CSR from edge_index
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) csr_count(const int64_t* __restrict__ dst, int64_t E, int64_t N, int self_loops,
+                                                 int* __restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E) {
+        const int64_t d = dst[i];
+        if (d >= 0 && d < N) atomicAdd(counts + d, 1);
+    } else if (self_loops && i - E < N) {
+        atomicAdd(counts + (i - E), 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) csr_fill(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                                                int64_t N, int self_loops, int* __restrict__ cursor, int32_t* __restrict__ col,
+                                                int32_t* __restrict__ eid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E) {
+        const int64_t d = dst[i];
+        if (d >= 0 && d < N) {
+            const int pos = atomicAdd(cursor + d, 1);
+            col[pos] = (int32_t)src[i];
+            if (eid) eid[pos] = (int32_t)i;
+        }
+    } else if (self_loops && i - E < N) {
+        const int64_t v = i - E;
+        const int pos = atomicAdd(cursor + v, 1);
+        col[pos] = (int32_t)v;
+        if (eid) eid[pos] = (int32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(256) rowptr_from_rows(const int64_t* __restrict__ rows, int64_t nnz, int64_t S,
+                                                        int32_t* __restrict__ rowptr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (nnz == 0) {
+        if (i <= S) rowptr[i] = 0;
+        return;
+    }
+    if (i < nnz) {
+        const int64_t r = rows[i];
+        const int64_t prev = (i > 0) ? rows[i - 1] : -1;
+        for (int64_t x = prev + 1; x <= r; ++x) rowptr[x] = (int32_t)i;
+        if (i == nnz - 1)
+            for (int64_t x = r + 1; x <= S; ++x) rowptr[x] = (int32_t)nnz;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) edge_weights_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                           const int32_t* __restrict__ eid, int64_t N, int64_t E, int self_loops,
+                                                           double slw, int gcn, T* __restrict__ deg, T* __restrict__ w,
+                                                           int phase) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (phase == 0) {
+        if (i < N) {
+            const int cnt = rowptr[i + 1] - rowptr[i];
+            const double d = self_loops ? (double)(cnt - 1) + slw : (double)cnt;
+            deg[i] = (T)d;
+        }
+        return;
+    }
+    // phase 1: one thread per destination row (rows are short); writes w for its slots
+    if (i < N && w) {
+        const int lo = rowptr[i], hi = rowptr[i + 1];
+        const double dd = (double)deg[i];
+        for (int p = lo; p < hi; ++p) {
+            const bool is_loop = self_loops && eid[p] >= E;
+            double b = is_loop ? slw : 1.0;
+            if (gcn) b = b / sqrt(dd) / sqrt((double)deg[col[p]]);
+            w[p] = (T)b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Segment plan
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) plan_stats(const int32_t* __restrict__ rowptr, int64_t n_fixed, const T* __restrict__ W,
+                                                  int64_t S, double thresh, double* __restrict__ mass, int32_t* __restrict__ info,
+                                                  int* __restrict__ hist /*[BUCKETS+1] last = max n_eff*/) {
+    __shared__ int sh[FSW_PLAN_BUCKETS + 1];
+    for (int i = threadIdx.x; i <= FSW_PLAN_BUCKETS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s < S) {
+        int64_t e0;
+        int n;
+        if (rowptr) {
+            e0 = rowptr[s];
+            n = rowptr[s + 1] - (int)e0;
+        } else {
+            e0 = s * n_fixed;
+            n = (int)n_fixed;
+        }
+        double m = 0.0;
+        bool uni = true;
+        if (W) {
+            const T w_first = (n > 0) ? W[e0] : (T)0;
+            for (int j = lane; j < n; j += 32) {
+                const T w = W[e0 + j];
+                m += (double)w;
+                uni = uni && (w == w_first);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) m += __shfl_xor_sync(0xffffffffu, m, d);
+            uni = __all_sync(0xffffffffu, uni);
+        } else {
+            m = (double)n;
+        }
+        const bool deficient = m < thresh;
+        const int n_eff = n + (deficient ? 1 : 0);
+        const bool uniform = uni && !deficient && n > 0;
+        if (lane == 0) {
+            mass[s] = m;
+            info[s] = n_eff | (uniform ? FSW_INFO_UNIFORM : 0);
+            atomicAdd(&sh[(uniform ? 0 : FSW_PLAN_BUCKETS_PER_KIND) + fsw_size_bucket(n_eff)], 1);
+            atomicMax(&sh[FSW_PLAN_BUCKETS], n_eff);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FSW_PLAN_BUCKETS; i += blockDim.x)
+        if (sh[i]) atomicAdd(hist + i, sh[i]);
+    if (threadIdx.x == 0 && sh[FSW_PLAN_BUCKETS]) atomicMax(hist + FSW_PLAN_BUCKETS, sh[FSW_PLAN_BUCKETS]);
+}
+
+__global__ void plan_scan(const int* __restrict__ hist, int32_t* __restrict__ offsets, int* __restrict__ cursor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < FSW_PLAN_BUCKETS; ++i) {
+            offsets[i] = run;
+            cursor[i] = run;
+            run += hist[i];
+        }
+        offsets[FSW_PLAN_BUCKETS] = run;
+        offsets[FSW_PLAN_BUCKETS + 1] = hist[FSW_PLAN_BUCKETS];  // max n_eff
+    }
+}
+
+// Stable-enough scatter: a block reserves one contiguous range per bucket, then hands out slots in
+// thread order, so the order inside a bucket follows the segment index up to block scheduling.
+__global__ void __launch_bounds__(256) plan_scatter(const int32_t* __restrict__ info, int64_t S, int* __restrict__ cursor,
+                                                    int32_t* __restrict__ order) {
+    __shared__ int cnt[FSW_PLAN_BUCKETS];
+    __shared__ int base[FSW_PLAN_BUCKETS];
+    for (int i = threadIdx.x; i < FSW_PLAN_BUCKETS; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int b = -1, local = 0;
+    if (s < S) {
+        const int w = info[s];
+        b = ((w & FSW_INFO_UNIFORM) ? 0 : FSW_PLAN_BUCKETS_PER_KIND) + fsw_size_bucket(w & FSW_INFO_NMASK);
+        local = atomicAdd(&cnt[b], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FSW_PLAN_BUCKETS; i += blockDim.x)
+        if (cnt[i]) base[i] = atomicAdd(cursor + i, cnt[i]);
+    __syncthreads();
+    if (b >= 0) order[base[b] + local] = (int32_t)s;
+}
+
+}  // namespace
+
+extern "C" size_t fsw_csr_workspace_bytes(int64_t N) {
+    // counts [N+1] + cursor [N+1] + block sums
+    return (size_t)(2 * (N + 1) + fsw_cdiv(N + 1, SCAN_BLOCK) + 64) * sizeof(int);
+}
+
+extern "C" int fsw_csr_from_edge_index(const int64_t* edge_index, int64_t E, int64_t N, int self_loops, int32_t* rowptr,
+                                       int32_t* col, int32_t* eid, void* workspace, size_t workspace_bytes, void* stream) {
+    if (N < 0 || E < 0) return fsw_fail(FSW_ERR_INVALID, "fsw_csr_from_edge_index: negative size");
+    if (E + (self_loops ? N : 0) >= (int64_t)INT32_MAX) return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_csr_from_edge_index: more than 2^31 elements");
+    if (workspace_bytes < fsw_csr_workspace_bytes(N)) return fsw_fail(FSW_ERR_WORKSPACE, "fsw_csr_from_edge_index: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* counts = (int*)workspace;
+    int* cursor = counts + (N + 1);
+    int* btmp = cursor + (N + 1);
+    FSW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(N + 1) * sizeof(int), st));
+    const int64_t tot = E + (self_loops ? N : 0);
+    const int64_t* src = edge_index;
+    const int64_t* dst = edge_index + E;
+    if (tot > 0) {
+        csr_count<<<(unsigned)fsw_cdiv(tot, 256), 256, 0, st>>>(dst, E, N, self_loops, counts);
+        FSW_CHECK_LAUNCH("csr_count");
+    }
+    int rc = exclusive_scan_i32(counts, N + 1, rowptr, btmp, st);
+    if (rc) return rc;
+    FSW_CUDA(cudaMemcpyAsync(cursor, rowptr, (size_t)(N + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (tot > 0) {
+        csr_fill<<<(unsigned)fsw_cdiv(tot, 256), 256, 0, st>>>(src, dst, E, N, self_loops, cursor, col, eid);
+        FSW_CHECK_LAUNCH("csr_fill");
+    }
+    return FSW_OK;
+}
+
+extern "C" int fsw_rowptr_from_sorted_rows(const int64_t* rows, int64_t nnz, int64_t S, int32_t* rowptr, void* stream) {
+    if (nnz >= (int64_t)INT32_MAX) return fsw_fail(FSW_ERR_UNSUPPORTED, "more than 2^31 nonzeros");
+    const int64_t work = nnz > 0 ? nnz : S + 1;
+    rowptr_from_rows<<<(unsigned)fsw_cdiv(work, 256), 256, 0, (cudaStream_t)stream>>>(rows, nnz, S, rowptr);
+    FSW_CHECK_LAUNCH("rowptr_from_rows");
+    return FSW_OK;
+}
+
+extern "C" int fsw_edge_weights(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t N,
+                                int64_t E, int self_loops, double self_loop_weight, int gcn, void* deg_out, void* w_out,
+                                void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!deg_out) return fsw_fail(FSW_ERR_INVALID, "fsw_edge_weights: deg_out is NULL");
+    if ((gcn || self_loops) && !w_out) return fsw_fail(FSW_ERR_INVALID, "fsw_edge_weights: w_out is NULL");
+    if (self_loops && !eid) return fsw_fail(FSW_ERR_INVALID, "fsw_edge_weights: eid needed with self loops");
+    if (N == 0) return FSW_OK;
+    const unsigned grid = (unsigned)fsw_cdiv(N, 256);
+    for (int phase = 0; phase < 2; ++phase) {
+        if (dtype == FSW_F32)
+            edge_weights_kernel<float><<<grid, 256, 0, st>>>(rowptr, col, eid, N, E, self_loops, self_loop_weight, gcn, (float*)deg_out, (float*)w_out, phase);
+        else if (dtype == FSW_F64)
+            edge_weights_kernel<double><<<grid, 256, 0, st>>>(rowptr, col, eid, N, E, self_loops, self_loop_weight, gcn, (double*)deg_out, (double*)w_out, phase);
+        else
+            return fsw_fail(FSW_ERR_INVALID, "fsw_edge_weights: dtype %d", dtype);
+        FSW_CHECK_LAUNCH("edge_weights_kernel");
+    }
+    return FSW_OK;
+}
+
+extern "C" size_t fsw_plan_workspace_bytes(int64_t S) {
+    (void)S;
+    return (size_t)(2 * (FSW_PLAN_BUCKETS + 8)) * sizeof(int);
+}
+
+extern "C" int fsw_segment_plan(int dtype, const int32_t* rowptr, int64_t n_fixed, const void* W, int64_t S, double thresh,
+                                double* mass, int32_t* info, int32_t* order, int32_t* bucket_offsets, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    if (workspace_bytes < fsw_plan_workspace_bytes(S)) return fsw_fail(FSW_ERR_WORKSPACE, "fsw_segment_plan: workspace too small");
+    if (!(thresh > 0)) return fsw_fail(FSW_ERR_INVALID, "fsw_segment_plan: thresh must be positive");
+    if (!rowptr && n_fixed <= 0) return fsw_fail(FSW_ERR_INVALID, "fsw_segment_plan: rowptr == NULL needs n_fixed > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* hist = (int*)workspace;
+    int* cursor = hist + (FSW_PLAN_BUCKETS + 8);
+    FSW_CUDA(cudaMemsetAsync(hist, 0, (size_t)(2 * (FSW_PLAN_BUCKETS + 8)) * sizeof(int), st));
+    if (S > 0) {
+        const unsigned grid = (unsigned)fsw_cdiv(S * 32, 256);
+        if (dtype == FSW_F32)
+            plan_stats<float><<<grid, 256, 0, st>>>(rowptr, n_fixed, (const float*)W, S, thresh, mass, info, hist);
+        else if (dtype == FSW_F64)
+            plan_stats<double><<<grid, 256, 0, st>>>(rowptr, n_fixed, (const double*)W, S, thresh, mass, info, hist);
+        else
+            return fsw_fail(FSW_ERR_INVALID, "fsw_segment_plan: dtype %d", dtype);
+        FSW_CHECK_LAUNCH("plan_stats");
+    }
+    plan_scan<<<1, 32, 0, st>>>(hist, bucket_offsets, cursor);
+    FSW_CHECK_LAUNCH("plan_scan");
+    if (S > 0) {
+        plan_scatter<<<(unsigned)fsw_cdiv(S, 256), 256, 0, st>>>(info, S, cursor, order);
+        FSW_CHECK_LAUNCH("plan_scatter");
+    }
+    return FSW_OK;
+}

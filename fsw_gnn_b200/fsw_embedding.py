@@ -1,0 +1,579 @@
+"""FSW_embedding - host-side mirror of the reference module (fsw_embedding.py:169-1144) on top of the
+B200-native library.
+
+Same constructor keywords, parameters (`projVecs [K, d_in+d_edge]`, `freqs [K]`, `bias`,
+`total_mass_encoding_scale`; state_dicts of the reference load unchanged) and the same
+`forward(X, W='unit', X_edge=None, graph_mode=False, serialize_num_slices=None)`.
+
+What differs is below the interface: instead of ~40 torch ops over sparse-COO tensors
+(forward_helper, class ag, class sp) the forward is  K1 projection -> K2 fused
+gather/sort/cumsum/Fourier/reduce  and the backward is one fused kernel K3 plus two contractions
+(see fsw_gnn_b200/ops.py and csrc/).  CUDA only: there is no CPU or pure-torch fallback.
+"""
+import numbers
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import graph as _graph
+from . import ops as _ops
+
+version = "b200-1.0 (interface of fsw_embedding.py 2.14)"
+
+# Mirrors of the reference's module-level switches (fsw_embedding.py:104-116)
+fsw_embedding_basic_safety_checks = True
+fsw_embedding_debug_mode = False
+
+
+def ifnone(a, b):
+    return a if (a is not None) else b
+
+
+def qprint(q, s=""):
+    if q:
+        print(s, end="")
+
+
+def qprintln(q, s=""):
+    qprint(q, s + "\n")
+
+
+class FSW_embedding(nn.Module):
+    def __init__(self,
+                 d_in, d_out=None,
+                 nSlices=None, nFreqs=None, collapse_freqs=False,
+                 d_edge=0,
+                 encode_total_mass=False,
+                 total_mass_encoding_function="identity",
+                 total_mass_encoding_scale=1.0,
+                 total_mass_encoding_method="plain",
+                 total_mass_pad_thresh=1.0,
+                 learnable_slices=False, learnable_freqs=False, learnable_total_mass_encoding_scale=False,
+                 freqs_init="random",
+                 minimize_slice_coherence=False,
+                 enable_bias=True,
+                 device=None, dtype=torch.float32,
+                 load_custom_cuda_lib=True,
+                 report=False, user_warnings=True,
+                 report_on_coherence_minimization=False):
+        super().__init__()
+        self.user_warnings = user_warnings
+        # The library IS the implementation here: load failure is fatal (north star: no fallback).
+        # `load_custom_cuda_lib=False` selected the pure-torch path in the reference (:187, :2847);
+        # it is accepted for signature compatibility and ignored.
+        _lib.load()
+        if not load_custom_cuda_lib and user_warnings:
+            warnings.warn("load_custom_cuda_lib=False is ignored: fsw_gnn_b200 has no pure-torch path", UserWarning)
+
+        assert d_in >= 0, "d_in must be nonnegative"
+        assert d_edge >= 0, "d_edge must be nonnegative"
+        assert (d_out is None) or (d_out >= 0), "d_out must be nonnegative or None"
+        if d_out == 0:
+            encode_total_mass = False
+
+        self.d_in = d_in
+        self.d_edge = d_edge
+        self.encode_total_mass = bool(encode_total_mass)
+        self.total_mass_encoding_dim = 1 if self.encode_total_mass else 0
+        self.total_mass_encoding_scale_init = total_mass_encoding_scale
+
+        total_mass_pad_thresh = float(total_mass_pad_thresh)
+        assert not np.isinf(total_mass_pad_thresh), "total_mass_pad_thresh cannot be inf"
+        assert not np.isnan(total_mass_pad_thresh), "total_mass_pad_thresh cannot be NaN"
+        assert total_mass_pad_thresh > 0, "total_mass_pad_thresh must be positive"
+        self.total_mass_pad_thresh = total_mass_pad_thresh
+
+        assert total_mass_encoding_method in {"plain", "homog", "homog_alt"}, \
+            "<total_mass_encoding_method> must be one of 'plain', 'homog', 'homog_alg'"
+        self.total_mass_encoding_method = total_mass_encoding_method
+        assert total_mass_encoding_function in {"identity", "sqrt", "log"}, \
+            "<total_mass_encoding_function> must be one of 'identity', 'sqrt', 'log'"
+        self.total_mass_encoding_function = total_mass_encoding_function
+
+        if (d_out is not None) and (nSlices is None) and (nFreqs is None):
+            self.cartesian_mode = False
+            self.collapse_freqs = False
+            self.d_out = d_out
+            self.nSlices = d_out - self.total_mass_encoding_dim
+            self.nFreqs = d_out - self.total_mass_encoding_dim
+        elif (d_out is None) and (nSlices is not None) and (nFreqs is not None):
+            assert collapse_freqs or (not encode_total_mass), \
+                "Cartesian mode with collapse_freqs=False is not supported when encode_total_mass=True"
+            self.cartesian_mode = True
+            self.collapse_freqs = collapse_freqs
+            self.nSlices = nSlices
+            self.nFreqs = nFreqs
+            self.d_out = nSlices * nFreqs + self.total_mass_encoding_dim
+        else:
+            assert False, "Expected exactly one of (d_out != None) or (nSlices != None and nFreqs != None)"
+        assert self.d_out >= 0, "d_out must be nonnegative"
+
+        self.minimize_slice_coherence = minimize_slice_coherence
+        self.learnable_slices = learnable_slices
+        self.learnable_freqs = learnable_freqs
+        self.learnable_total_mass_encoding_scale = learnable_total_mass_encoding_scale
+        self.freqs_init = freqs_init
+        self.enable_bias = enable_bias
+
+        self.device_new = ifnone(device, torch.device("cuda" if torch.cuda.is_available() else "cpu"))
+        assert dtype.is_floating_point and (not dtype.is_complex), \
+            "dtype must be real floating-point; instead got dtype=%s" % (dtype)
+        self.dtype_new = dtype
+        self.report = report
+        self.report_on_coherence_minimization = report_on_coherence_minimization
+        self._plan_cache = []
+        self.reset_parameters()
+
+    # ------------------------------------------------------------------------------------------
+    def reset_parameters(self, freqs_init=None, minimize_slice_coherence=None, report=None,
+                         report_on_coherence_minimization=None):
+        self.freqs_init = ifnone(freqs_init, self.freqs_init)
+        self.minimize_slice_coherence = ifnone(minimize_slice_coherence, self.minimize_slice_coherence)
+        self.report = ifnone(report, self.report)
+        self.report_on_coherence_minimization = ifnone(report_on_coherence_minimization,
+                                                       self.report_on_coherence_minimization)
+        if hasattr(self, "device_new"):
+            device = self.device_new
+            delattr(self, "device_new")
+        else:
+            device = self.get_device()
+        if hasattr(self, "dtype_new"):
+            dtype = self.dtype_new
+            delattr(self, "dtype_new")
+        else:
+            dtype = self.get_dtype()
+
+        projVecs, freqs, bias, tm_scale = FSW_embedding.generate_embedding_parameters(
+            d_in=self.d_in + self.d_edge, nSlices=self.nSlices, nFreqs=self.nFreqs,
+            cartesian_mode=self.cartesian_mode, collapse_freqs=self.collapse_freqs,
+            total_mass_encoding_dim=self.total_mass_encoding_dim,
+            total_mass_encoding_scale_init=self.total_mass_encoding_scale_init,
+            freqs_init=self.freqs_init, minimize_slice_coherence=self.minimize_slice_coherence,
+            device=device, report=self.report,
+            report_on_coherence_minimization=self.report_on_coherence_minimization)
+
+        self.projVecs = nn.Parameter(projVecs.to(dtype=dtype, device=device), requires_grad=self.learnable_slices)
+        self.freqs = nn.Parameter(freqs.to(dtype=dtype, device=device), requires_grad=self.learnable_freqs)
+        if self.enable_bias:
+            bias = bias.to(dtype=dtype, device=device)
+            if self.cartesian_mode and self.collapse_freqs:
+                bias = bias.reshape((self.nSlices * self.nFreqs))
+            # as in the reference the bias is trainable exactly when the slices are (:406)
+            self.bias = nn.Parameter(bias, requires_grad=self.learnable_slices)
+        if self.encode_total_mass:
+            self.total_mass_encoding_scale = nn.Parameter(tm_scale.to(device=device),
+                                                          requires_grad=self.learnable_total_mass_encoding_scale)
+        self.to(device=self.get_device(), dtype=self.get_dtype())
+        return self
+
+    def to(self, *args, **kwargs):
+        if "dtype" in kwargs:
+            arg = kwargs["dtype"]
+            assert isinstance(arg, torch.dtype), "invalid input type %s at argument dtype" % (type(arg))
+            assert arg.is_floating_point and not arg.is_complex, \
+                "dtype must be real floating-point; instead got dtype=%s" % (arg)
+        for arg in args:
+            if isinstance(arg, torch.dtype):
+                assert arg.is_floating_point and not arg.is_complex, \
+                    "dtype must be real floating-point; instead got dtype=%s" % (arg)
+        super().to(*args, **kwargs)
+        self._plan_cache = []
+        return self
+
+    def get_device(self):
+        return self.projVecs.device
+
+    def get_dtype(self):
+        return self.projVecs.dtype
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def generate_embedding_parameters(d_in, nSlices, nFreqs, cartesian_mode, collapse_freqs,
+                                      total_mass_encoding_dim, total_mass_encoding_scale_init,
+                                      freqs_init, minimize_slice_coherence, device, report,
+                                      report_on_coherence_minimization):
+        """Initial slices / frequencies / bias, generated in fp64 like the reference (:445-559):
+        unit-norm Gaussian slices (optionally spread by coherence minimisation), frequencies
+        'random' (u/(1-u), sorted), 'spread' (((i+1/2)/K)/(1-.)), a scalar, or an interval."""
+        dt = torch.float64
+        projVecs = torch.randn(size=(nSlices, d_in), dtype=dt, device=device)
+        projVecs = nn.functional.normalize(projVecs, p=2.0, dim=1, eps=0)
+        if minimize_slice_coherence:
+            projVecs = minimize_mutual_coherence(projVecs, report=report_on_coherence_minimization)
+        assert not torch.isinf(projVecs).any(), "Found infs in projVecs"
+        assert not torch.isnan(projVecs).any(), "Found nans in projVecs"
+        assert not (projVecs == 0).all(dim=1).any(), "Found zero vectors in projVecs"
+
+        shape = (nFreqs,)
+        if nFreqs == 0:
+            freqs = torch.zeros(size=shape, dtype=dt, device=device)
+        elif isinstance(freqs_init, numbers.Real):
+            assert not np.isinf(freqs_init), "freqs_init cannot be infinite"
+            assert not np.isnan(freqs_init), "freqs_init cannot be NaN"
+            freqs = freqs_init * torch.ones(size=shape, dtype=dt, device=device)
+        elif isinstance(freqs_init, tuple):
+            assert len(freqs_init) == 2, "When freqs_init is a tuple, it must be of length 2"
+            a, b = freqs_init
+            assert not np.isinf(a) and not np.isinf(b), "Received infinite value in freqs_init tuple"
+            assert not np.isnan(a) and not np.isnan(b), "Received NaN value in freqs_init tuple"
+            assert a <= b, "When freqs_init is a tuple, it is required to satisfy freqs_init[0] <= freqs_init[1]"
+            if nFreqs == 1:
+                freqs = a + (b - a) / 2 * torch.ones(size=shape, dtype=dt, device=device)
+            else:
+                freqs = a + (b - a) * (torch.arange(nFreqs, dtype=dt, device=device) / (nFreqs - 1))
+        elif freqs_init == "random":
+            u, _ = torch.sort(torch.rand(size=shape, dtype=dt, device=device), dim=0)
+            assert (u < 1).all()
+            freqs = u / (1 - u)
+        elif freqs_init == "spread":
+            u = (0.5 + torch.arange(nFreqs, dtype=dt, device=device)) / nFreqs
+            freqs = u / (1 - u)
+        else:
+            raise RuntimeError("Invalid value for argument freqs_init; expected number, tuple (a,b) of numbers "
+                               "denoting an interval, 'random' or 'spread'")
+        if nFreqs > 0:
+            assert not torch.isinf(freqs).any(), "Found infs in freqs"
+            assert not torch.isnan(freqs).any(), "Found nans in freqs"
+
+        if cartesian_mode and not collapse_freqs:
+            bias_shape = (nSlices, nFreqs)
+        elif cartesian_mode and collapse_freqs:
+            bias_shape = (nSlices * nFreqs + total_mass_encoding_dim,)
+        else:
+            bias_shape = (nSlices + total_mass_encoding_dim,)
+        bias = torch.zeros(size=bias_shape, dtype=dt, device=device)
+        tm_scale = torch.tensor(total_mass_encoding_scale_init, device=device, dtype=dt) \
+            if total_mass_encoding_dim > 0 else None
+        return projVecs, freqs, bias, tm_scale
+
+    def spread_freqs_at_interval(self, center, radius):
+        """fsw_embedding.py:568-582."""
+        assert radius >= 0
+        if (self.nFreqs == 1) or (radius == 0):
+            freqs_new = center * torch.ones_like(self.freqs)
+        else:
+            spread = 2 * (0.5 + torch.arange(self.nFreqs, dtype=self.get_dtype(), device=self.get_device())
+                          .reshape(self.freqs.shape)) / self.nFreqs - 1
+            spread = spread * 1 / (1 - 1 / self.nFreqs)
+            freqs_new = center + radius * spread
+        sd = self.state_dict()
+        sd["freqs"] = freqs_new
+        self.load_state_dict(sd)
+        return self
+
+    def get_mutual_coherence(self):
+        gram = self.projVecs @ self.projVecs.transpose(0, 1)
+        gram = gram - torch.diag(torch.diag(gram))
+        return torch.max(torch.abs(gram))
+
+    @staticmethod
+    def total_mass_homog_alt_encoding_part1(totmass):
+        return torch.where(totmass <= 1, totmass * (2 - totmass), torch.ones_like(totmass))
+
+    @staticmethod
+    def total_mass_homog_alt_encoding_part2(totmass):
+        return torch.where(totmass <= 1, totmass.square(), 2 * totmass - 1)
+
+    # ------------------------------------------------------------------------------------------
+    def _cached_plan(self, key, refs, builder):
+        key = key + (str(self.get_device()),)
+        for i, (k, r, plan) in enumerate(self._plan_cache):
+            if k == key:
+                self._plan_cache.append(self._plan_cache.pop(i))
+                return plan
+        plan = builder()
+        self._plan_cache.append((key, refs, plan))
+        while len(self._plan_cache) > 4:
+            self._plan_cache.pop(0)
+        return plan
+
+    def forward(self, X, W="unit", X_edge=None, graph_mode=False, serialize_num_slices=None):
+        """See the reference docstring (fsw_embedding.py:587-623).  `serialize_num_slices` is accepted
+        and has no effect: it "does not affect the result" there (:622-623) and the fused kernel never
+        materialises the per-(element, slice) tensors it was meant to chunk."""
+        dtype, device = self.get_dtype(), self.get_device()
+        if device.type != "cuda":
+            raise RuntimeError("fsw_gnn_b200.FSW_embedding runs on CUDA devices only (got %s): no CPU fallback" % device)
+        checks = fsw_embedding_basic_safety_checks
+        if checks and self.learnable_slices:
+            assert torch.isfinite(self.projVecs).all(), "Projection vectors contain NaNs or infs"
+        if checks and self.learnable_freqs:
+            assert torch.isfinite(self.freqs).all(), "Frequencies contain NaNs or infs"
+
+        # ---- A. types and content (fsw_embedding.py:636-705) ----
+        if self.d_edge > 0:
+            assert graph_mode, "d_edge > 0 (given at initialization) necessitates graph_mode=True on forward call"
+            assert X_edge is not None, "X_edge must be provided since d_edge > 0"
+        else:
+            assert (X_edge is None) or (X_edge.numel() == 0), "X_edge should be None or empty since d_edge == 0"
+            X_edge = None
+        assert torch.is_tensor(X), "X must be a pytorch tensor. Instead got type %s" % (type(X))
+        assert torch.is_tensor(W) or W in {"unit", "uniform"}, "W must be a pytorch tensor, 'unit' or 'uniform'"
+        assert X.dtype == dtype, "X has the wrong dtype. Expected %s, got %s" % (dtype, X.dtype)
+        assert X.device == device, "X is on the wrong device. Expected %s, got %s" % (device, X.device)
+        if checks:
+            assert torch.isfinite(X).all(), "All entries of X must be finite (no NaNs / infs)"
+        W_sparse = False
+        if torch.is_tensor(W):
+            assert W.dtype == dtype, "W has the wrong dtype. Expected %s, got %s" % (dtype, W.dtype)
+            assert W.device == device, "W is on the wrong device. Expected %s, got %s" % (device, W.device)
+            if W.is_sparse or W.layout != torch.strided:
+                assert W.layout == torch.sparse_coo, \
+                    "Sparse W has an unsupported sparsity layout '%s'. Only the COO layout (torch.sparse_coo) is currently supported." % (W.layout)
+                assert W.is_coalesced(), "Sparse W must be coalesced"
+                assert W.dense_dim() == 0, "W.dense_dim() must be zero"
+                W_sparse = True
+                W_vals = W.values()
+            else:
+                W_vals = W
+            if checks:
+                assert torch.isfinite(W_vals).all(), "All entries of W must be finite (no NaNs / infs)"
+                assert (W_vals >= 0).all(), "All entries of W must be nonnegative"
+            if W.requires_grad:
+                raise NotImplementedError("fsw_gnn_b200: gradients with respect to the weights W are not implemented")
+        X_edge_sparse = False
+        if X_edge is not None:
+            assert torch.is_tensor(W), "When X_edge is provided, W must be provided explicitly"
+            assert X_edge.device == device, "X_edge is on the wrong device. Expected %s, got %s" % (device, X_edge.device)
+            assert X_edge.dtype == dtype, "X_edge has the wrong dtype. Expected %s, got %s" % (dtype, X_edge.dtype)
+            if X_edge.is_sparse or X_edge.layout != torch.strided:
+                assert X_edge.layout == torch.sparse_coo, "Sparse X_edge has an unsupported sparsity layout '%s'." % (X_edge.layout)
+                assert X_edge.is_coalesced(), "Sparse X_edge must be coalesced"
+                assert X_edge.dense_dim() in (0, 1), "X_edge.dense_dim() must be 1 or 0"
+                assert (self.d_edge == 1) or (X_edge.dense_dim() == 1), "X_edge.dense_dim() must be 1 since d_edge > 1"
+                X_edge_sparse = True
+            if checks:
+                xe_vals = X_edge.values() if X_edge_sparse else X_edge
+                assert torch.isfinite(xe_vals).all(), "All entries of X_edge must be finite (no NaNs / infs)"
+            assert X_edge_sparse == W_sparse, "X_edge and W must either both or neither be sparse"
+
+        # ---- B. sizes (fsw_embedding.py:708-757) ----
+        assert len(X.shape) >= 2, "X must be a tensor of order at least 2"
+        assert X.shape[-1] == self.d_in, \
+            "The last dimension of X must equal d_in=%d. Instead got %d" % (self.d_in, X.shape[-1])
+        nRecipients = None
+        if not graph_mode:
+            batch_dims = tuple(X.shape[0:-2])
+            n = X.shape[-2]
+            if torch.is_tensor(W):
+                assert (len(W.shape) == len(X.shape) - 1) and (tuple(W.shape) == tuple(X.shape[0:-1])), \
+                    "Shape mismatch between X and W: If X.shape = (b1,b2,...,bk,n,d_in) then W.shape should be (b1,b2,...,bk,n) (unless graph_mode=True)"
+        else:
+            assert torch.is_tensor(W), "W must be explicitly provided when graph_mode=True"
+            batch_dims = tuple(W.shape[0:-2])
+            nRecipients = W.shape[-2]
+            n = W.shape[-1]
+            assert (len(W.shape) == len(X.shape)) and (W.shape[-1] == X.shape[-2]) and (tuple(W.shape[0:-2]) == tuple(X.shape[0:-2])), \
+                "Shape mismatch between X and W: When graph_mode=True, if W.shape = (b1,b2,...,bk,nRecipients,n) then X.shape should be (b1,b2,...,bk,n,d_in)"
+            if X_edge is not None:
+                assert (((self.d_edge == 1) and (tuple(X_edge.shape) == tuple(W.shape))) or
+                        ((X_edge.dim() == W.dim() + 1) and (tuple(X_edge.shape[0:-1]) == tuple(W.shape)) and (X_edge.shape[-1] == self.d_edge))), \
+                    "Shape mismatch between X_edge and W"
+                if X_edge_sparse:
+                    assert X_edge.values().shape[0] == W.values().shape[0], "Sparse X_edge must have the same number of values() as W"
+                    if checks:
+                        assert (X_edge.indices() == W.indices()).all(), "Sparse X_edge must have the same nonzero pattern as W"
+
+        out_batch_shape = batch_dims + ((nRecipients,) if graph_mode else ())
+        if self.cartesian_mode and not self.collapse_freqs:
+            out_shape = out_batch_shape + (self.nSlices, self.nFreqs)
+        else:
+            out_shape = out_batch_shape + (self.d_out,)
+        if self.d_out == 0 or int(np.prod(out_batch_shape, dtype=np.int64)) == 0:
+            return torch.zeros(size=out_shape, dtype=dtype, device=device)
+        if serialize_num_slices is not None:
+            assert isinstance(serialize_num_slices, int) and (serialize_num_slices >= 1), \
+                "serialize_num_slices must be None or a positive integer"
+
+        # ---- C. segments ----
+        thresh = self.total_mass_pad_thresh
+        Xf = X.reshape(-1, self.d_in)
+        E_feat = None
+        if not graph_mode and not W_sparse:
+            B = int(np.prod(batch_dims, dtype=np.int64)) if batch_dims else 1
+            if torch.is_tensor(W):
+                Wf = W.reshape(-1).contiguous()
+                plan = self._cached_plan(("dense", Wf.data_ptr(), W._version, B, n, thresh, dtype), W,
+                                         lambda: _graph.plan_dense(B, n, Wf, thresh, dtype, device))
+            elif W == "unit":
+                plan = self._cached_plan(("unit", B, n, thresh, dtype), None,
+                                         lambda: _graph.plan_dense(B, n, None, thresh, dtype, device))
+            else:  # 'uniform': explicit 1/n weights, as the reference materialises them (:732)
+                def build_uniform():
+                    Wf = torch.full((B * n,), 1.0 / n, dtype=dtype, device=device)
+                    return _graph.plan_dense(B, n, Wf, thresh, dtype, device)
+                plan = self._cached_plan(("uniform", B, n, thresh, dtype), None, build_uniform)
+        else:
+            wshape = tuple(W.shape)
+            key_ptr = W.values().data_ptr() if W_sparse else W.data_ptr()
+
+            def build_coo():
+                if W_sparse:
+                    idx, vals = W.indices(), W.values()
+                else:
+                    # dense adjacency: zero weights contribute nothing and are dropped
+                    idx = torch.nonzero(W).t().contiguous()
+                    vals = W[tuple(idx)]
+                plan_ = _graph.plan_from_coo(idx, vals, wshape, graph_mode, thresh, dtype)
+                plan_.coo_indices = idx
+                return plan_
+
+            plan = self._cached_plan(("coo", key_ptr, W._version, wshape, W_sparse, graph_mode, thresh, dtype), W, build_coo)
+            if X_edge is not None:
+                if X_edge_sparse:
+                    E_feat = X_edge.values()
+                    if E_feat.dim() == 1:
+                        E_feat = E_feat.unsqueeze(-1)
+                else:
+                    xe = X_edge if X_edge.dim() == W.dim() + 1 else X_edge.unsqueeze(-1)
+                    E_feat = xe[tuple(plan.coo_indices)]
+        out = self.embed_plan(Xf, plan, E_feat)
+        return out.reshape(out_shape)
+
+    # ------------------------------------------------------------------------------------------
+    def embed_plan(self, Xf, plan, E_feat=None):
+        """[S, d_out] embedding of the segments of `plan` over the point matrix Xf [Nrows, d_in].
+        This is the entry FSW_conv uses directly with its cached graph plan."""
+        theta, xi = self.projVecs, self.freqs
+        if self.cartesian_mode:
+            # every (slice, frequency) pair becomes one fused (slice, frequency) column: k * nFreqs + f
+            theta = theta.repeat_interleave(self.nFreqs, dim=0)
+            xi = xi.repeat(self.nSlices)
+        bias = self.bias if self.enable_bias else None
+        if bias is not None and bias.dim() == 2:
+            bias = bias.reshape(-1)
+        scale = self.total_mass_encoding_scale if self.encode_total_mass else None
+        if not self.encode_total_mass:
+            return _ops.fsw_embed(Xf, theta, xi, bias, None, E_feat, plan, None)
+        if self.total_mass_encoding_method == "plain":
+            return _ops.fsw_embed(Xf, theta, xi, bias, scale, E_feat, plan, self.total_mass_encoding_function)
+        # homogeneous variants (fsw_embedding.py:876-884): composed in torch on the [S, K] core
+        core = _ops.fsw_embed(Xf, theta, xi, None, None, E_feat, plan, None)
+        tm = _ops.total_mass_function(plan.mass_as(core.dtype), self.total_mass_encoding_function).unsqueeze(-1) * scale
+        nrm = torch.mean(core.abs(), dim=-1, keepdim=True)
+        if self.total_mass_encoding_method == "homog":
+            out = torch.cat((tm * nrm, core), dim=-1)
+        else:
+            out = torch.cat((FSW_embedding.total_mass_homog_alt_encoding_part1(tm) * nrm,
+                             FSW_embedding.total_mass_homog_alt_encoding_part2(tm) * core), dim=-1)
+        if bias is not None:
+            out = out + bias
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Segmented cumulative sum: public function of the reference (fsw_embedding.py:2795-2850)
+# ------------------------------------------------------------------------------------------------
+def segcumsum(values, segment_ids, max_seg_size=None, in_place=False, thorough_verify_input=False,
+              always_use_pure_torch=False):
+    """Segmented inclusive cumulative sum of `values` over maximal runs of equal `segment_ids`.
+    One single-pass kernel (decoupled look-back) instead of the reference's hierarchy of launches;
+    `max_seg_size` is accepted and not needed.  CUDA tensors only."""
+    assert values.dim() == 1, "values must be a 1-dimensional tensor"
+    assert segment_ids.dim() == 1, "segment_ids must be a 1-dimensional tensor"
+    assert segment_ids.numel() == values.numel(), "values and segment_ids must contain the same number of elements"
+    assert segment_ids.dtype in (torch.int32, torch.int64), "segment_ids must have int32 or int64 dtype"
+    assert values.device == segment_ids.device, "values and segment_ids must be on the same device"
+    assert not segment_ids.is_sparse, "segment_ids cannot be sparse"
+    assert segment_ids.is_contiguous(), "segment_ids must be in contiguous format"
+    assert not values.is_sparse, "values cannot be sparse"
+    assert (not in_place) or values.is_contiguous(), "when in_place==True, values must be in contiguous format"
+    if max_seg_size is not None:
+        assert isinstance(max_seg_size, numbers.Number) and max_seg_size >= 1
+    if always_use_pure_torch:
+        raise RuntimeError("fsw_gnn_b200.segcumsum has no pure-torch implementation (always_use_pure_torch=True)")
+    if thorough_verify_input:
+        _, c1 = torch.unique_consecutive(segment_ids, return_counts=True)
+        _, c2 = torch.unique(segment_ids, return_counts=True)
+        assert c1.numel() == c2.numel(), "repeated segment IDs detected"
+        assert torch.isfinite(values).all(), "Found infs or nans in values"
+    return _ops.segcumsum_cuda(values, segment_ids, in_place=in_place)
+
+
+def segcumsum_slow(x, segment_ids):
+    """O(n) host loop with the semantics of the reference's checker (fsw_embedding.py:3016-3027)."""
+    xs = x.detach().cpu()
+    ids = segment_ids.detach().cpu()
+    out = torch.empty_like(xs)
+    for i in range(len(xs)):
+        if i > 0 and ids[i] == ids[i - 1]:
+            out[i] = out[i - 1] + xs[i]
+        else:
+            out[i] = xs[i]
+    return out.to(x.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# Mutual-coherence minimisation (init-time only; SURVEY.md 2: out of the hot path)
+# ------------------------------------------------------------------------------------------------
+def _coherence(X):
+    G = X @ X.t()
+    G = G - torch.diag(torch.diag(G))
+    return G, G.abs().max()
+
+
+def minimize_mutual_coherence(X_init, report=True):
+    """Spread the rows of X_init on the unit sphere by lowering max_{i != j} |<x_i, x_j>|.
+
+    Same purpose and call signature as the reference's routine (fsw_embedding.py:3045-3248):
+    projected gradient descent on a smooth p-norm surrogate of the off-diagonal Gram entries with p
+    increased in stages.  This is an independent, shorter implementation (backtracking line search per
+    stage); it is initialisation-time code and not part of the measured path.
+    """
+    X = nn.functional.normalize(X_init, p=2, dim=1, eps=0)
+    n = X.shape[0]
+    if X.numel() == 0 or n <= 1:
+        return X
+    G, mu = _coherence(X)
+    step = 1.0
+    for p in (4.0, 8.0, 16.0, 32.0, 64.0, 128.0, 256.0, 512.0, 1024.0):
+        stall = 0
+        for it in range(200):
+            G, mu = _coherence(X)
+            if mu <= 0:
+                return X
+            Gn = G / mu
+            s = Gn.abs().pow(p).sum()
+            obj = mu * s.pow(1.0 / p)
+            grad = mu * s.pow(1.0 / p - 1.0) * ((Gn.abs().pow(p - 1.0) * Gn.sign()) @ X) * 2.0 / mu
+            grad = grad - (grad * X).sum(dim=1, keepdim=True) * X  # tangent to the sphere
+            gn = grad.norm()
+            if gn == 0:
+                break
+            improved = False
+            t = step
+            for _ in range(30):
+                Xn = nn.functional.normalize(X - t * grad / gn, p=2, dim=1, eps=0)
+                Gn2, mu2 = _coherence(Xn)
+                obj2 = mu2 * (Gn2 / mu2).abs().pow(p).sum().pow(1.0 / p) if mu2 > 0 else mu2
+                if obj2 < obj:
+                    improved = True
+                    break
+                t *= 0.5
+            if not improved:
+                break
+            rel = (obj - obj2) / obj
+            X = Xn
+            step = min(t * 2.0, 10.0)
+            qprintln(report, "p=%g it=%d coherence=%g step=%g" % (p, it, float(mu2), t))
+            if rel < 1e-5:
+                stall += 1
+                if stall >= 3:
+                    break
+            else:
+                stall = 0
+    return X
+
+
+class sp:
+    """The two sparse helpers of the reference that are part of FSW_conv's/FSW_readout's surface
+    (fsw_conv.py:400, :504).  The rest of `sp` / `ag` (fsw_embedding.py:1232-2775) has no counterpart:
+    the fused kernels replace them."""
+
+    @staticmethod
+    def sparse_coo_tensor_coalesced(indices, values, size):
+        out = torch.sparse_coo_tensor(indices=indices, values=values, size=size, is_coalesced=True)
+        return out

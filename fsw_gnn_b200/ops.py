@@ -1,0 +1,239 @@
+"""Host-side wrappers around the C ABI: segment plans, projection, fused embed forward/backward.
+
+Everything here launches kernels of libfsw_embedding.so on torch's current CUDA stream; torch is
+used for memory (allocation) and autograd bookkeeping only.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, ptr, stream_ptr
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=device)
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class SegmentPlan:
+    """CSR description of a batch of weighted multisets + the launch plan of the fused kernels.
+
+    Replaces the reference's coalesced sparse-COO weight tensor and the `slice_info` dictionaries
+    that `sp.get_slice_info` rebuilds 3-4 times per forward (fsw_embedding.py:2586-2678, :2657-2663).
+
+    rowptr [S+1] int32 or None (then every segment has n_fixed elements, stored contiguously)
+    col    [E] int32 row of the point matrix for each element, or None (identity)
+    W      [E] raw weights in the compute dtype, or None (unit weights)
+    """
+
+    def __init__(self, S, E, rowptr, n_fixed, col, W, thresh, dtype, device):
+        lib = _lib.load()
+        self.S, self.E = int(S), int(E)
+        self.rowptr, self.n_fixed, self.col, self.W = rowptr, int(n_fixed), col, W
+        self.thresh = float(thresh)
+        self.dtype, self.device = dtype, device
+        self.mass = torch.empty(self.S, dtype=torch.float64, device=device)
+        self.info = torch.empty(self.S, dtype=torch.int32, device=device)
+        self.order = torch.empty(self.S, dtype=torch.int32, device=device)
+        self._bucket_dev = torch.empty(_lib.PLAN_BUCKETS + 2, dtype=torch.int32, device=device)
+        ws = _ws(lib.fsw_plan_workspace_bytes(self.S), device)
+        check(lib.fsw_segment_plan(dtype_code(dtype), ptr(rowptr), self.n_fixed, ptr(W), self.S, self.thresh,
+                                   ptr(self.mass), ptr(self.info), ptr(self.order), ptr(self._bucket_dev),
+                                   ptr(ws), ws.numel(), stream_ptr(device)), "fsw_segment_plan")
+        # one small D2H read per new plan (the reference syncs in every get_slice_info, :2655)
+        host = self._bucket_dev.cpu()
+        self.bucket_offsets = (ctypes.c_int * (_lib.PLAN_BUCKETS + 2))(*host.tolist())
+        self.max_n_eff = int(host[_lib.PLAN_BUCKETS + 1])
+        self._scratch = {}
+        self._mass_t = None
+
+    def mass_as(self, dtype):
+        """Total mass per segment (W_sum of fsw_embedding.py:778-784) in the compute dtype, [S]."""
+        if self._mass_t is None or self._mass_t.dtype != dtype:
+            self._mass_t = self.mass.to(dtype)
+        return self._mass_t
+
+    def scratch(self, K, backward):
+        key = (int(K), bool(backward))
+        if key not in self._scratch:
+            lib = _lib.load()
+            nbytes = lib.fsw_embed_scratch_bytes(dtype_code(self.dtype), self.bucket_offsets, int(K), self.max_n_eff,
+                                                 1 if backward else 0)
+            self._scratch[key] = _ws(nbytes, self.device) if nbytes > 0 else None
+        return self._scratch[key]
+
+    def uniform_fraction(self):
+        bo = list(self.bucket_offsets)
+        return (bo[_lib.PLAN_BUCKETS_PER_KIND] - bo[0]) / max(self.S, 1)
+
+
+def gemm(op, A, B, M, N, Kd, lda, ldb, out=None, ldc=None, accumulate=False):
+    """C = A.B in the input precision (op 0: NT, 1: NN, 2: TN, see include/fsw_embedding.h section 4)."""
+    lib = _lib.load()
+    if out is None:
+        ldc = N if ldc is None else ldc
+        out = torch.empty((M, ldc), dtype=A.dtype, device=A.device)
+    check(lib.fsw_gemm(dtype_code(A.dtype), op, M, N, Kd, ptr(A), lda, ptr(B), ldb, ptr(out), ldc,
+                       1 if accumulate else 0, stream_ptr(A.device)), "fsw_gemm")
+    return out
+
+
+def project(X, theta_part, ldp):
+    """Xp[:, :K] = X . theta_part^T  (fsw_embedding.py:911).  X [N, d] contiguous; theta_part [K, d] view
+    with row stride theta_part.stride(0).  Columns K..ldp-1 of the result are zero."""
+    Nrows, d = X.shape
+    K = theta_part.shape[0]
+    if ldp == K:
+        out = torch.empty((Nrows, ldp), dtype=X.dtype, device=X.device)
+    else:
+        out = torch.zeros((Nrows, ldp), dtype=X.dtype, device=X.device)
+    if Nrows == 0 or K == 0:
+        return out
+    return gemm(0, X, theta_part, Nrows, K, d, X.stride(0), theta_part.stride(0), out=out, ldc=ldp)
+
+
+def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias):
+    lib = _lib.load()
+    K = freqs.numel()
+    scratch = plan.scratch(K, False)
+    check(lib.fsw_embed_forward(dtype_code(plan.dtype), ptr(Xp), ldp, ptr(Ep), ptr(plan.rowptr), plan.n_fixed,
+                                ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
+                                plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(out), ld_out, out_col0,
+                                ptr(bias), plan.max_n_eff, ptr(scratch), 0 if scratch is None else scratch.numel(),
+                                stream_ptr(plan.device)), "fsw_embed_forward")
+
+
+def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_acc):
+    lib = _lib.load()
+    K = freqs.numel()
+    scratch = plan.scratch(K, True)
+    check(lib.fsw_embed_backward(dtype_code(plan.dtype), ptr(Xp), ldp, ptr(Ep), ptr(plan.rowptr), plan.n_fixed,
+                                 ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
+                                 plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(g), ld_g, g_col0,
+                                 ptr(dXp), ptr(dEp), ptr(dfreqs_acc), None, plan.max_n_eff, ptr(scratch),
+                                 0 if scratch is None else scratch.numel(), stream_ptr(plan.device)),
+          "fsw_embed_backward")
+
+
+def total_mass_function(T, name):
+    """fsw_embedding.py:857-865."""
+    if name == "identity":
+        return T
+    if name == "sqrt":
+        return 2 * (T / (torch.sqrt(T + 1) + 1))
+    if name == "log":
+        return torch.log1p(T)
+    raise RuntimeError("This should not happen")
+
+
+class FSWEmbedFunction(torch.autograd.Function):
+    """out[S, d_out] = [ total-mass channel | (1+xi_k) sum_j p_(j) D_j ] + bias   (+ autograd).
+
+    Forward: K1 projection(s) + K2 fused kernel.  Backward: K3 fused kernel + the three contractions
+    dX = dXp.theta, dtheta = dXp^T.X, and the edge-feature analogues.
+    Inputs that are None: E_feat, bias, tm_scale.  `tm_function` None disables the total-mass channel
+    ('plain' method only; the homogeneous variants are composed in torch by the caller).
+    """
+
+    @staticmethod
+    def forward(ctx, X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function):
+        d = X.shape[1]
+        K = projVecs.shape[0]
+        tm_dim = 0 if tm_function is None else 1
+        d_out = K + tm_dim
+        ldp = round_up(max(K, 1), 8)
+        X = X.contiguous()
+        theta_x = projVecs[:, :d]
+        Xp = project(X, theta_x, ldp)
+        Ep = None
+        if E_feat is not None:
+            E_feat = E_feat.contiguous()
+            Ep = project(E_feat, projVecs[:, d:], ldp)
+        out = torch.empty((plan.S, d_out), dtype=X.dtype, device=X.device)
+        bias_core = None
+        if bias is not None:
+            bias = bias.contiguous()
+            bias_core = bias[tm_dim:]
+        embed_forward(plan, Xp, ldp, Ep, freqs.contiguous(), out, d_out, tm_dim, bias_core)
+        fT = None
+        if tm_dim:
+            fT = total_mass_function(plan.mass_as(X.dtype), tm_function)
+            col0 = fT * tm_scale
+            if bias is not None:
+                col0 = col0 + bias[0]
+            out[:, 0] = col0
+        ctx.plan, ctx.ldp, ctx.tm_dim = plan, ldp, tm_dim
+        ctx.has_E, ctx.has_bias, ctx.has_scale = E_feat is not None, bias is not None, tm_scale is not None
+        ctx.save_for_backward(X, projVecs, freqs, Xp, Ep, E_feat, fT)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        X, projVecs, freqs, Xp, Ep, E_feat, fT = ctx.saved_tensors
+        plan, ldp, tm_dim = ctx.plan, ctx.ldp, ctx.tm_dim
+        need_X, need_theta, need_xi, need_bias, need_scale, need_E = ctx.needs_input_grad[:6]
+        d = X.shape[1]
+        K = projVecs.shape[0]
+        g = g.contiguous()
+        dX = dtheta = dxi = dbias = dscale = dE = None
+        if need_bias and ctx.has_bias:
+            dbias = g.sum(dim=0)
+        if need_scale and ctx.has_scale and tm_dim:
+            dscale = (g[:, 0] * fT).sum()
+        if (need_X or need_theta or need_xi or (need_E and ctx.has_E)) and K > 0 and plan.S > 0:
+            Nrows = X.shape[0]
+            # dXp is accumulated with atomics in graph mode -> must start from zero
+            dXp = torch.zeros((Nrows, ldp), dtype=X.dtype, device=X.device) if plan.col is not None \
+                else torch.empty((Nrows, ldp), dtype=X.dtype, device=X.device)
+            if plan.col is None and ldp != K:
+                dXp.zero_()
+            dEp = torch.zeros((plan.E, ldp), dtype=X.dtype, device=X.device) if ctx.has_E else None
+            dxi_acc = torch.zeros(K, dtype=torch.float64, device=X.device) if need_xi else None
+            embed_backward(plan, Xp, ldp, Ep, freqs.contiguous(), g, g.shape[1], tm_dim, dXp, dEp, dxi_acc)
+            if need_xi:
+                dxi = dxi_acc.to(X.dtype)
+            if need_X:
+                dX = gemm(1, dXp, projVecs, Nrows, d, K, ldp, projVecs.stride(0))
+            if need_theta:
+                dtheta = torch.zeros_like(projVecs)
+                gemm(2, dXp, X, K, d, Nrows, ldp, X.stride(0), out=dtheta, ldc=dtheta.stride(0), accumulate=True)
+            if ctx.has_E:
+                de = E_feat.shape[1]
+                if need_E:
+                    dE = gemm(1, dEp, projVecs[:, d:], plan.E, de, K, ldp, projVecs.stride(0))
+                if need_theta:
+                    gemm(2, dEp, E_feat, K, de, plan.E, ldp, E_feat.stride(0), out=dtheta[:, d:], ldc=dtheta.stride(0),
+                         accumulate=True)
+        else:
+            if need_X:
+                dX = torch.zeros_like(X)
+            if need_theta:
+                dtheta = torch.zeros_like(projVecs)
+            if need_xi:
+                dxi = torch.zeros_like(freqs)
+        return dX, dtheta, dxi, dbias, dscale, dE, None, None
+
+
+def fsw_embed(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function):
+    return FSWEmbedFunction.apply(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function)
+
+
+# ------------------------------------------------------------------------------------------------
+# Segmented cumulative sum (public function of the reference, fsw_embedding.py:2795)
+# ------------------------------------------------------------------------------------------------
+def segcumsum_cuda(values, segment_ids, in_place=False):
+    lib = _lib.load()
+    _lib.require_cuda(values, "values")
+    out = values if in_place else torch.empty_like(values, memory_format=torch.contiguous_format)
+    vin = values if values.is_contiguous() else values.contiguous()
+    n = vin.numel()
+    if n == 0:
+        return out
+    ws = _ws(lib.fsw_segcumsum_workspace_bytes(n), values.device)
+    check(lib.fsw_segcumsum(dtype_code(values.dtype), ptr(vin), ptr(out), ptr(segment_ids), segment_ids.element_size(), n,
+                            ptr(ws), ws.numel(), stream_ptr(values.device)), "fsw_segcumsum")
+    return out

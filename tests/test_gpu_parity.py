@@ -1,0 +1,448 @@
+"""GPU parity tests: the CUDA path (through the host modules and the C ABI of libfsw_embedding.so)
+against (a) the golden vectors of the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances (north star): fp32 results within rel 1e-5 / abs 1e-6 of the reference evaluated in fp64
+(the reference's own fp32 path is 5e-5..1e-4 away from its fp64 result, SURVEY.md 7 hard part 2 - the
+committed *_f32 arrays are that noise floor and are reported, not asserted); fp64 results within
+1e-9 / 1e-10.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import coo_to_csr, load_golden
+
+pytestmark = pytest.mark.gpu
+
+F32 = dict(rtol=1e-5, atol=1e-6)
+# gradients are sums of many O(1) terms: same relative bar, absolute bar scaled to the gradient size
+F64 = dict(rtol=1e-9, atol=1e-10)
+DT = {"f32": torch.float32, "f64": torch.float64}
+
+
+def tol(tag, ref):
+    if tag == "f64":
+        return F64
+    return F32
+
+
+def gtol(tag, ref):
+    """gradient tolerance: rel 1e-5 of the largest entry (entries are sums over slices / segments)"""
+    if tag == "f64":
+        return dict(rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(ref).max())))
+    return dict(rtol=1e-5, atol=1e-6 + 1e-5 * float(np.abs(ref).max()))
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def t(a, dtype):
+    return torch.as_tensor(np.asarray(a), dtype=dtype, device=dev())
+
+
+def load_emb_state(mod, g, prefix="param_"):
+    sd = {}
+    for k in mod.state_dict().keys():
+        sd[k] = t(g[prefix + k], mod.state_dict()[k].dtype)
+    mod.load_state_dict(sd)
+
+
+# ------------------------------------------------------------------------------------------------
+DENSE = {
+    "emb_dense_weighted": dict(d_in=4, d_out=9),
+    "emb_dense_unit": dict(d_in=3, d_out=16),
+    "emb_dense_uniform": dict(d_in=3, d_out=6),
+    "emb_dense_deficient_tm": dict(d_in=2, d_out=7, encode_total_mass=True, total_mass_encoding_function="sqrt",
+                                   learnable_total_mass_encoding_scale=True),
+    "emb_dense_n1": dict(d_in=5, d_out=8),
+    "emb_dense_big": dict(d_in=3, d_out=32, freqs_init="spread"),
+}
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", list(DENSE))
+def test_dense_embedding(name, tag):
+    from fsw_gnn_b200 import FSW_embedding
+    g = load_golden(name)
+    dtype = DT[tag]
+    mod = FSW_embedding(device=dev(), dtype=dtype, learnable_slices=True, learnable_freqs=True, **DENSE[name])
+    load_emb_state(mod, g)
+    X = t(g["X"], dtype).requires_grad_(True)
+    mode = str(g["Wmode"])
+    W = t(g["W"], dtype) if mode == "tensor" else mode
+    out = mod(X, W)
+    ref = g["out_f64"]
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, **tol(tag, ref))
+    (out * t(g["gout"], dtype)).sum().backward()
+    np.testing.assert_allclose(X.grad.cpu().numpy(), g["dX_f64"], **gtol(tag, g["dX_f64"]))
+    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), g["dprojVecs_f64"], **gtol(tag, g["dprojVecs_f64"]))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), g["dfreqs_f64"], **gtol(tag, g["dfreqs_f64"]))
+    if "dbias_f64" in g:
+        np.testing.assert_allclose(mod.bias.grad.cpu().numpy(), g["dbias_f64"], **gtol(tag, g["dbias_f64"]))
+
+
+GRAPH = {
+    "emb_graph_unit": dict(d_in=5, d_out=10),
+    "emb_graph_weighted": dict(d_in=5, d_out=10, encode_total_mass=True, total_mass_encoding_function="log",
+                               learnable_total_mass_encoding_scale=True),
+    "emb_graph_homog": dict(d_in=4, d_out=8, encode_total_mass=True, total_mass_encoding_method="homog", enable_bias=False),
+}
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", list(GRAPH))
+def test_sparse_graph_embedding(name, tag):
+    from fsw_gnn_b200 import FSW_embedding
+    g = load_golden(name)
+    dtype = DT[tag]
+    mod = FSW_embedding(device=dev(), dtype=dtype, learnable_slices=True, learnable_freqs=True, **GRAPH[name])
+    load_emb_state(mod, g)
+    S, N = [int(v) for v in g["A_shape"]]
+    A = torch.sparse_coo_tensor(torch.as_tensor(g["A_indices"], device=dev()), t(g["A_values"], dtype), (S, N)).coalesce()
+    X = t(g["X"], dtype).requires_grad_(True)
+    out = mod(X, A, graph_mode=True)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_f64"], **tol(tag, g["out_f64"]))
+    (out * t(g["gout"], dtype)).sum().backward()
+    np.testing.assert_allclose(X.grad.cpu().numpy(), g["dX_f64"], **gtol(tag, g["dX_f64"]))
+    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), g["dprojVecs_f64"], **gtol(tag, g["dprojVecs_f64"]))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), g["dfreqs_f64"], **gtol(tag, g["dfreqs_f64"]))
+    if "dscale_f64" in g:
+        np.testing.assert_allclose(mod.total_mass_encoding_scale.grad.cpu().numpy(), g["dscale_f64"], **gtol(tag, g["dscale_f64"]))
+
+
+def test_dense_graph_mode_equals_sparse():
+    """graph_mode with a dense adjacency == the same adjacency as sparse COO (fsw_embedding.py:603-605)."""
+    from fsw_gnn_b200 import FSW_embedding
+    g = load_golden("emb_graph_weighted")
+    mod = FSW_embedding(device=dev(), dtype=torch.float64, **GRAPH["emb_graph_weighted"])
+    load_emb_state(mod, g)
+    S, N = [int(v) for v in g["A_shape"]]
+    A = torch.sparse_coo_tensor(torch.as_tensor(g["A_indices"], device=dev()), t(g["A_values"], torch.float64), (S, N)).coalesce()
+    X = t(g["X"], torch.float64)
+    out_sparse = mod(X, A, graph_mode=True)
+    out_dense = mod(X, A.to_dense(), graph_mode=True)
+    np.testing.assert_allclose(out_dense.detach().cpu().numpy(), out_sparse.detach().cpu().numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(out_dense.detach().cpu().numpy(), g["out_f64"], **F64)
+
+
+# ------------------------------------------------------------------------------------------------
+CONV = {
+    "conv_default": dict(args=(6, 5), kw={}),
+    "conv_selfloop_gcn": dict(args=(5, 7), kw=dict(self_loop_weight=0.2, edge_weighting="gcn", vertex_degree_encoding_function="log",
+                                                     learnable_vertex_degree_encoding_scale=True, mlp_layers=2)),
+    "conv_edgefeat": dict(args=(5, 6), kw=dict(edgefeat_dim=3, mlp_layers=3)),
+    "conv_homog_nomlp": dict(args=(4, 6), kw=dict(mlp_layers=0, bias=False, homog_degree_encoding=True)),
+    "conv_wide": dict(args=(8, 8), kw=dict(embed_dim=40)),
+}
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", list(CONV))
+def test_conv(name, tag):
+    from fsw_gnn_b200 import FSW_conv
+    g = load_golden(name)
+    dtype = DT[tag]
+    torch.manual_seed(0)
+    mod = FSW_conv(*CONV[name]["args"], device=dev(), dtype=dtype, **CONV[name]["kw"])
+    load_emb_state(mod, g)
+    x = t(g["x"], dtype).requires_grad_(True)
+    ei = torch.as_tensor(g["edge_index"], device=dev())
+    ef = t(g["edge_features"], dtype).requires_grad_(True) if "edge_features" in g else None
+    out = mod(x, ei, edge_features=ef)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_f64"], **tol(tag, g["out_f64"]))
+    (out * t(g["gout"], dtype)).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["dx_f64"], **gtol(tag, g["dx_f64"]))
+    if ef is not None:
+        np.testing.assert_allclose(ef.grad.cpu().numpy(), g["def_f64"], **gtol(tag, g["def_f64"]))
+    for pn, p in mod.named_parameters():
+        key = "grad_%s_f64" % pn
+        if key in g:
+            assert p.grad is not None, pn
+            np.testing.assert_allclose(p.grad.cpu().numpy(), g[key], err_msg=pn, **gtol(tag, g[key]))
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_readout(tag):
+    from fsw_gnn_b200 import FSW_readout
+    g = load_golden("readout_default")
+    dtype = DT[tag]
+    mod = FSW_readout(6, 4, concat_self=False, device=dev(), dtype=dtype)
+    load_emb_state(mod, g)
+    x = t(g["x"], dtype).requires_grad_(True)
+    gi = torch.as_tensor(g["graph_index"], device=dev())
+    out = mod(x, graph_index=gi, batch_size=int(g["out_f64"].shape[0]))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_f64"], **tol(tag, g["out_f64"]))
+    (out * t(g["gout"], dtype)).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["dx_f64"], **gtol(tag, g["dx_f64"]))
+
+
+@pytest.mark.parametrize("name", ["emb_cartesian", "emb_cartesian_collapse"])
+def test_cartesian(name):
+    from fsw_gnn_b200 import FSW_embedding
+    g = load_golden(name)
+    mod = FSW_embedding(d_in=4, nSlices=5, nFreqs=3, collapse_freqs=(name.endswith("collapse")), device=dev(), dtype=torch.float64)
+    load_emb_state(mod, g)
+    out = mod(t(g["X"], torch.float64), t(g["W"], torch.float64))
+    assert tuple(out.shape) == tuple(g["out_f64"].shape)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_f64"], **F64)
+
+
+# ------------------------------------------------------------------------------------------------
+# segmented cumulative sum
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+def test_segcumsum_single_pass(tag, idt):
+    from fsw_gnn_b200 import segcumsum
+    g = load_golden("segcumsum")
+    v = t(g["values_" + tag], DT[tag])
+    ids = torch.as_tensor(g["segment_ids"], device=dev()).to(idt)
+    out = segcumsum(v, ids)
+    ref = g["out_slow_" + tag]
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=(1e-12 if tag == "f64" else 2e-6), atol=(1e-12 if tag == "f64" else 2e-6))
+    v2 = v.clone()
+    out2 = segcumsum(v2, ids, in_place=True)
+    assert out2.data_ptr() == v2.data_ptr()
+    assert torch.equal(out2, out)
+
+
+def test_segcumsum_long_segments_many_tiles():
+    """segments spanning many 2048-element tiles exercise the decoupled look-back chain"""
+    from fsw_gnn_b200 import segcumsum
+    rng = np.random.default_rng(0)
+    lens = np.concatenate([[50000], rng.integers(1, 30, 2000), [9000], rng.integers(1, 5000, 40)])
+    ids = np.repeat(np.arange(len(lens)), lens)
+    vals = rng.integers(-3, 4, ids.shape[0]).astype(np.float64)  # small integers: every association order is exact
+    ref = np.concatenate([np.cumsum(vals[a:b]) for a, b in zip(np.cumsum(lens) - lens, np.cumsum(lens))])
+    for dtype in (torch.float32, torch.float64):
+        out = segcumsum(t(vals, dtype), torch.as_tensor(ids, device=dev()))
+        assert np.array_equal(out.cpu().numpy().astype(np.float64), ref)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_segcumsum_legacy_abi(tag):
+    """Drive the reference's hierarchy (fsw_embedding.py:2878-3012) through the legacy symbols."""
+    import ctypes
+    from fsw_gnn_b200 import _lib
+    lib = _lib.load()
+    g = load_golden("segcumsum")
+    dtype = DT[tag]
+    values = t(g["values_" + tag], dtype)
+    ids = torch.as_tensor(g["segment_ids"], device=dev())
+    n = values.numel()
+    tpb = min(max(64, (n + 31) // 32), 256)
+    sizes, nblocks = [n], []
+    while sizes[-1] > tpb:
+        sizes.append((sizes[-1] + tpb - 1) // tpb)
+        nblocks.append(sizes[-1])
+    nblocks.append(1)
+    outs = [values.clone()] + [torch.empty(s, dtype=dtype, device=dev()) for s in sizes[1:]]
+    idl = [ids] + [torch.empty(s, dtype=torch.int64, device=dev()) for s in sizes[1:]]
+    code = 0 if tag == "f32" else 1
+    for i, s in enumerate(sizes):
+        nxt = i < len(sizes) - 1
+        lib.segcumsum_wrapper(code, outs[i].data_ptr(), idl[i].data_ptr(), s, 1 << 20,
+                              outs[i + 1].data_ptr() if nxt else None, idl[i + 1].data_ptr() if nxt else None,
+                              nxt, nblocks[i], tpb, tpb * (4 if tag == "f32" else 8))
+    for i in reversed(range(len(sizes) - 1)):
+        lib.add_block_sums_wrapper(code, outs[i].data_ptr(), outs[i + 1].data_ptr(), idl[i].data_ptr(), idl[i + 1].data_ptr(),
+                                   sizes[i], nblocks[i], tpb)
+    torch.cuda.synchronize()
+    ref = g["out_slow_" + tag]
+    np.testing.assert_allclose(outs[0].cpu().numpy(), ref, rtol=(1e-12 if tag == "f64" else 2e-6), atol=(1e-12 if tag == "f64" else 2e-6))
+    assert lib.get_max_threads_per_block(0) == 1024
+
+
+# ------------------------------------------------------------------------------------------------
+# graph preparation (index work: exact)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("self_loops", [0.0, 0.3])
+@pytest.mark.parametrize("weighting", ["unit", "gcn"])
+def test_csr_matches_oracle(self_loops, weighting):
+    from fsw_gnn_b200.graph import GraphCSR
+    from oracle import fsw_oracle as O
+    rng = np.random.default_rng(3)
+    N, E = 300, 4000
+    ei = rng.integers(0, N, (2, E))
+    ei[1][ei[1] == 7] = 8  # an empty row
+    if weighting == "gcn" and self_loops == 0.0:
+        ei[0][ei[0] == 7] = 9  # a vertex without in-edges must not be a source under gcn weighting (1/sqrt(0))
+    csr = GraphCSR(torch.as_tensor(ei, device=dev()), N, self_loops, weighting, torch.float64)
+    rowptr = csr.rowptr.cpu().numpy().astype(np.int64)
+    col = csr.col.cpu().numpy()
+    eid = csr.eid.cpu().numpy()
+    W = csr.W.cpu().numpy() if csr.W is not None else np.ones(len(col))
+    o_rowptr, o_col, o_W, o_deg, _ = O.edge_index_to_csr(ei, N, self_loops, weighting)
+    # segment offsets: the oracle merges duplicate edges, we keep them -> compare degrees with multiplicity
+    src = np.concatenate([ei[0], np.arange(N)]) if self_loops > 0 else ei[0]
+    dst = np.concatenate([ei[1], np.arange(N)]) if self_loops > 0 else ei[1]
+    assert np.array_equal(np.diff(rowptr), np.bincount(dst, minlength=N))
+    # every slot points back at its own edge
+    assert np.array_equal(np.sort(eid), np.arange(len(src)))
+    assert np.array_equal(col, src[eid])
+    for v in range(N):
+        assert np.all(dst[eid[rowptr[v]:rowptr[v + 1]]] == v)
+    np.testing.assert_allclose(csr.in_degrees.cpu().numpy(), o_deg, rtol=1e-14)
+    # per (dst, src) weight sums equal the coalesced reference weights
+    agg = {}
+    for v in range(N):
+        for p in range(rowptr[v], rowptr[v + 1]):
+            agg[(v, col[p])] = agg.get((v, col[p]), 0.0) + W[p]
+    ref = {}
+    for v in range(N):
+        for p in range(o_rowptr[v], o_rowptr[v + 1]):
+            ref[(v, o_col[p])] = o_W[p]
+    assert agg.keys() == ref.keys()
+    for k in ref:
+        assert abs(agg[k] - ref[k]) <= 1e-12 * max(1.0, abs(ref[k]))
+
+
+def test_plan_buckets():
+    from fsw_gnn_b200.ops import SegmentPlan
+    rng = np.random.default_rng(0)
+    lens = np.concatenate([rng.integers(0, 70, 500), [129, 300, 1500, 0, 0, 64, 65]])
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    W = rng.random(int(rowptr[-1])) + 0.5
+    W[rowptr[10]:rowptr[11]] = 0.25  # uniform weights but small mass for short segments
+    plan = SegmentPlan(len(lens), int(rowptr[-1]), torch.as_tensor(rowptr, device=dev()), 0, None,
+                       torch.as_tensor(W, device=dev()), 1.0, torch.float64, dev())
+    mass = plan.mass.cpu().numpy()
+    info = plan.info.cpu().numpy()
+    order = plan.order.cpu().numpy()
+    ref_mass = np.array([W[a:b].sum() for a, b in zip(rowptr[:-1], rowptr[1:])])
+    np.testing.assert_allclose(mass, ref_mass, rtol=1e-14)
+    n_eff = lens + (ref_mass < 1.0)
+    assert np.array_equal(info & ((1 << 30) - 1), n_eff)
+    uni = np.array([(b > a) and np.all(W[a:b] == W[a]) and m >= 1.0 for a, b, m in zip(rowptr[:-1], rowptr[1:], ref_mass)])
+    assert np.array_equal((info >> 30) & 1, uni.astype(np.int64))
+    assert np.array_equal(np.sort(order), np.arange(len(lens)))
+    bo = np.array(list(plan.bucket_offsets))
+    assert bo[144] == len(lens) and bo[145] == n_eff.max() and plan.max_n_eff == n_eff.max()
+
+    def bucket(ne):
+        if ne <= 64:
+            return ne
+        for i, c in enumerate([128, 256, 512, 1024, 2048, 4096]):
+            if ne <= c:
+                return 65 + i
+        return 71
+    for b in range(144):
+        for s in order[bo[b]:bo[b + 1]]:
+            assert (0 if uni[s] else 72) + bucket(n_eff[s]) == b
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA path vs oracle on seeded random inputs (moderate sizes; all size classes incl. generic/scratch)
+# ------------------------------------------------------------------------------------------------
+def _random_graph_case(seed, N, degs, d, K, weighted, dtype, thresh=1.0):
+    from fsw_gnn_b200 import FSW_embedding
+    from fsw_gnn_b200.ops import SegmentPlan
+    from oracle import fsw_oracle as O
+    rng = np.random.default_rng(seed)
+    S = len(degs)
+    rowptr = np.concatenate([[0], np.cumsum(degs)]).astype(np.int64)
+    Etot = int(rowptr[-1])
+    col = rng.integers(0, N, Etot)
+    X = rng.standard_normal((N, d))
+    W = (rng.random(Etot) + 0.1) if weighted else None
+    torch.manual_seed(seed)
+    mod = FSW_embedding(d_in=d, d_out=K, device=dev(), dtype=dtype, freqs_init="spread", learnable_slices=True, learnable_freqs=True,
+                        total_mass_pad_thresh=thresh)
+    theta = mod.projVecs.detach().cpu().numpy().astype(np.float64)
+    xi = mod.freqs.detach().cpu().numpy().astype(np.float64)
+    plan = SegmentPlan(S, Etot, torch.as_tensor(rowptr.astype(np.int32), device=dev()), 0,
+                       torch.as_tensor(col.astype(np.int32), device=dev()),
+                       None if W is None else t(W, dtype), thresh, dtype, dev())
+    Xt = t(X, dtype).requires_grad_(True)
+    out = mod.embed_plan(Xt, plan)
+    gout = rng.standard_normal((S, K))
+    (out * t(gout, dtype)).sum().backward()
+    Xq = Xt.detach().cpu().numpy().astype(np.float64)   # the oracle sees the same (rounded) inputs
+    Wq = None if W is None else t(W, dtype).cpu().numpy().astype(np.float64)
+    ref = O.fsw_embed_csr(Xq, rowptr, col, Wq, theta, xi, thresh=thresh) + mod.bias.detach().cpu().numpy().astype(np.float64)
+    rb = O.fsw_embed_csr_backward(Xq, rowptr, col, Wq, theta, xi, gout, thresh=thresh)
+    return out.detach().cpu().numpy(), ref, Xt.grad.cpu().numpy(), rb, mod
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_random_graph_vs_oracle(tag, weighted):
+    rng = np.random.default_rng(11)
+    degs = np.concatenate([rng.integers(0, 12, 60), rng.integers(12, 70, 40), [100, 129, 257, 600, 1100, 2300]])
+    out, ref, dX, rb, mod = _random_graph_case(5, 400, degs, 6, 37, weighted, DT[tag])
+    np.testing.assert_allclose(out, ref, **tol(tag, ref))
+    np.testing.assert_allclose(dX, rb["dX"], **gtol(tag, rb["dX"]))
+    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), rb["dtheta"], **gtol(tag, rb["dtheta"]))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], **gtol(tag, rb["dxi"]))
+
+
+def test_high_pad_threshold_vs_oracle():
+    """pad threshold 5: every segment with fewer than 5 unit-weight elements is padded (general path)"""
+    degs = np.array([0, 1, 2, 3, 4, 5, 6, 9, 20, 33, 70])
+    out, ref, dX, rb, mod = _random_graph_case(9, 50, degs, 4, 21, False, torch.float64, thresh=5.0)
+    np.testing.assert_allclose(out, ref, **F64)
+    np.testing.assert_allclose(dX, rb["dX"], **gtol("f64", rb["dX"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at the BASELINE shapes
+# ------------------------------------------------------------------------------------------------
+def test_conv_config2_properties():
+    """demo_conv-shaped case (N=10k, E=100k, d=64): permutation invariance of the edge list,
+    positive homogeneity of the embedding, and an oracle check on a row subsample."""
+    from fsw_gnn_b200 import FSW_conv
+    from oracle import fsw_oracle as O
+    torch.manual_seed(0)
+    N, E, d = 10000, 100000, 64
+    conv = FSW_conv(d, d, device=dev())
+    x = torch.randn(N, d, device=dev())
+    ei = torch.randint(0, N, (2, E), device=dev())
+    emb_mod = conv.fsw_embed
+    out = conv(x, ei)
+    perm = torch.randperm(E, device=dev())
+    out_p = conv(x, ei[:, perm].contiguous())
+    assert torch.allclose(out, out_p, rtol=1e-5, atol=1e-6)
+    # homogeneity of the neighbourhood embedding (all but the degree channel): E(a X) = a E(X)
+    from fsw_gnn_b200.graph import cached_graph
+    csr, plan = cached_graph(ei, N, 0, "unit", 1.0, torch.float32)
+    e1 = emb_mod.embed_plan(x, plan)
+    e4 = emb_mod.embed_plan(4.0 * x, plan)
+    assert torch.allclose(e4[:, 1:], 4.0 * e1[:, 1:], rtol=1e-5, atol=1e-5)
+    assert torch.equal(e4[:, 0], e1[:, 0])
+    # total-mass channel = in-degree (with multiplicity)
+    deg = torch.bincount(ei[1], minlength=N).to(torch.float32)
+    assert torch.equal(e1[:, 0], deg)
+    # oracle on 40 rows
+    rows = np.arange(0, N, N // 40)
+    rowptr = csr.rowptr.cpu().numpy().astype(np.int64)
+    col = csr.col.cpu().numpy()
+    sub_ptr = np.concatenate([[0], np.cumsum(np.diff(rowptr)[rows])])
+    sub_col = np.concatenate([col[rowptr[r]:rowptr[r + 1]] for r in rows])
+    ref = O.fsw_embed_csr(x.cpu().numpy().astype(np.float64), sub_ptr, sub_col, None,
+                          emb_mod.projVecs.detach().cpu().numpy().astype(np.float64),
+                          emb_mod.freqs.detach().cpu().numpy().astype(np.float64))
+    got = e1[torch.as_tensor(rows, device=dev()), 1:].detach().cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
+
+
+def test_pointcloud_config3_properties():
+    """256 x 1024 x 3 -> 256 (ModelNet-shaped): point-order invariance, homogeneity, batch independence,
+    oracle on two multisets."""
+    from fsw_gnn_b200 import FSW_embedding
+    from oracle import fsw_oracle as O
+    torch.manual_seed(0)
+    B, n, d, K = 256, 1024, 3, 256
+    mod = FSW_embedding(d, K, device=dev())
+    X = torch.randn(B, n, d, device=dev())
+    out = mod(X)
+    assert tuple(out.shape) == (B, K)
+    perm = torch.randperm(n, device=dev())
+    assert torch.allclose(mod(X[:, perm].contiguous()), out, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(mod(3.0 * X), 3.0 * out, rtol=1e-5, atol=1e-5)
+    assert torch.equal(mod(X[7:9].contiguous()), out[7:9])
+    rowptr, col = O.dense_to_csr(2, n)
+    ref = O.fsw_embed_csr(X[:2].reshape(-1, d).cpu().numpy().astype(np.float64), rowptr, col, None,
+                          mod.projVecs.detach().cpu().numpy().astype(np.float64),
+                          mod.freqs.detach().cpu().numpy().astype(np.float64))
+    np.testing.assert_allclose(out[:2].detach().cpu().numpy(), ref + mod.bias.detach().cpu().numpy(), rtol=1e-5, atol=2e-6)
