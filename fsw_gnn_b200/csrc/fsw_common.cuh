@@ -93,6 +93,25 @@ __device__ __forceinline__ T fsw_dsinc(T x) {
     return (Num<T>::cospi_(x) - fsw_sinc(x)) / x;
 }
 
+// Amplitude of one element of normalised weight w at frequency xi:
+//   a  = 2 w sinc(xi w)          (so that D_j = a cos(pi xi (2C - w)), fsw_embedding.py:1047-1075)
+//   ap = da/dxi = 2 w^2 sinc'(xi w)
+// x = xi*w is passed in DOUBLE: for large xi*w the numerator sin(pi x) needs the phase reduced mod 2
+// before it is rounded to fp32 (same reason as for the cosine phase).
+template <typename T, bool NEED_AP>
+__device__ __forceinline__ void fsw_amplitude(double x, T w, T xi, T& a, T& ap) {
+    if (fabs(x) < 0.25) {
+        const T xf = (T)x;
+        a = (T)2 * w * fsw_sinc(xf);
+        if (NEED_AP) ap = (T)2 * w * w * fsw_dsinc(xf);
+    } else {
+        const T r = Num<T>::reduce(x);
+        const T sincx = Num<T>::sinpi_(r) / ((T)M_PI * (T)x);
+        a = (T)2 * w * sincx;
+        if (NEED_AP) ap = (T)2 * w * (Num<T>::cospi_(r) - sincx) / xi;
+    }
+}
+
 // Arguments shared by the forward and backward embedding kernels.
 template <typename T>
 struct SegArgs {

@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(128) fsw_fwd_small_kernel(SegArgs<T> a, int se
 #pragma unroll
                 for (int j = 0; j < NP; ++j)
                     coef[j] = (j < n) ? Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * j + 1))) : (T)0;
-                const T wn = (T)(1.0 / (double)n);
-                A = ((T)1 + xi) * (T)2 * wn * fsw_sinc((T)u);
+                T a0, a0p;
+                fsw_amplitude<T, false>(u, (T)(1.0 / (double)n), xi, a0, a0p);
+                A = ((T)1 + xi) * a0;
                 n_prev = n;
             }
             fsw_sort_network<NP>([&](int i, int l) {
@@ -190,8 +191,8 @@ __global__ void __launch_bounds__(128) fsw_fwd_small_kernel(SegArgs<T> a, int se
                     const double wn = wr * invS;
                     const double phi = xid * (2.0 * Craw * invS - wn);
                     const T c = Num<T>::cospi_(Num<T>::reduce(phi));
-                    const T wnf = (T)wn;
-                    const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                    T aj, ajp;
+                    fsw_amplitude<T, false>(xid * wn, (T)wn, xi, aj, ajp);
                     acc = fma(key[j], aj * c, acc);
                 }
             }
@@ -290,8 +291,7 @@ __global__ void __launch_bounds__(128) fsw_bwd_small_kernel(SegArgs<T> a, int se
                         if (NEED_DXI) sm_t[j * 32 + lane] = (T)M_PI * wn * (T)(2 * j + 1) * Num<T>::sinpi_(r);
                     }
                 }
-                A0 = (T)2 * wn * fsw_sinc((T)u);
-                if (NEED_DXI) A0p = (T)2 * wn * wn * fsw_dsinc((T)u);
+                fsw_amplitude<T, NEED_DXI>(u, wn, xi, A0, A0p);
                 n_prev = n;
             }
             T Sc = (T)0, Ss = (T)0;
@@ -336,13 +336,13 @@ __global__ void __launch_bounds__(128) fsw_bwd_small_kernel(SegArgs<T> a, int se
                     const double two_c_minus_w = 2.0 * Craw * invS - wn;
                     const T r = Num<T>::reduce(xid * two_c_minus_w);
                     const T c = Num<T>::cospi_(r);
-                    const T wnf = (T)wn;
-                    const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                    T aj, ajp = (T)0;
+                    fsw_amplitude<T, NEED_DXI>(xid * wn, (T)wn, xi, aj, ajp);
                     const T D = aj * c;
                     sm_val[id * 32 + lane] = Gk * D;
                     if (NEED_DXI) {
                         const T sn = Num<T>::sinpi_(r);
-                        const T dD = (T)2 * wnf * wnf * fsw_dsinc(xi * wnf) * c - aj * (T)M_PI * (T)two_c_minus_w * sn;
+                        const T dD = ajp * c - aj * (T)M_PI * (T)two_c_minus_w * sn;
                         sPD = fma(key[j], D, sPD);
                         sPdD = fma(key[j], dD, sPdD);
                     }
@@ -467,8 +467,9 @@ __global__ void __launch_bounds__(256) fsw_fwd_generic_kernel(SegArgs<T> a, int 
                 const T c = Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * r + 1)));
                 acc += (double)(keys[r * 32 + lane] * c);
             }
-            const T wn = (T)(1.0 / (double)n);
-            acc *= (double)(((T)1 + xi) * (T)2 * wn * fsw_sinc((T)u));
+            T a0, a0p;
+            fsw_amplitude<T, false>(u, (T)(1.0 / (double)n), xi, a0, a0p);
+            acc *= (double)(((T)1 + xi) * a0);
         } else {
             const double Ts = a.mass[s];
             const double invS = 1.0 / fmax(Ts, a.thresh);
@@ -489,8 +490,8 @@ __global__ void __launch_bounds__(256) fsw_fwd_generic_kernel(SegArgs<T> a, int 
                 Craw += wr;
                 const double wn = wr * invS;
                 const T c = Num<T>::cospi_(Num<T>::reduce(xid * (2.0 * Craw * invS - wn)));
-                const T wnf = (T)wn;
-                const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                T aj, ajp;
+                fsw_amplitude<T, false>(xid * wn, (T)wn, xi, aj, ajp);
                 acc += (double)(keys[r * 32 + lane] * (aj * c));
             }
             acc *= (double)((T)1 + xi);
@@ -565,8 +566,8 @@ __global__ void __launch_bounds__(256) fsw_bwd_generic_kernel(SegArgs<T> a, int 
         if (UNIFORM) {
             const double u = xid / (double)n;
             const T wn = (T)(1.0 / (double)n);
-            const T A0 = (T)2 * wn * fsw_sinc((T)u);
-            const T A0p = NEED_DXI ? (T)2 * wn * wn * fsw_dsinc((T)u) : (T)0;
+            T A0, A0p = (T)0;
+            fsw_amplitude<T, NEED_DXI>(u, wn, xi, A0, A0p);
             double Sc = 0.0, Ss = 0.0;
             for (int r = r0; r < r1; ++r) {
                 const T rr = Num<T>::reduce(u * (double)(2 * r + 1));
@@ -603,14 +604,14 @@ __global__ void __launch_bounds__(256) fsw_bwd_generic_kernel(SegArgs<T> a, int 
                 const double tcw = 2.0 * Craw * invS - wn;
                 const T rr = Num<T>::reduce(xid * tcw);
                 const T c = Num<T>::cospi_(rr);
-                const T wnf = (T)wn;
-                const T aj = (T)2 * wnf * fsw_sinc(xi * wnf);
+                T aj, ajp = (T)0;
+                fsw_amplitude<T, NEED_DXI>(xid * wn, (T)wn, xi, aj, ajp);
                 const T D = aj * c;
                 const T p = keys[r * 32 + lane];
                 keys[r * 32 + lane] = Gk * D;
                 if (NEED_DXI) {
                     const T sn = Num<T>::sinpi_(rr);
-                    const T dD = (T)2 * wnf * wnf * fsw_dsinc(xi * wnf) * c - aj * (T)M_PI * (T)tcw * sn;
+                    const T dD = ajp * c - aj * (T)M_PI * (T)tcw * sn;
                     sPD += (double)(p * D);
                     sPdD += (double)(p * dD);
                 }
@@ -714,7 +715,7 @@ int launch_bwd_small(const SegArgs<T>& a, int lo, int hi, const T* g, int64_t ld
     const int64_t blocks = fsw_cdiv(warps, 4);
     const size_t smem = (size_t)4 * 3 * NP * 32 * sizeof(T);
     auto kern = fsw_bwd_small_kernel<T, NP, UNIFORM, NEED_DXI>;
-    if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, 128, smem, st>>>(a, lo, hi, G, nchunks, g, ld_g, g_col0, dXp, dEp, dfreqs);
     FSW_CHECK_LAUNCH("fsw_bwd_small_kernel");
     return FSW_OK;
@@ -803,11 +804,11 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
             }
             if (kind == 0) {
                 auto kern = fsw_fwd_generic_kernel<T, 0>;
-                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, out, ld_out, out_col0, bias, cap, gs);
             } else {
                 auto kern = fsw_fwd_generic_kernel<T, 1>;
-                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, out, ld_out, out_col0, bias, cap, gs);
             }
             FSW_CHECK_LAUNCH("fsw_fwd_generic_kernel");
@@ -853,11 +854,11 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             }
             if (kind == 0) {
                 auto kern = fsw_bwd_generic_kernel<T, true, NEED_DXI>;
-                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);
             } else {
                 auto kern = fsw_bwd_generic_kernel<T, false, NEED_DXI>;
-                if (smem > 48 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);
             }
             FSW_CHECK_LAUNCH("fsw_bwd_generic_kernel");

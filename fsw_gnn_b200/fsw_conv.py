@@ -179,7 +179,8 @@ class FSW_conv(_Base):
             assert edge_features is None, "Edge features should not be provided since edgefeat_dim = 0"
 
         csr, plan = _graph.cached_graph(edge_index, n, self.self_loop_weight, self.edge_weighting,
-                                        emb_mod.total_mass_pad_thresh, vertex_features.dtype, use_cache=self.cache_graph)
+                                        emb_mod.total_mass_pad_thresh, vertex_features.dtype, use_cache=self.cache_graph,
+                                        coalesce=(edge_features is not None))
         E_feat = csr.edge_features_in_slot_order(edge_features) if edge_features is not None else None
         emb = emb_mod.embed_plan(vertex_features, plan, E_feat)
         return self._combine(emb, vertex_features)

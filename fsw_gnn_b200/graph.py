@@ -58,7 +58,15 @@ def plan_from_coo(indices, values, shape, graph_mode, thresh, dtype):
 class GraphCSR:
     """Destination-major CSR of a graph given as edge_index (fsw_conv.py:384-409)."""
 
-    def __init__(self, edge_index, num_vertices, self_loop_weight, edge_weighting, dtype):
+    def __init__(self, edge_index, num_vertices, self_loop_weight, edge_weighting, dtype, coalesce=False):
+        """coalesce=False: duplicate (dst, src) pairs stay separate elements (exact for the embedding and
+        its gradients, see include/fsw_embedding.h section 3).  coalesce=True merges them like the
+        reference's `coalesce()` (fsw_conv.py:397-398, :438-439) - needed with edge features, where
+        the merged element carries the SUM of the duplicates' feature vectors."""
+        self.coalesced = bool(coalesce)
+        if coalesce:
+            self._init_coalesced(edge_index, num_vertices, self_loop_weight, edge_weighting, dtype)
+            return
         lib = _lib.load()
         _lib.require_cuda(edge_index, "edge_index")
         assert edge_weighting in {"unit", "gcn"}, "invalid value passed in argument <edge_weighting>"
@@ -84,6 +92,32 @@ class GraphCSR:
                                    float(self_loop_weight), gcn, ptr(self.in_degrees), ptr(self.W), stream_ptr(device)),
               "fsw_edge_weights")
 
+    def _init_coalesced(self, edge_index, num_vertices, self_loop_weight, edge_weighting, dtype):
+        _lib.require_cuda(edge_index, "edge_index")
+        assert edge_weighting in {"unit", "gcn"}, "invalid value passed in argument <edge_weighting>"
+        device = edge_index.device
+        N, E = int(num_vertices), int(edge_index.shape[1])
+        src, dst = edge_index[0].to(torch.int64), edge_index[1].to(torch.int64)
+        base = torch.ones(E, dtype=dtype, device=device)
+        if self_loop_weight > 0:
+            loops = torch.arange(N, device=device, dtype=torch.int64)
+            src, dst = torch.cat((src, loops)), torch.cat((dst, loops))
+            base = torch.cat((base, torch.full((N,), float(self_loop_weight), dtype=dtype, device=device)))
+        uniq, inverse = torch.unique(dst * N + src, sorted=True, return_inverse=True)
+        nslots = int(uniq.numel())
+        rows, cols = uniq // N, uniq % N
+        W = torch.zeros(nslots, dtype=dtype, device=device).index_add_(0, inverse, base)
+        deg = torch.zeros(N, dtype=dtype, device=device).index_add_(0, rows, W)
+        if edge_weighting == "gcn":
+            W = W / torch.sqrt(deg[rows]) / torch.sqrt(deg[cols])
+        self.N, self.E, self.Etot = N, E, nslots
+        self.rowptr = rowptr_from_sorted_rows(rows, N)
+        self.col = cols.to(torch.int32)
+        self.eid = None
+        self.slot_of_edge = inverse[:E]
+        self.in_degrees = deg
+        self.W = W.contiguous()
+
     def plan(self, thresh, dtype):
         return SegmentPlan(self.N, self.Etot, self.rowptr, 0, self.col, self.W, thresh, dtype, self.rowptr.device)
 
@@ -92,6 +126,9 @@ class GraphCSR:
         fsw_conv.py:430-439)."""
         if edge_features.dim() == 1:
             edge_features = edge_features.unsqueeze(-1)
+        if self.coalesced:
+            out = torch.zeros((self.Etot, edge_features.shape[1]), dtype=edge_features.dtype, device=edge_features.device)
+            return out.index_add(0, self.slot_of_edge, edge_features)
         if self.Etot > self.E:
             pad = torch.zeros((self.N, edge_features.shape[1]), dtype=edge_features.dtype, device=edge_features.device)
             edge_features = torch.cat((edge_features, pad), dim=0)
@@ -108,15 +145,15 @@ _GRAPH_CACHE = []
 _GRAPH_CACHE_SIZE = 4
 
 
-def cached_graph(edge_index, num_vertices, self_loop_weight, edge_weighting, thresh, dtype, use_cache=True):
+def cached_graph(edge_index, num_vertices, self_loop_weight, edge_weighting, thresh, dtype, use_cache=True, coalesce=False):
     key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), edge_index.dtype, int(num_vertices),
-           float(self_loop_weight), edge_weighting, float(thresh), dtype, edge_index.device)
+           float(self_loop_weight), edge_weighting, float(thresh), dtype, edge_index.device, bool(coalesce))
     if use_cache:
         for i, (k, ref, csr, plan) in enumerate(_GRAPH_CACHE):
             if k == key:
                 _GRAPH_CACHE.append(_GRAPH_CACHE.pop(i))
                 return csr, plan
-    csr = GraphCSR(edge_index, num_vertices, self_loop_weight, edge_weighting, dtype)
+    csr = GraphCSR(edge_index, num_vertices, self_loop_weight, edge_weighting, dtype, coalesce=coalesce)
     plan = csr.plan(thresh, dtype)
     if use_cache:
         _GRAPH_CACHE.append((key, edge_index, csr, plan))

@@ -43,15 +43,36 @@ def emb_params(mod):
     return {("param_" + k): npy(v) for k, v in mod.state_dict().items()}
 
 
+def round_module_to_f32(mod):
+    """Round every floating-point parameter / buffer to the nearest fp32 value, keep fp64 storage."""
+    with torch.no_grad():
+        for t_ in list(mod.parameters()) + list(mod.buffers()):
+            if t_.is_floating_point():
+                t_.copy_(t_.to(torch.float32).to(torch.float64))
+    return mod
+
+
+# tags: f64 = reference in fp64 (truth for fp64 runs); f32 = reference in fp32 (its own noise floor);
+#       r64 = reference in fp64 evaluated on the fp32-ROUNDED inputs and parameters, i.e. the exact value
+#             of the function at the point an fp32 implementation is given (truth for fp32 runs).
+VARIANTS = ((torch.float64, "f64", False), (torch.float32, "f32", False), (torch.float64, "r64", True))
+
+
+def rnd(t_, rounded):
+    return t_.to(torch.float32).to(torch.float64) if rounded else t_
+
+
 def run_both_dtypes(build, run):
-    """build(dtype)->module (seeded identically), run(module, dtype)->dict of outputs."""
+    """build(dtype)->module (seeded identically), run(module, dtype, rounded)->dict of outputs."""
     out = {}
-    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+    for dtype, tag, rounded in VARIANTS:
         mod = build(dtype)
-        res = run(mod, dtype)
+        if rounded:
+            round_module_to_f32(mod)
+        res = run(mod, dtype, rounded)
         for k, v in res.items():
             out["%s_%s" % (k, tag)] = v
-        if dtype == torch.float64:
+        if tag == "f64":
             out.update(emb_params(mod))
     return out
 
@@ -76,9 +97,9 @@ def case_dense(name, batch_dims, n, d, d_out, Wmode, seed, **kw):
         return FSW_embedding(d_in=d, d_out=d_out, device="cpu", dtype=dtype, load_custom_cuda_lib=False,
                              learnable_slices=True, learnable_freqs=True, **kw)
 
-    def run(mod, dtype):
-        X = X64.clone().to(dtype).requires_grad_(True)
-        W = W64 if isinstance(W64, str) else W64.clone().to(dtype).requires_grad_(True)
+    def run(mod, dtype, rounded):
+        X = rnd(X64.clone(), rounded).to(dtype).requires_grad_(True)
+        W = W64 if isinstance(W64, str) else rnd(W64.clone(), rounded).to(dtype).requires_grad_(True)
         out = mod(X, W)
         (out * gout.to(dtype)).sum().backward()
         r = dict(out=npy(out), dX=npy(X.grad), dprojVecs=npy(mod.projVecs.grad), dfreqs=npy(mod.freqs.grad))
@@ -113,9 +134,9 @@ def case_sparse_graph(name, S, N, d, d_out, nnz, seed, weighted, **kw):
         return FSW_embedding(d_in=d, d_out=d_out, device="cpu", dtype=dtype, load_custom_cuda_lib=False,
                              learnable_slices=True, learnable_freqs=True, **kw)
 
-    def run(mod, dtype):
-        X = X64.clone().to(dtype).requires_grad_(True)
-        A = torch.sparse_coo_tensor(A64.indices(), A64.values().to(dtype), (S, N)).coalesce()
+    def run(mod, dtype, rounded):
+        X = rnd(X64.clone(), rounded).to(dtype).requires_grad_(True)
+        A = torch.sparse_coo_tensor(A64.indices(), rnd(A64.values(), rounded).to(dtype), (S, N)).coalesce()
         out = mod(X, A, graph_mode=True)
         (out * gout.to(dtype)).sum().backward()
         r = dict(out=npy(out), dX=npy(X.grad), dprojVecs=npy(mod.projVecs.grad), dfreqs=npy(mod.freqs.grad))
@@ -152,12 +173,14 @@ def case_conv(name, N, E, d_in, d_out, seed, edgefeat_dim=0, with_dups=True, **k
         return FSW_conv(d_in, d_out, edgefeat_dim=edgefeat_dim, device="cpu", dtype=dtype, **kw)
 
     out_all = {}
-    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
-        mod = build(dtype)
-        mod.fsw_embed  # noqa
+    for dtype, tag, rounded in VARIANTS:
+        # always initialise in fp64 (then cast) so that the three variants share the same parameters
+        mod = build(torch.float64).to(dtype=dtype)
+        if rounded:
+            round_module_to_f32(mod)
         ref_emb.libfsw_embedding = None  # pure-torch segcumsum on CPU
-        x = x64.clone().to(dtype).requires_grad_(True)
-        ef = ef64.clone().to(dtype).requires_grad_(True) if ef64 is not None else None
+        x = rnd(x64.clone(), rounded).to(dtype).requires_grad_(True)
+        ef = rnd(ef64.clone(), rounded).to(dtype).requires_grad_(True) if ef64 is not None else None
         out = mod(x, ei, edge_features=ef)
         (out * gout.to(dtype)).sum().backward()
         out_all["out_" + tag] = npy(out)
@@ -167,7 +190,7 @@ def case_conv(name, N, E, d_in, d_out, seed, edgefeat_dim=0, with_dups=True, **k
         for pn, p in mod.named_parameters():
             if p.grad is not None:
                 out_all["grad_%s_%s" % (pn, tag)] = npy(p.grad)
-        if dtype == torch.float64:
+        if tag == "f64":
             out_all.update(conv_params(mod))
     save(name, x=npy(x64), edge_index=npy(ei), edge_features=npy(ef64), gout=npy(gout), **out_all)
 
@@ -179,10 +202,12 @@ def case_readout(name, sizes, d_in, d_out, seed, **kw):
     gi = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
     gout = torch.randn(len(sizes), d_out, generator=g, dtype=torch.float64)
     out_all = {}
-    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+    for dtype, tag, rounded in VARIANTS:
         torch.manual_seed(seed)
-        mod = FSW_readout(d_in, d_out, concat_self=False, device="cpu", dtype=dtype, **kw)
-        x = x64.clone().to(dtype).requires_grad_(True)
+        mod = FSW_readout(d_in, d_out, concat_self=False, device="cpu", dtype=torch.float64, **kw).to(dtype=dtype)
+        if rounded:
+            round_module_to_f32(mod)
+        x = rnd(x64.clone(), rounded).to(dtype).requires_grad_(True)
         out = mod(x, graph_index=gi, batch_size=len(sizes))
         (out * gout.to(dtype)).sum().backward()
         out_all["out_" + tag] = npy(out)
@@ -190,7 +215,7 @@ def case_readout(name, sizes, d_in, d_out, seed, **kw):
         for pn, p in mod.named_parameters():
             if p.grad is not None:
                 out_all["grad_%s_%s" % (pn, tag)] = npy(p.grad)
-        if dtype == torch.float64:
+        if tag == "f64":
             out_all.update(conv_params(mod))
     save(name, x=npy(x64), graph_index=npy(gi), gout=npy(gout), **out_all)
 
@@ -247,7 +272,9 @@ if __name__ == "__main__":
     case_conv("conv_selfloop_gcn", 30, 150, 5, 7, seed=22, self_loop_weight=0.2, edge_weighting="gcn",
               vertex_degree_encoding_function="log", learnable_vertex_degree_encoding_scale=True, mlp_layers=2)
     case_conv("conv_edgefeat", 25, 120, 5, 6, seed=23, edgefeat_dim=3, mlp_layers=3, with_dups=True)
-    case_conv("conv_homog_nomlp", 25, 100, 4, 6, seed=24, mlp_layers=0, bias=False, homog_degree_encoding=True)
+    # embed_dim=13 (K=12): with the default odd K the 'spread' frequencies contain xi = 1 exactly, where a
+    # single-element neighbourhood embeds to exactly 0 - the kink of mean|emb| in the 'homog' encoding
+    case_conv("conv_homog_nomlp", 25, 100, 4, 6, seed=24, mlp_layers=0, bias=False, homog_degree_encoding=True, embed_dim=13)
     case_conv("conv_wide", 60, 900, 8, 8, seed=25, embed_dim=40)  # mean degree 15, some degrees > 32
     case_readout("readout_default", [5, 1, 40, 17, 30], 6, 4, seed=31)  # NB total >= 64: the reference torch segcumsum breaks when stride > n (fsw_embedding.py:2872)
     case_segcumsum("segcumsum", 60, seed=41)

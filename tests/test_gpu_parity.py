@@ -15,6 +15,9 @@ from conftest import coo_to_csr, load_golden
 pytestmark = pytest.mark.gpu
 
 F32 = dict(rtol=1e-5, atol=1e-6)
+# NB for fp32 the truth is the reference evaluated in fp64 ON THE SAME fp32 INPUTS AND PARAMETERS
+# (`*_r64` arrays): rounding xi ~ 2K to fp32 alone moves the exact result by ~1e-5, so a comparison with
+# the fp64-parameter run (`*_f64`) would measure the input rounding, not the kernel.
 # gradients are sums of many O(1) terms: same relative bar, absolute bar scaled to the gradient size
 F64 = dict(rtol=1e-9, atol=1e-10)
 DT = {"f32": torch.float32, "f64": torch.float64}
@@ -31,6 +34,9 @@ def gtol(tag, ref):
     if tag == "f64":
         return dict(rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(ref).max())))
     return dict(rtol=1e-5, atol=1e-6 + 1e-5 * float(np.abs(ref).max()))
+
+
+REFTAG = {"f32": "r64", "f64": "f64"}  # fp32 runs: reference fp64 arithmetic on the fp32-rounded inputs/params
 
 
 def dev():
@@ -72,14 +78,14 @@ def test_dense_embedding(name, tag):
     mode = str(g["Wmode"])
     W = t(g["W"], dtype) if mode == "tensor" else mode
     out = mod(X, W)
-    ref = g["out_f64"]
+    ref = g["out_" + REFTAG[tag]]
     np.testing.assert_allclose(out.detach().cpu().numpy(), ref, **tol(tag, ref))
     (out * t(g["gout"], dtype)).sum().backward()
-    np.testing.assert_allclose(X.grad.cpu().numpy(), g["dX_f64"], **gtol(tag, g["dX_f64"]))
-    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), g["dprojVecs_f64"], **gtol(tag, g["dprojVecs_f64"]))
-    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), g["dfreqs_f64"], **gtol(tag, g["dfreqs_f64"]))
+    np.testing.assert_allclose(X.grad.cpu().numpy(), g["dX_" + REFTAG[tag]], **gtol(tag, g["dX_f64"]))
+    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), g["dprojVecs_" + REFTAG[tag]], **gtol(tag, g["dprojVecs_f64"]))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), g["dfreqs_" + REFTAG[tag]], **gtol(tag, g["dfreqs_f64"]))
     if "dbias_f64" in g:
-        np.testing.assert_allclose(mod.bias.grad.cpu().numpy(), g["dbias_f64"], **gtol(tag, g["dbias_f64"]))
+        np.testing.assert_allclose(mod.bias.grad.cpu().numpy(), g["dbias_" + REFTAG[tag]], **gtol(tag, g["dbias_f64"]))
 
 
 GRAPH = {
@@ -102,13 +108,13 @@ def test_sparse_graph_embedding(name, tag):
     A = torch.sparse_coo_tensor(torch.as_tensor(g["A_indices"], device=dev()), t(g["A_values"], dtype), (S, N)).coalesce()
     X = t(g["X"], dtype).requires_grad_(True)
     out = mod(X, A, graph_mode=True)
-    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_f64"], **tol(tag, g["out_f64"]))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_" + REFTAG[tag]], **tol(tag, g["out_f64"]))
     (out * t(g["gout"], dtype)).sum().backward()
-    np.testing.assert_allclose(X.grad.cpu().numpy(), g["dX_f64"], **gtol(tag, g["dX_f64"]))
-    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), g["dprojVecs_f64"], **gtol(tag, g["dprojVecs_f64"]))
-    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), g["dfreqs_f64"], **gtol(tag, g["dfreqs_f64"]))
+    np.testing.assert_allclose(X.grad.cpu().numpy(), g["dX_" + REFTAG[tag]], **gtol(tag, g["dX_f64"]))
+    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), g["dprojVecs_" + REFTAG[tag]], **gtol(tag, g["dprojVecs_f64"]))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), g["dfreqs_" + REFTAG[tag]], **gtol(tag, g["dfreqs_f64"]))
     if "dscale_f64" in g:
-        np.testing.assert_allclose(mod.total_mass_encoding_scale.grad.cpu().numpy(), g["dscale_f64"], **gtol(tag, g["dscale_f64"]))
+        np.testing.assert_allclose(mod.total_mass_encoding_scale.grad.cpu().numpy(), g["dscale_" + REFTAG[tag]], **gtol(tag, g["dscale_f64"]))
 
 
 def test_dense_graph_mode_equals_sparse():
@@ -132,7 +138,7 @@ CONV = {
     "conv_selfloop_gcn": dict(args=(5, 7), kw=dict(self_loop_weight=0.2, edge_weighting="gcn", vertex_degree_encoding_function="log",
                                                      learnable_vertex_degree_encoding_scale=True, mlp_layers=2)),
     "conv_edgefeat": dict(args=(5, 6), kw=dict(edgefeat_dim=3, mlp_layers=3)),
-    "conv_homog_nomlp": dict(args=(4, 6), kw=dict(mlp_layers=0, bias=False, homog_degree_encoding=True)),
+    "conv_homog_nomlp": dict(args=(4, 6), kw=dict(mlp_layers=0, bias=False, homog_degree_encoding=True, embed_dim=13)),
     "conv_wide": dict(args=(8, 8), kw=dict(embed_dim=40)),
 }
 
@@ -150,16 +156,25 @@ def test_conv(name, tag):
     ei = torch.as_tensor(g["edge_index"], device=dev())
     ef = t(g["edge_features"], dtype).requires_grad_(True) if "edge_features" in g else None
     out = mod(x, ei, edge_features=ef)
-    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_f64"], **tol(tag, g["out_f64"]))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_" + REFTAG[tag]], **tol(tag, g["out_f64"]))
     (out * t(g["gout"], dtype)).sum().backward()
-    np.testing.assert_allclose(x.grad.cpu().numpy(), g["dx_f64"], **gtol(tag, g["dx_f64"]))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["dx_" + REFTAG[tag]], **gtol(tag, g["dx_f64"]))
     if ef is not None:
-        np.testing.assert_allclose(ef.grad.cpu().numpy(), g["def_f64"], **gtol(tag, g["def_f64"]))
+        np.testing.assert_allclose(ef.grad.cpu().numpy(), g["def_" + REFTAG[tag]], **gtol(tag, g["def_f64"]))
     for pn, p in mod.named_parameters():
-        key = "grad_%s_f64" % pn
+        key = "grad_%s_%s" % (pn, REFTAG[tag])
         if key in g:
             assert p.grad is not None, pn
-            np.testing.assert_allclose(p.grad.cpu().numpy(), g[key], err_msg=pn, **gtol(tag, g[key]))
+            got, want = p.grad.cpu().numpy(), g[key]
+            if name == "conv_homog_nomlp" and pn == "fsw_embed.freqs":
+                # 'homog' puts mean|emb| into the output.  At an integer frequency a single-element
+                # neighbourhood embeds to EXACTLY 0 (2 sinc(2 xi) = 0), the kink of |.|: we return the
+                # subgradient 0 there, the reference gets +-1 from the rounding noise of sin(pi * integer).
+                # 'spread' frequencies (2i+1)/(2K-2i-1) always contain integers (the last one is 2K-1).
+                xi = g["param_fsw_embed.freqs"]
+                keep = np.abs(xi - np.round(xi)) > 1e-9
+                got, want = got[keep], want[keep]
+            np.testing.assert_allclose(got, want, err_msg=pn, **gtol(tag, g[key]))
 
 
 @pytest.mark.parametrize("tag", ["f32", "f64"])
@@ -172,9 +187,9 @@ def test_readout(tag):
     x = t(g["x"], dtype).requires_grad_(True)
     gi = torch.as_tensor(g["graph_index"], device=dev())
     out = mod(x, graph_index=gi, batch_size=int(g["out_f64"].shape[0]))
-    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_f64"], **tol(tag, g["out_f64"]))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_" + REFTAG[tag]], **tol(tag, g["out_f64"]))
     (out * t(g["gout"], dtype)).sum().backward()
-    np.testing.assert_allclose(x.grad.cpu().numpy(), g["dx_f64"], **gtol(tag, g["dx_f64"]))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["dx_" + REFTAG[tag]], **gtol(tag, g["dx_f64"]))
 
 
 @pytest.mark.parametrize("name", ["emb_cartesian", "emb_cartesian_collapse"])
@@ -200,7 +215,7 @@ def test_segcumsum_single_pass(tag, idt):
     ids = torch.as_tensor(g["segment_ids"], device=dev()).to(idt)
     out = segcumsum(v, ids)
     ref = g["out_slow_" + tag]
-    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=(1e-12 if tag == "f64" else 2e-6), atol=(1e-12 if tag == "f64" else 2e-6))
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=(1e-12 if tag == "f64" else 1e-5), atol=(1e-12 if tag == "f64" else 1e-5))
     v2 = v.clone()
     out2 = segcumsum(v2, ids, in_place=True)
     assert out2.data_ptr() == v2.data_ptr()
@@ -250,7 +265,8 @@ def test_segcumsum_legacy_abi(tag):
                                    sizes[i], nblocks[i], tpb)
     torch.cuda.synchronize()
     ref = g["out_slow_" + tag]
-    np.testing.assert_allclose(outs[0].cpu().numpy(), ref, rtol=(1e-12 if tag == "f64" else 2e-6), atol=(1e-12 if tag == "f64" else 2e-6))
+    # fp32: the block hierarchy associates the sums differently from the left-to-right checker
+    np.testing.assert_allclose(outs[0].cpu().numpy(), ref, rtol=(1e-12 if tag == "f64" else 1e-5), atol=(1e-12 if tag == "f64" else 1e-5))
     assert lib.get_max_threads_per_block(0) == 1024
 
 

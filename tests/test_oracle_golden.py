@@ -176,3 +176,35 @@ def test_cartesian(name):
     out = core + g["param_bias"].reshape((1,) + core.shape[1:]) if g["param_bias"].ndim == 2 else \
         core.reshape(B, -1) + g["param_bias"]
     np.testing.assert_allclose(out.reshape(g["out_f64"].shape), g["out_f64"], **TOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# the C restatement (oracle/fsw_oracle.c, used as the CPU baseline of bench.py) against the same vectors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["emb_dense_weighted", "emb_dense_unit", "emb_dense_big"])
+def test_c_oracle_dense(name):
+    from oracle import c_oracle as C
+    g = load_golden(name)
+    Xf, rowptr, col, W, bd, n, d = dense_inputs(g)
+    gout = g["gout"].reshape(-1, g["gout"].shape[-1])
+    out, mass, dX, dtheta, dxi = C.embed_forward_backward(Xf, rowptr, col, W, g["param_projVecs"], g["param_freqs"], gout)
+    np.testing.assert_allclose((out + g["param_bias"]).reshape(g["out_f64"].shape), g["out_f64"], **TOL)
+    np.testing.assert_allclose(dX.reshape(g["dX_f64"].shape), g["dX_f64"], **TOL)
+    np.testing.assert_allclose(dtheta, g["dprojVecs_f64"], **TOL)
+    np.testing.assert_allclose(dxi, g["dfreqs_f64"], rtol=1e-8, atol=1e-9)
+
+
+def test_c_oracle_graph():
+    from oracle import c_oracle as C
+    g = load_golden("emb_graph_unit")
+    S, N = g["A_shape"]
+    rowptr, col, W = coo_to_csr(g["A_indices"], g["A_values"], int(S))
+    out, mass, dX, dtheta, dxi = C.embed_forward_backward(g["X"], rowptr, col, W, g["param_projVecs"], g["param_freqs"], g["gout"])
+    np.testing.assert_allclose(out + g["param_bias"], g["out_f64"], **TOL)
+    np.testing.assert_allclose(dX, g["dX_f64"], **TOL)
+    np.testing.assert_allclose(dtheta, g["dprojVecs_f64"], **TOL)
+    np.testing.assert_allclose(dxi, g["dfreqs_f64"], rtol=1e-8, atol=1e-9)
+    # float build: same algorithm in fp32, close to the reference's own fp32 output
+    out32, _ = C.embed_forward_backward(g["X"], rowptr, col, W, g["param_projVecs"], g["param_freqs"], dtype=np.float32)
+    np.testing.assert_allclose(out32 + g["param_bias"], g["out_f64"], rtol=1e-3, atol=1e-3)
+    assert C.threads() >= 1
