@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""Benchmark of the FSW hot path (BASELINE.json metric: FSW_conv edges/s & FSW_embedding multisets/s,
+forward + backward, and % of HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU port of the reference algorithm (oracle/)
+
+Headline workload (N = 1 and the 1/2/4/8-GPU scaling runs): BASELINE.json configs[3] - three
+FSW_conv(100, 100) layers on an ogbn-products-shaped synthetic graph (2.4M vertices, ~62M edges), fp32,
+destination vertices sharded edge-balanced over the GPUs, strong scaling.  `value` counts every edge once
+per layer per step (edges x layers / step time), forward + backward.  One JSON line on stdout.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "FSW_conv edges/sec & FSW_embedding multisets/sec fwd+bwd, % of HBM roofline"
+N_VERT, N_EDGE, D_FEAT, N_LAYERS = 2_400_000, 62_000_000, 100, 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only; invalid as a bench value)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C2 / C3) and the CPU baseline")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for i, nm in enumerate(names):
+                if f[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def label_buckets(label):
+    """buckets of the segment plan covered by a profiled kernel label (fwd_small_u32_f32 -> uniform 17..32)."""
+    parts = label.split("_")
+    kind = 0 if parts[2][0] == "u" else 1
+    size = int(parts[2][1:])
+    base = kind * 72
+    if parts[1] == "small":
+        lo = {4: 0, 8: 5, 16: 9, 32: 17, 64: 33}[size]
+        return [base + b for b in range(lo, size + 1)]
+    caps = {64: list(range(33, 65)), 128: [65], 256: [66], 512: [67], 1024: [68], 2048: [69], 4096: [70]}
+    return [base + b for b in caps.get(size, [71])]
+
+
+def algorithmic_bytes(label, plan, K):
+    """the fused kernel moves 4 B per (element, slice) gathered, 4 B per element (column id) and
+    4 B per (segment, slice) written (forward) or read (backward: upstream gradient); the backward also
+    scatters 4 B per (element, slice) into dXp."""
+    bs = label_buckets(label)
+    elems = sum(plan.bucket_elems[b] for b in bs)
+    segs = sum(plan.bucket_counts[b] for b in bs)
+    per_es = 8 if label.startswith("bwd") else 4
+    return per_es * elems * K + 4 * elems + 4 * segs * K
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the C port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_conv_step(sample_edges, seed=0):
+    """One fwd+bwd of the 3-layer FSW_conv stack on a destination-row SUBSAMPLE of the synthetic graph,
+    computed by oracle/fsw_oracle.c (fp32 build, OpenMP over all host cores) + numpy for the small
+    Linear/LeakyReLU part.  Returns (seconds, edges in the sample, threads)."""
+    import numpy as np
+    from oracle import c_oracle as C
+    rng = np.random.default_rng(seed)
+    mean_deg = N_EDGE / N_VERT
+    mu = np.log(mean_deg) - 0.5
+    S = max(int(sample_edges / mean_deg), 16)
+    deg = np.clip(np.round(np.exp(mu + rng.standard_normal(S))), 1, 17000).astype(np.int64)
+    rowptr = np.concatenate([[0], np.cumsum(deg)])
+    E = int(rowptr[-1])
+    Nsrc = max(S, 4096)  # sources live in a vertex set at least as large as the sampled rows
+    col = rng.integers(0, Nsrc, E).astype(np.int32)
+    K = 2 * D_FEAT - 1
+    xs = [rng.standard_normal((Nsrc, D_FEAT)).astype(np.float32) for _ in range(N_LAYERS)]
+    theta = rng.standard_normal((K, D_FEAT)).astype(np.float32)
+    theta /= np.linalg.norm(theta, axis=1, keepdims=True)
+    u = (0.5 + np.arange(K)) / K
+    xi = (u / (1 - u)).astype(np.float32)
+    Wl = (rng.standard_normal((D_FEAT, K + 1 + D_FEAT)) / np.sqrt(K + 1 + D_FEAT)).astype(np.float32)
+    t0 = time.perf_counter()
+    for layer in range(N_LAYERS):
+        x = xs[layer]
+        g_core = np.ones((S, K), dtype=np.float32)
+        out, mass, dX, dth, dxi = C.embed_forward_backward(x, rowptr, col, None, theta, xi, g_core, dtype=np.float32)
+        emb = np.concatenate([mass[:, None].astype(np.float32), out, x[:S]], axis=1)  # degree channel | embedding | self
+        h = emb @ Wl.T
+        h = np.where(h >= 0, h, 0.2 * h)
+        gh = np.where(h >= 0, 1.0, 0.2).astype(np.float32) * (2.0 / h.size) * h
+        _ = gh.T @ emb     # dW
+        _ = gh @ Wl        # d emb
+    dt = time.perf_counter() - t0
+    return dt, E * 1, C.threads()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's algorithm on the host cores (oracle port; the reference is a
+    Python/torch program that cannot travel to the GPU box - DESIGN.md 'Reference arm')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 250_000
+    times = []
+    E = thr = 0
+    for i in range(args.warmup + args.steps):
+        dt, E, thr = cpu_conv_step(sample, seed=i)
+        if i >= args.warmup:
+            times.append(dt)
+    t = sum(times) / max(len(times), 1)
+    val = E * N_LAYERS / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[3]: 3 x FSW_conv(100,100) on an ogbn-products-shaped synthetic graph; CPU port timed on a "
+                               "destination-row subsample of ~%d edges per step (rows are independent)" % E},
+        "cpu_baseline": {"value": val, "unit": "edges/s", "cores": thr, "kind": "port",
+                         "sample": "destination-row subsample with ~%d edges x %d layers per step (rows are independent), fp32, oracle/fsw_oracle.c (OpenMP) + numpy MLP" % (E, N_LAYERS)},
+        "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fsw_gnn_b200 import FSW_conv, FSW_embedding, _lib
+    from fsw_gnn_b200 import dist as fdist
+    from fsw_gnn_b200 import synthetic as syn
+    from fsw_gnn_b200.graph import cached_graph, clear_graph_cache
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the FSW kernels have no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.load()
+
+    Nv = max(int(N_VERT * args.scale), 1000)
+    Ne = max(int(N_EDGE * args.scale), 10000)
+    K = 2 * D_FEAT - 1
+
+    # ---- workload: this rank's destination range of the synthetic graph ----
+    deg = syn.products_like_degrees(Nv, Ne, seed=0, device=dev)
+    ranges = syn.balanced_row_ranges(deg, world)
+    lo, hi = ranges[rank]
+    ei_local = syn.edges_for_rows(deg, lo, hi, Nv, seed=0, device=dev)
+    E_total = int(deg.sum())
+    E_local = int(ei_local.shape[1])
+    n_local = hi - lo
+    torch.manual_seed(0)
+    layers = [FSW_conv(D_FEAT, D_FEAT, device=dev) for _ in range(N_LAYERS)]
+    gx = torch.Generator(device=dev)
+    gx.manual_seed(100 + rank)
+    x_local = torch.randn(n_local, D_FEAT, device=dev, generator=gx)
+
+    if world == 1:
+        def prepare(ei):
+            return ei
+
+        def step(x, graph):
+            h = x
+            for conv in layers:
+                h = conv(h, graph)
+            loss = h.square().sum() / (Nv * D_FEAT)
+            loss.backward()
+            return loss
+    else:
+        def prepare(ei):
+            return fdist.ShardedGraph(ei, ranges, rank, 1.0, torch.float32)
+
+        def step(x, graph):
+            h = x
+            for conv in layers:
+                h = fdist.sharded_conv_forward(conv, h, graph)
+            loss = h.square().sum() / (Nv * D_FEAT)
+            loss.backward()
+            fdist.all_reduce_gradients(layers)
+            return loss
+
+    def zero_grads():
+        for m in layers:
+            for p in m.parameters():
+                p.grad = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize, device time from CUDA events, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # ---- device-resident run: inputs in HBM, graph plan prepared once (K0 is cacheable) ----
+    graph = prepare(ei_local)
+    x_req = x_local.clone().requires_grad_(True)
+
+    def resident_step():
+        zero_grads()
+        x_req.grad = None
+        step(x_req, graph)
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_step = timed(resident_step, args.steps)
+    clocks = sampler.stop()
+    gpu_launches = _lib.launch_count() - launches0
+
+    # ---- end-to-end run: host buffers in, loss out, graph preparation inside the step ----
+    x_host = x_local.cpu().pin_memory()
+    ei_host = ei_local.cpu().pin_memory()
+    x_dev = torch.empty_like(x_local)
+    ei_dev = torch.empty_like(ei_local)
+
+    def e2e_step():
+        zero_grads()
+        x_dev.copy_(x_host, non_blocking=True)
+        ei_dev.copy_(ei_host, non_blocking=True)   # bumps the tensor version -> the graph is prepared again
+        xr = x_dev.detach().requires_grad_(True)
+        g = prepare(ei_dev)
+        loss = step(xr, g)
+        return float(loss.item())
+
+    clear_graph_cache()
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, max(2, min(args.steps, 5)))
+    h2d = x_host.numel() * 4 + ei_host.numel() * 8
+    d2h = 4
+
+    # ---- roofline of the dominant kernel: per-kernel CUDA-event timers of the library, separate pass ----
+    roofline = None
+    plan = graph.plan if world > 1 else cached_graph(ei_local, Nv, 0, "unit", 1.0, torch.float32)[1]
+    _lib.profile_enable(True)
+    nprof = 2
+    for _ in range(nprof):
+        resident_step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    peaks, peak_kind = measured_peaks()
+    kern = {k: v for k, v in prof.items() if k.startswith(("fwd_", "bwd_"))}
+    breakdown = {k: round(v[1] / nprof, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    if kern:
+        top = max(kern, key=lambda k: kern[k][1])
+        cnt, tot_ms = kern[top]
+        bytes_per_launch = algorithmic_bytes(top, plan, K)
+        ach = bytes_per_launch / (tot_ms / cnt * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": tot_ms / cnt,
+                    "share_of_step": (tot_ms / nprof) / ms_step}
+        # the whole fused forward family (all size classes) for the north-star 70 % target
+        fwd = {k: v for k, v in kern.items() if k.startswith("fwd_")}
+        fb = sum(algorithmic_bytes(k, plan, K) * v[0] for k, v in fwd.items())
+        ft = sum(v[1] for v in fwd.values()) * 1e-3
+        roofline["fused_forward_all_classes"] = {"achieved": fb / ft / 1e9, "frac": fb / ft / 1e9 / peaks["hbm_gbs"]}
+
+    line = {
+        "metric": METRIC, "value": E_total * N_LAYERS / (ms_step * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[3]: %d x FSW_conv(%d,%d) (K=%d slices, learnable embedding) fwd+bwd on an ogbn-products-shaped "
+                               "synthetic graph, N=%d vertices, E=%d edges (lognormal in-degree, mean %.1f, max 17000)"
+                               % (N_LAYERS, D_FEAT, D_FEAT, K, Nv, E_total, E_total / Nv),
+                   "edges_counted": "edges x layers per step", "parallelism": "dst-sharded x%d, all-gather(X) per layer" % world,
+                   "l2": "inputs (>= 1 GB per tensor) far exceed the 126 MB L2", "scale": args.scale},
+        "clocks": clocks,
+        "e2e": {"value": E_total * N_LAYERS / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "includes": "H2D of vertex features + edge_index from pinned memory, graph preparation (K0), fwd+bwd, D2H of the loss"},
+        "gpu_launches": int(gpu_launches),
+        "roofline": roofline,
+        "kernel_ms_per_step": breakdown,
+    }
+
+    # ---- secondary workloads + CPU baseline (rank 0 does the printing; every rank runs its shard) ----
+    extras = {}
+    if not args.no_extras:
+        # C3: batched point clouds 256 x 1024 x 3 -> 256, batch sharded over the ranks, no communication
+        B, n, d3, K3 = 256 // world, 1024, 3, 256
+        emb = FSW_embedding(d3, K3, device=dev)
+        X3 = torch.randn(B, n, d3, device=dev, requires_grad=True)
+
+        def pc_step():
+            X3.grad = None
+            emb(X3).square().sum().backward()
+        for _ in range(3):
+            pc_step()
+        ms_pc = timed(pc_step, 10)
+        bytes_pc = (n * (16 * K3 + 12 * d3) + 8 * K3) * B * world
+        extras["pointcloud_c3"] = {"multisets_per_s": B * world / (ms_pc * 1e-3), "ms_per_step": ms_pc,
+                                   "roofline_frac_model": bytes_pc / (ms_pc * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                   "config": "configs[2]: 256 x 1024 points, d_in=3, d_out=256, fwd+bwd (dX), batch sharded x%d" % world}
+        if rank == 0:
+            # C2: demo_conv-shaped single layer (N=10k, E=100k, d=64), one GPU
+            torch.manual_seed(1)
+            c2 = FSW_conv(64, 64, device=dev)
+            x2 = torch.randn(10000, 64, device=dev, requires_grad=True)
+            e2 = torch.randint(0, 10000, (2, 100000), device=dev)
+
+            def c2_step():
+                x2.grad = None
+                for p in c2.parameters():
+                    p.grad = None
+                c2(x2, e2).square().sum().backward()
+            for _ in range(3):
+                c2_step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                c2_step()
+            b.record()
+            torch.cuda.synchronize()
+            ms_c2 = a.elapsed_time(b) / 20
+            extras["conv_c2"] = {"edges_per_s": 100000 / (ms_c2 * 1e-3), "ms_per_step": ms_c2,
+                                 "config": "configs[1]: FSW_conv(64,64) fwd+bwd, N=10k, E=100k (launch-latency bound)"}
+    if world > 1:
+        # all ranks took part in the timed sections above; only rank 0 reports
+        pass
+    if rank == 0 and world == 1 and not args.no_extras:
+        dt, E_s, thr = cpu_conv_step(250_000, seed=0)  # warm
+        dts = []
+        for i in range(2):
+            dt, E_s, thr = cpu_conv_step(250_000, seed=1 + i)
+            dts.append(dt)
+        t = sum(dts) / len(dts)
+        line["cpu_baseline"] = {"value": E_s * N_LAYERS / t, "unit": "edges/s", "cores": thr, "kind": "port",
+                                "sample": "destination-row subsample with ~%d edges x %d layers per step (rows are independent), fp32, "
+                                          "oracle/fsw_oracle.c (OpenMP) + numpy MLP; %.1f s per step" % (E_s, N_LAYERS, t)}
+    line["extra"] = extras
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,8 @@ _SIGNATURES = {
     "fsw_last_error": (ctypes.c_char_p, []),
     "fsw_built_for_sm": (c_i32, []),
     "fsw_launch_count": (c_i64, []),
+    "fsw_profile_enable": (c_i32, [c_i32]),
+    "fsw_profile_read": (c_i64, [ctypes.c_char_p, c_i64]),
     "segcumsum_wrapper": (None, [c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, ctypes.c_bool, c_i64, c_i64, c_sz]),
     "add_block_sums_wrapper": (None, [c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64]),
     "get_max_threads_per_block": (c_i32, [c_i32]),
@@ -44,7 +46,7 @@ _SIGNATURES = {
     "fsw_rowptr_from_sorted_rows": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "fsw_edge_weights": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_dbl, c_i32, c_vp, c_vp, c_vp]),
     "fsw_plan_workspace_bytes": (c_sz, [c_i64]),
-    "fsw_segment_plan": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "fsw_segment_plan": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "fsw_gemm": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp]),
     "fsw_embed_scratch_bytes": (c_sz, [c_i32, c_vp, c_i64, c_i64, c_i32]),
     "fsw_embed_forward": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
@@ -110,3 +112,20 @@ def require_cuda(t, name):
 
 def launch_count():
     return int(load().fsw_launch_count())
+
+
+def profile_enable(on=True):
+    load().fsw_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{label: (count, total_ms)} of the launches since the last read (synchronises their events)."""
+    lib = load()
+    cap = 1 << 16  # one call: reading consumes the records
+    buf = ctypes.create_string_buffer(cap)
+    lib.fsw_profile_read(buf, cap)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        label, cnt, ms = line.split()
+        out[label] = (int(cnt), float(ms))
+    return out

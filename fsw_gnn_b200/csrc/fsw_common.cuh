@@ -27,6 +27,10 @@ void fsw_count_launch(int n = 1);
             return fsw_fail(FSW_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));         \
     } while (0)
 
+// per-kernel event timers (fsw_api.cu); no-ops unless fsw_profile_enable(1)
+void fsw_prof_begin(const char* label, cudaStream_t st);
+void fsw_prof_end(cudaStream_t st);
+
 static inline int64_t fsw_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- info word of the segment plan ----------------------------------------------------------------

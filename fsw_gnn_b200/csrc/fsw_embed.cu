@@ -17,6 +17,7 @@
 // weights and reduced mod 2 before it is rounded to fp32; everything else is fp32 for fp32 inputs.
 // The sparse product form D_j = 2 w sinc(xi w) cos(pi xi (2C - w)) (fsw_embedding.py:1047-1075) is
 // used for both value and gradient; it is well conditioned for every xi >= 0.
+#include <string>
 #include <utility>
 
 #include "fsw_common.cuh"
@@ -686,7 +687,10 @@ int launch_fwd_small(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out
     const int G = pick_G(hi - lo, nchunks);
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
+    static const std::string label = std::string("fwd_small_") + (UNIFORM ? "u" : "g") + std::to_string(NP) + (sizeof(T) == 4 ? "_f32" : "_f64");
+    fsw_prof_begin(label.c_str(), st);
     fsw_fwd_small_kernel<T, NP, UNIFORM><<<(unsigned)blocks, 128, 0, st>>>(a, lo, hi, G, nchunks, out, ld_out, out_col0, bias);
+    fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_fwd_small_kernel");
     return FSW_OK;
 }
@@ -716,7 +720,10 @@ int launch_bwd_small(const SegArgs<T>& a, int lo, int hi, const T* g, int64_t ld
     const size_t smem = (size_t)4 * 3 * NP * 32 * sizeof(T);
     auto kern = fsw_bwd_small_kernel<T, NP, UNIFORM, NEED_DXI>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const std::string label = std::string("bwd_small_") + (UNIFORM ? "u" : "g") + std::to_string(NP) + (sizeof(T) == 4 ? "_f32" : "_f64");
+    fsw_prof_begin(label.c_str(), st);
     kern<<<(unsigned)blocks, 128, smem, st>>>(a, lo, hi, G, nchunks, g, ld_g, g_col0, dXp, dEp, dfreqs);
+    fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_bwd_small_kernel");
     return FSW_OK;
 }
@@ -802,6 +809,8 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 gs = (unsigned char*)scratch;
                 smem = 0;
             }
+            const std::string label = std::string("fwd_generic_") + (kind == 0 ? "u" : "g") + std::to_string(cap) + (sizeof(T) == 4 ? "_f32" : "_f64");
+            fsw_prof_begin(label.c_str(), st);
             if (kind == 0) {
                 auto kern = fsw_fwd_generic_kernel<T, 0>;
                 if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -811,6 +820,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, out, ld_out, out_col0, bias, cap, gs);
             }
+            fsw_prof_end(st);
             FSW_CHECK_LAUNCH("fsw_fwd_generic_kernel");
         }
     }
@@ -852,6 +862,8 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
                 gs = (unsigned char*)scratch;
                 smem = 0;
             }
+            const std::string label = std::string("bwd_generic_") + (kind == 0 ? "u" : "g") + std::to_string(cap) + (sizeof(T) == 4 ? "_f32" : "_f64");
+            fsw_prof_begin(label.c_str(), st);
             if (kind == 0) {
                 auto kern = fsw_bwd_generic_kernel<T, true, NEED_DXI>;
                 if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -861,6 +873,7 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
                 if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);
             }
+            fsw_prof_end(st);
             FSW_CHECK_LAUNCH("fsw_bwd_generic_kernel");
         }
     }

@@ -149,10 +149,12 @@ int gemm_t(int op, int64_t M, int64_t N, int64_t Kd, const T* A, int64_t lda, co
     case D:                                                                                             \
         fsw_project_small_kernel<T, D><<<grid, 256, 0, st>>>(M, N, A, lda, B, ldb, C, ldc);             \
         break;
+        fsw_prof_begin(sizeof(T) == 4 ? "project_small_f32" : "project_small_f64", st);
         switch ((int)Kd) {
             FSW_PS(1) FSW_PS(2) FSW_PS(3) FSW_PS(4) FSW_PS(5) FSW_PS(6) FSW_PS(7) FSW_PS(8)
         }
 #undef FSW_PS
+        fsw_prof_end(st);
         FSW_CHECK_LAUNCH("fsw_project_small_kernel");
         return FSW_OK;
     }
@@ -169,7 +171,10 @@ int gemm_t(int op, int64_t M, int64_t N, int64_t Kd, const T* A, int64_t lda, co
     splits = fsw_cdiv(Kd, k_per_split);
     dim3 grid((unsigned)fsw_cdiv(M, BM), (unsigned)fsw_cdiv(N, BN), (unsigned)splits);
     const int use_atomics = (op == 2) ? 1 : 0;
+    static const char* labels[3] = {"gemm_nt", "gemm_nn", "gemm_tn"};
+    fsw_prof_begin(labels[op], st);
     fsw_gemm_kernel<T><<<grid, 256, 0, st>>>(M, N, Kd, A, sa_m, sa_k, B, sb_n, sb_k, C, ldc, accumulate, k_per_split, use_atomics);
+    fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_gemm_kernel");
     return FSW_OK;
 }

@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256) edge_weights_kernel(const int32_t* __rest
 template <typename T>
 __global__ void __launch_bounds__(256) plan_stats(const int32_t* __restrict__ rowptr, int64_t n_fixed, const T* __restrict__ W,
                                                   int64_t S, double thresh, double* __restrict__ mass, int32_t* __restrict__ info,
-                                                  int* __restrict__ hist /*[BUCKETS+1] last = max n_eff*/) {
+                                                  int* __restrict__ hist /*[BUCKETS+1] last = max n_eff*/,
+                                                  unsigned long long* __restrict__ elems /*[BUCKETS] or null*/) {
     __shared__ int sh[FSW_PLAN_BUCKETS + 1];
     for (int i = threadIdx.x; i <= FSW_PLAN_BUCKETS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -227,8 +228,10 @@ __global__ void __launch_bounds__(256) plan_stats(const int32_t* __restrict__ ro
         if (lane == 0) {
             mass[s] = m;
             info[s] = n_eff | (uniform ? FSW_INFO_UNIFORM : 0);
-            atomicAdd(&sh[(uniform ? 0 : FSW_PLAN_BUCKETS_PER_KIND) + fsw_size_bucket(n_eff)], 1);
+            const int b = (uniform ? 0 : FSW_PLAN_BUCKETS_PER_KIND) + fsw_size_bucket(n_eff);
+            atomicAdd(&sh[b], 1);
             atomicMax(&sh[FSW_PLAN_BUCKETS], n_eff);
+            if (elems) atomicAdd(elems + b, (unsigned long long)n_eff);
         }
     }
     __syncthreads();
@@ -341,8 +344,8 @@ extern "C" size_t fsw_plan_workspace_bytes(int64_t S) {
 }
 
 extern "C" int fsw_segment_plan(int dtype, const int32_t* rowptr, int64_t n_fixed, const void* W, int64_t S, double thresh,
-                                double* mass, int32_t* info, int32_t* order, int32_t* bucket_offsets, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                double* mass, int32_t* info, int32_t* order, int32_t* bucket_offsets,
+                                int64_t* bucket_elems, void* workspace, size_t workspace_bytes, void* stream) {
     if (workspace_bytes < fsw_plan_workspace_bytes(S)) return fsw_fail(FSW_ERR_WORKSPACE, "fsw_segment_plan: workspace too small");
     if (!(thresh > 0)) return fsw_fail(FSW_ERR_INVALID, "fsw_segment_plan: thresh must be positive");
     if (!rowptr && n_fixed <= 0) return fsw_fail(FSW_ERR_INVALID, "fsw_segment_plan: rowptr == NULL needs n_fixed > 0");
@@ -350,12 +353,13 @@ extern "C" int fsw_segment_plan(int dtype, const int32_t* rowptr, int64_t n_fixe
     int* hist = (int*)workspace;
     int* cursor = hist + (FSW_PLAN_BUCKETS + 8);
     FSW_CUDA(cudaMemsetAsync(hist, 0, (size_t)(2 * (FSW_PLAN_BUCKETS + 8)) * sizeof(int), st));
+    if (bucket_elems) FSW_CUDA(cudaMemsetAsync(bucket_elems, 0, (size_t)FSW_PLAN_BUCKETS * sizeof(int64_t), st));
     if (S > 0) {
         const unsigned grid = (unsigned)fsw_cdiv(S * 32, 256);
         if (dtype == FSW_F32)
-            plan_stats<float><<<grid, 256, 0, st>>>(rowptr, n_fixed, (const float*)W, S, thresh, mass, info, hist);
+            plan_stats<float><<<grid, 256, 0, st>>>(rowptr, n_fixed, (const float*)W, S, thresh, mass, info, hist, (unsigned long long*)bucket_elems);
         else if (dtype == FSW_F64)
-            plan_stats<double><<<grid, 256, 0, st>>>(rowptr, n_fixed, (const double*)W, S, thresh, mass, info, hist);
+            plan_stats<double><<<grid, 256, 0, st>>>(rowptr, n_fixed, (const double*)W, S, thresh, mass, info, hist, (unsigned long long*)bucket_elems);
         else
             return fsw_fail(FSW_ERR_INVALID, "fsw_segment_plan: dtype %d", dtype);
         FSW_CHECK_LAUNCH("plan_stats");

@@ -1,0 +1,101 @@
+"""Multi-GPU FSW_conv: destination vertices sharded across the GPUs of one box.
+
+Recipient rows of the adjacency are independent, so each rank owns a contiguous range of destination
+vertices chosen to hold an equal share of the EDGES, keeps the CSR rows / plan of that range only, and
+produces the output rows of that range.  The only exchange per layer is an all-gather of the layer's
+input features (NCCL over NVLink / NVSwitch); its adjoint in the backward pass is a reduce-scatter of the
+feature gradients; parameter gradients are all-reduced once per step.  Point-cloud batches need no
+exchange at all (shard the batch dimension; see bench.py).
+
+One process per GPU; torch.distributed provides the communicator (backend nccl on GPUs, gloo in the
+CPU tests of the host-side logic).
+"""
+import torch
+import torch.distributed as dist
+
+from . import graph as _graph
+
+
+def remap_sources(src, row_ranges, max_rows):
+    """Global source id -> row of the padded all-gathered feature matrix [G * max_rows, d]
+    (rank r's vertices occupy rows r*max_rows .. r*max_rows + n_r)."""
+    lows = torch.tensor([lo for lo, hi in row_ranges], device=src.device, dtype=torch.int64)
+    owner = torch.searchsorted(lows, src, right=True) - 1
+    return owner * max_rows + (src - lows[owner])
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """[max_rows, d] per rank -> [G * max_rows, d]; backward = reduce-scatter (sum) of the gradient."""
+
+    @staticmethod
+    def forward(ctx, x_pad, group):
+        ctx.group = group
+        G = dist.get_world_size(group)
+        out = torch.empty((G * x_pad.shape[0],) + tuple(x_pad.shape[1:]), dtype=x_pad.dtype, device=x_pad.device)
+        dist.all_gather_into_tensor(out, x_pad.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        group = ctx.group
+        G = dist.get_world_size(group)
+        rows = g.shape[0] // G
+        g = g.contiguous()
+        if dist.get_backend(group) == "gloo":  # gloo has no reduce_scatter: all-reduce and keep our block
+            dist.all_reduce(g, group=group)
+            r = dist.get_rank(group)
+            return g[r * rows:(r + 1) * rows].clone(), None
+        out = torch.empty((rows,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        dist.reduce_scatter_tensor(out, g, group=group)
+        return out, None
+
+
+def all_gather_rows(x_local, max_rows, group=None):
+    """Pad the local block to max_rows rows, all-gather, return [G * max_rows, d] (autograd-aware)."""
+    n = x_local.shape[0]
+    if n < max_rows:
+        pad = torch.zeros((max_rows - n,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        x_local = torch.cat((x_local, pad), dim=0)
+    return _AllGatherRows.apply(x_local, group)
+
+
+class ShardedGraph:
+    """This rank's share of a graph: destination rows [row_lo, row_hi) with all their in-edges."""
+
+    def __init__(self, edge_index_local, row_ranges, rank, thresh, dtype, group=None):
+        self.group = group
+        self.rank = rank
+        self.row_ranges = list(row_ranges)
+        self.row_lo, self.row_hi = self.row_ranges[rank]
+        self.n_local = self.row_hi - self.row_lo
+        self.max_rows = max(hi - lo for lo, hi in self.row_ranges)
+        src, dst = edge_index_local[0], edge_index_local[1]
+        assert bool(((dst >= self.row_lo) & (dst < self.row_hi)).all()), "edge_index_local holds foreign destinations"
+        col = remap_sources(src, self.row_ranges, self.max_rows)
+        ei = torch.stack((col, dst - self.row_lo), dim=0).contiguous()
+        self.num_edges = int(ei.shape[1])
+        self.csr = _graph.GraphCSR(ei, self.n_local, 0, "unit", dtype)
+        self.plan = self.csr.plan(thresh, dtype)
+
+
+def sharded_conv_forward(conv, x_local, sg):
+    """One FSW_conv layer on this rank's destination rows (unit edge weights, no edge features)."""
+    assert conv.edgefeat_dim == 0 and conv.edge_weighting == "unit" and not (conv.self_loop_weight > 0), \
+        "the sharded path covers the default FSW_conv configuration (unit weights, no self loops / edge features)"
+    x_all = all_gather_rows(x_local, sg.max_rows, sg.group)
+    emb = conv.fsw_embed.embed_plan(x_all, sg.plan, None)
+    return conv._combine(emb, x_local)
+
+
+def all_reduce_gradients(modules, group=None):
+    """Sum the parameter gradients over the ranks (one flat all-reduce)."""
+    grads = [p.grad for m in modules for p in m.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -40,14 +40,17 @@ class SegmentPlan:
         self.info = torch.empty(self.S, dtype=torch.int32, device=device)
         self.order = torch.empty(self.S, dtype=torch.int32, device=device)
         self._bucket_dev = torch.empty(_lib.PLAN_BUCKETS + 2, dtype=torch.int32, device=device)
+        self._elems_dev = torch.empty(_lib.PLAN_BUCKETS, dtype=torch.int64, device=device)
         ws = _ws(lib.fsw_plan_workspace_bytes(self.S), device)
         check(lib.fsw_segment_plan(dtype_code(dtype), ptr(rowptr), self.n_fixed, ptr(W), self.S, self.thresh,
                                    ptr(self.mass), ptr(self.info), ptr(self.order), ptr(self._bucket_dev),
-                                   ptr(ws), ws.numel(), stream_ptr(device)), "fsw_segment_plan")
+                                   ptr(self._elems_dev), ptr(ws), ws.numel(), stream_ptr(device)), "fsw_segment_plan")
         # one small D2H read per new plan (the reference syncs in every get_slice_info, :2655)
         host = self._bucket_dev.cpu()
         self.bucket_offsets = (ctypes.c_int * (_lib.PLAN_BUCKETS + 2))(*host.tolist())
         self.max_n_eff = int(host[_lib.PLAN_BUCKETS + 1])
+        self.bucket_counts = [int(host[i + 1] - host[i]) for i in range(_lib.PLAN_BUCKETS)]
+        self.bucket_elems = self._elems_dev.cpu().tolist()
         self._scratch = {}
         self._mass_t = None
 

@@ -119,12 +119,14 @@ int fsw_edge_weights(int dtype, const int32_t* rowptr, const int32_t* col, const
  *                      uniform = all weights of the segment equal and T >= thresh;
  *   order [S] int32  = segments sorted by plan bucket (kind * 72 + size bucket);
  *   bucket_offsets [FSW_PLAN_BUCKETS + 2] int32 (device) = start of each bucket inside `order`,
- *                      then S, then max n_eff.
+ *                      then S, then max n_eff;
+ *   bucket_elems [FSW_PLAN_BUCKETS] int64 (device, may be NULL) = sum of n_eff over each bucket
+ *                      (used by the benchmark to turn per-class kernel times into bytes/s).
  * workspace: fsw_plan_workspace_bytes(S). */
 size_t fsw_plan_workspace_bytes(int64_t S);
 int fsw_segment_plan(int dtype, const int32_t* rowptr, int64_t n_fixed, const void* W, int64_t S, double thresh,
-                     double* mass, int32_t* info, int32_t* order, int32_t* bucket_offsets, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     double* mass, int32_t* info, int32_t* order, int32_t* bucket_offsets, int64_t* bucket_elems,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. K1: dense contractions at full input precision (fp32 FMA / fp64), row-major operands
@@ -173,8 +175,17 @@ int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, c
                        void* dXp, void* dEp, double* dfreqs_acc, void* dW, int64_t max_n_eff, void* scratch,
                        size_t scratch_bytes, void* stream);
 
-/* Counters for tests / bench: number of kernel launches issued by this library since load. */
+/* ------------------------------------------------------------------------------------------------
+ * 7. Counters and per-kernel timers (the reference has only unused wall-clock globals,
+ *    fsw_embedding.py:118-119, :1150-1160)
+ * ---------------------------------------------------------------------------------------------- */
+/* number of kernel launches issued by this library since load */
 int64_t fsw_launch_count(void);
+/* When enabled, every launch of the embed / gemm kernels is bracketed by CUDA events on the launching
+ * stream.  fsw_profile_read synchronises those events and writes one line per label
+ * "label count total_ms\n" into buf (returns the number of bytes needed), then clears the records. */
+int fsw_profile_enable(int on);
+int64_t fsw_profile_read(char* buf, int64_t buf_bytes);
 
 #ifdef __cplusplus
 }
