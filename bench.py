@@ -105,12 +105,13 @@ def label_buckets(label):
     parts = label.split("_")
     kind = 0 if parts[2][0] == "u" else 1
     size = int(parts[2][1:])
-    base = kind * 72
+    base = kind * 517
     if parts[1] == "small":
         lo = {4: 0, 8: 5, 16: 9, 32: 17, 64: 33}[size]
         return [base + b for b in range(lo, size + 1)]
-    caps = {64: list(range(33, 65)), 128: [65], 256: [66], 512: [67], 1024: [68], 2048: [69], 4096: [70]}
-    return [base + b for b in caps.get(size, [71])]
+    ranges = {64: (33, 64), 128: (65, 128), 256: (129, 256), 512: (257, 512), 1024: (513, 513), 2048: (514, 514), 4096: (515, 515)}
+    lo, hi = ranges.get(size, (516, 516))
+    return [base + b for b in range(lo, hi + 1)]
 
 
 def algorithmic_bytes(label, plan, K):

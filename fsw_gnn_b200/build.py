@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfsw_embedding.so")
-SOURCES = ["fsw_api.cu", "fsw_prep.cu", "fsw_gemm.cu", "fsw_segcumsum.cu", "fsw_embed.cu"]
+SOURCES = ["fsw_api.cu", "fsw_prep.cu", "fsw_gemm.cu", "fsw_segcumsum.cu", "fsw_embed.cu", "fsw_embed_medium.cu"]
 NVCC_FLAGS = ["-std=c++17", "--expt-relaxed-constexpr", "-O3", "-lineinfo",
               "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
 
@@ -44,6 +44,7 @@ def build(force=False, verbose=True):
         srcp = os.path.join(CSRC, src)
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 os.path.getmtime(srcp), os.path.getmtime(os.path.join(CSRC, "fsw_common.cuh")),
+                os.path.getmtime(os.path.join(CSRC, "fsw_sortnet.cuh")),
                 os.path.getmtime(os.path.join(HERE, "..", "include", "fsw_embedding.h"))):
             continue
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", srcp, "-o", obj]

@@ -37,16 +37,13 @@ static inline int64_t fsw_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 #define FSW_INFO_UNIFORM (1 << 30)
 #define FSW_INFO_NMASK ((1 << 30) - 1)
 
-// plan bucket of a segment of n_eff elements (0..64 exact, then power-of-two ranges)
+// plan bucket of a segment of n_eff elements (0..512 exact, then power-of-two ranges)
 __host__ __device__ static inline int fsw_size_bucket(int n_eff) {
     if (n_eff < FSW_PLAN_EXACT) return n_eff;
-    if (n_eff <= 128) return 65;
-    if (n_eff <= 256) return 66;
-    if (n_eff <= 512) return 67;
-    if (n_eff <= 1024) return 68;
-    if (n_eff <= 2048) return 69;
-    if (n_eff <= 4096) return 70;
-    return 71;
+    if (n_eff <= 1024) return 513;
+    if (n_eff <= 2048) return 514;
+    if (n_eff <= 4096) return 515;
+    return 516;
 }
 
 // ---- numeric helpers --------------------------------------------------------------------------------
@@ -133,6 +130,14 @@ struct SegArgs {
     int K;
     double thresh;
 };
+
+// medium / large path (fsw_embed_medium.cu): uniform-weight fp32 segments of more than 64 elements
+int fsw_medium_forward_f32(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
+                           const float* bias, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int fsw_medium_backward_f32(const SegArgs<float>& a, int lo, int hi, int cap, const float* g, int64_t ld_g, int64_t g_col0,
+                            float* dXp, float* dEp, double* dfreqs, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t fsw_medium_tile_bytes(int cap, bool backward);  // global scratch per CTA (0: shared-memory tile)
+int fsw_medium_grid();
 
 template <typename T>
 __device__ __forceinline__ void fsw_seg_range(const SegArgs<T>& a, int s, int64_t& e0, int& n) {

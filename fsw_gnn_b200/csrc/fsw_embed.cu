@@ -17,65 +17,7 @@
 // weights and reduced mod 2 before it is rounded to fp32; everything else is fp32 for fp32 inputs.
 // The sparse product form D_j = 2 w sinc(xi w) cos(pi xi (2C - w)) (fsw_embedding.py:1047-1075) is
 // used for both value and gradient; it is well conditioned for every xi >= 0.
-#include <string>
-#include <utility>
-
-#include "fsw_common.cuh"
-
-#define FSW_FULL 0xffffffffu
-
-// ---------------------------------------------------------------------------------------------------
-// Batcher odd-even merge sort network over NP compile-time indexed slots (NP power of two).
-// ---------------------------------------------------------------------------------------------------
-// The comparator list is produced at compile time and applied through a fold expression, so every
-// index is a constant and the arrays stay in registers whatever NP is.
-template <int NP>
-struct FswNet {
-    static constexpr int kMax = (NP <= 4) ? 8 : NP * 10;  // >= number of comparators (543 for NP = 64)
-    struct Pairs {
-        int a[kMax];
-        int b[kMax];
-        int n;
-    };
-    static constexpr Pairs make() {
-        Pairs P{};
-        int c = 0;
-        for (int p = 1; p < NP; p <<= 1)
-            for (int k = p; k >= 1; k >>= 1)
-                for (int j = k % p; j <= NP - 1 - k; j += 2 * k)
-                    for (int i = 0; i <= ((k - 1) < (NP - j - k - 1) ? (k - 1) : (NP - j - k - 1)); ++i)
-                        if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-                            P.a[c] = i + j;
-                            P.b[c] = i + j + k;
-                            ++c;
-                        }
-        P.n = c;
-        return P;
-    }
-    static constexpr int count = make().n;
-};
-
-// scalar compile-time constants are usable from device code (aggregate constexpr members are not)
-template <int NP, int I>
-struct FswPair {
-    static constexpr int a = FswNet<NP>::make().a[I];
-    static constexpr int b = FswNet<NP>::make().b[I];
-};
-
-template <int NP, typename CE, int... Is>
-__device__ __forceinline__ void fsw_sort_network_apply(CE&& ce, std::integer_sequence<int, Is...>) {
-    (ce(FswPair<NP, Is>::a, FswPair<NP, Is>::b), ...);
-}
-
-template <int NP, typename CE>
-__device__ __forceinline__ void fsw_sort_network(CE&& ce) {
-    fsw_sort_network_apply<NP>(ce, std::make_integer_sequence<int, FswNet<NP>::count>{});
-}
-
-template <typename T>
-__device__ __forceinline__ T fsw_ldg(const T* p) {
-    return __ldg(p);
-}
+#include "fsw_sortnet.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // Small path, forward
@@ -111,24 +53,10 @@ __global__ void __launch_bounds__(128) fsw_fwd_small_kernel(SegArgs<T> a, int se
         int n;
         fsw_seg_range(a, s, e0, n);
 
-        // ---- gather (column ids and raw weights are loaded coalesced, then broadcast by shuffle) ----
-        int c0 = 0, c1 = 0;
-        if (a.col) {
-            if (lane < n) c0 = a.col[e0 + lane];
-            if (NP > 32 && lane + 32 < n) c1 = a.col[e0 + 32 + lane];
-        }
+        // ---- gather (column ids are loaded coalesced, then broadcast by shuffle; all loads in flight at once) ----
+        int c0, c1;
         T key[NP];
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-            int64_t row = e0 + j;
-            if (a.col) row = __shfl_sync(FSW_FULL, (j < 32) ? c0 : c1, j & 31);
-            T v = Num<T>::big();
-            if (j < n) {
-                v = fsw_ldg(a.Xp + row * a.ldp + kk);
-                if (a.Ep) v += fsw_ldg(a.Ep + (e0 + j) * a.ldp + kk);
-            }
-            key[j] = v;
-        }
+        fsw_gather_keys<T, NP>(a, e0, n, kk, lane, key, c0, c1);
 
         T result;
         if constexpr (UNIFORM) {
@@ -247,24 +175,13 @@ __global__ void __launch_bounds__(128) fsw_bwd_small_kernel(SegArgs<T> a, int se
         const int n_eff = UNIFORM ? n : (a.info[s] & FSW_INFO_NMASK);
         const bool padded = n_eff > n;
 
-        int c0 = 0, c1 = 0;
-        if (a.col) {
-            if (lane < n) c0 = a.col[e0 + lane];
-            if (NP > 32 && lane + 32 < n) c1 = a.col[e0 + 32 + lane];
-        }
+        int c0, c1;
         T key[NP];
         int idx[NP];
+        fsw_gather_keys<T, NP>(a, e0, n, kk, lane, key, c0, c1);
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-            int64_t row = e0 + j;
-            if (a.col) row = __shfl_sync(FSW_FULL, (j < 32) ? c0 : c1, j & 31);
-            T v = Num<T>::big();
-            if (j < n) {
-                v = fsw_ldg(a.Xp + row * a.ldp + kk);
-                if (a.Ep) v += fsw_ldg(a.Ep + (e0 + j) * a.ldp + kk);
-            }
-            if (!UNIFORM && padded && j == n) v = (T)0;
-            key[j] = v;
+            if (!UNIFORM && padded && j == n) key[j] = (T)0;
             idx[j] = j;
         }
         fsw_sort_network<NP>([&](int i, int l) {
@@ -664,13 +581,25 @@ int max_small_np() {
     return sizeof(T) == 4 ? 64 : 32;
 }
 
-int bucket_cap(int b, int64_t max_n_eff) {  // upper bound of n_eff in size bucket b (65..71)
-    static const int caps[] = {128, 256, 512, 1024, 2048, 4096};
-    if (b <= 64) return 64;
-    if (b <= 70) return caps[b - 65];
-    int64_t c = 8192;
-    while (c < max_n_eff) c <<= 1;
-    return (int)c;
+struct SizeRange {
+    int lo, hi;  // size-bucket range [lo, hi]
+    int cap;     // upper bound of n_eff in the range
+};
+
+// ranges served by the generic kernels, beyond the small-path limit `msn`
+int generic_ranges(int msn, int64_t max_n_eff, SizeRange* out) {
+    int c = 0;
+    if (msn < 64) out[c++] = {msn + 1, 64, 64};
+    out[c++] = {65, 128, 128};
+    out[c++] = {129, 256, 256};
+    out[c++] = {257, 512, 512};
+    out[c++] = {513, 513, 1024};
+    out[c++] = {514, 514, 2048};
+    out[c++] = {515, 515, 4096};
+    int64_t big = 8192;
+    while (big < max_n_eff) big <<= 1;
+    out[c++] = {516, 516, (int)big};
+    return c;
 }
 
 int pick_G(int64_t cnt, int nchunks) {
@@ -788,14 +717,19 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                                : dispatch_fwd_small<T, false>(a, c.np, lo, hi, out, ld_out, out_col0, bias, st);
             if (rc) return rc;
         }
-        // generic buckets; for fp64 the exact buckets 33..64 are handled here too (cap 64)
-        for (int b = msn + 1; b < FSW_PLAN_BUCKETS_PER_KIND; ++b) {
-            int b_hi = b;
-            if (b <= 64) b_hi = 64;  // fold all exact buckets above the small limit into one launch
-            const int lo = bo[base + b], hi = bo[base + b_hi + 1];
-            const int cap = bucket_cap(b_hi, max_n_eff);
-            b = b_hi;
+        SizeRange rr[12];
+        const int nr = generic_ranges(msn, max_n_eff, rr);
+        for (int ri = 0; ri < nr; ++ri) {
+            const int lo = bo[base + rr[ri].lo], hi = bo[base + rr[ri].hi + 1];
+            const int cap = rr[ri].cap;
             if (hi <= lo) continue;
+            if constexpr (sizeof(T) == 4) {
+                if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 64 elements
+                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, st);
+                    if (rc) return rc;
+                    continue;
+                }
+            }
             const int64_t ntiles = (int64_t)(hi - lo) * nchunks;
             const size_t tb = generic_tile_bytes<T>(cap, false, kind == 0);
             unsigned grid = (unsigned)(ntiles < kGenericGrid ? ntiles : kGenericGrid);
@@ -842,13 +776,19 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
                                : dispatch_bwd_small<T, false, NEED_DXI>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
             if (rc) return rc;
         }
-        for (int b = msn + 1; b < FSW_PLAN_BUCKETS_PER_KIND; ++b) {
-            int b_hi = b;
-            if (b <= 64) b_hi = 64;
-            const int lo = bo[base + b], hi = bo[base + b_hi + 1];
-            const int cap = bucket_cap(b_hi, max_n_eff);
-            b = b_hi;
+        SizeRange rr[12];
+        const int nr = generic_ranges(msn, max_n_eff, rr);
+        for (int ri = 0; ri < nr; ++ri) {
+            const int lo = bo[base + rr[ri].lo], hi = bo[base + rr[ri].hi + 1];
+            const int cap = rr[ri].cap;
             if (hi <= lo) continue;
+            if constexpr (sizeof(T) == 4) {
+                if (kind == 0 && cap >= 128) {
+                    int rc = fsw_medium_backward_f32(a, lo, hi, cap, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, st);
+                    if (rc) return rc;
+                    continue;
+                }
+            }
             const int64_t ntiles = (int64_t)(hi - lo) * nchunks;
             const size_t tb = generic_tile_bytes<T>(cap, true, kind == 0);
             unsigned grid = (unsigned)(ntiles < kGenericGrid ? ntiles : kGenericGrid);
@@ -883,21 +823,31 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
 }  // namespace
 
 extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t K, int64_t max_n_eff, int backward) {
-    // worst case over the non-empty generic buckets of grid * tile_bytes, only for tiles beyond the smem budget
+    // worst case over the non-empty generic ranges of grid * tile_bytes, only for tiles beyond the smem budget
     size_t need = 0;
     const size_t es = dtype == FSW_F64 ? 8 : 4;
     const int msn = dtype == FSW_F64 ? 32 : 64;
     const int nchunks = (int)((K + 31) / 32);
+    SizeRange rr[12];
+    const int nr = generic_ranges(msn, max_n_eff, rr);
     for (int kind = 0; kind < 2; ++kind) {
         const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
-        for (int b = msn + 1; b < FSW_PLAN_BUCKETS_PER_KIND; ++b) {
-            const int cnt = bo[base + b + 1] - bo[base + b];
+        for (int ri = 0; ri < nr; ++ri) {
+            const int cnt = bo[base + rr[ri].hi + 1] - bo[base + rr[ri].lo];
             if (cnt <= 0) continue;
-            const int cap = bucket_cap(b, max_n_eff);
-            const size_t per = backward ? (es + 4) : (kind == 0 ? es : 2 * es);
-            const size_t tb = (size_t)cap * 32 * per;
-            if (tb <= (size_t)kSmemBudget) continue;
             int64_t ntiles = (int64_t)cnt * nchunks;
+            if (dtype == FSW_F32 && kind == 0 && rr[ri].cap >= 128) {  // medium / large path
+                const size_t tb = fsw_medium_tile_bytes(rr[ri].cap, backward != 0);
+                size_t grid = (size_t)(ntiles < fsw_medium_grid() ? ntiles : fsw_medium_grid());
+                size_t want = grid * tb;
+                const size_t cap_bytes = (size_t)2 << 30;  // never ask for more than 2 GiB: fewer resident CTAs instead
+                if (want > cap_bytes) want = (cap_bytes / tb ? cap_bytes / tb : 1) * tb;
+                if (want > need) need = want;
+                continue;
+            }
+            const size_t per = backward ? (es + 4) : (kind == 0 ? es : 2 * es);
+            const size_t tb = (size_t)rr[ri].cap * 32 * per;
+            if (tb <= (size_t)kSmemBudget) continue;
             size_t grid = (size_t)(ntiles < kGenericGrid ? ntiles : kGenericGrid);
             if (grid * tb > need) need = grid * tb;
         }

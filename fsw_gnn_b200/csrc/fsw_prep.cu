@@ -192,9 +192,6 @@ __global__ void __launch_bounds__(256) plan_stats(const int32_t* __restrict__ ro
                                                   int64_t S, double thresh, double* __restrict__ mass, int32_t* __restrict__ info,
                                                   int* __restrict__ hist /*[BUCKETS+1] last = max n_eff*/,
                                                   unsigned long long* __restrict__ elems /*[BUCKETS] or null*/) {
-    __shared__ int sh[FSW_PLAN_BUCKETS + 1];
-    for (int i = threadIdx.x; i <= FSW_PLAN_BUCKETS; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s < S) {
@@ -229,15 +226,11 @@ __global__ void __launch_bounds__(256) plan_stats(const int32_t* __restrict__ ro
             mass[s] = m;
             info[s] = n_eff | (uniform ? FSW_INFO_UNIFORM : 0);
             const int b = (uniform ? 0 : FSW_PLAN_BUCKETS_PER_KIND) + fsw_size_bucket(n_eff);
-            atomicAdd(&sh[b], 1);
-            atomicMax(&sh[FSW_PLAN_BUCKETS], n_eff);
+            atomicAdd(hist + b, 1);
+            atomicMax(hist + FSW_PLAN_BUCKETS, n_eff);
             if (elems) atomicAdd(elems + b, (unsigned long long)n_eff);
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < FSW_PLAN_BUCKETS; i += blockDim.x)
-        if (sh[i]) atomicAdd(hist + i, sh[i]);
-    if (threadIdx.x == 0 && sh[FSW_PLAN_BUCKETS]) atomicMax(hist + FSW_PLAN_BUCKETS, sh[FSW_PLAN_BUCKETS]);
 }
 
 __global__ void plan_scan(const int* __restrict__ hist, int32_t* __restrict__ offsets, int* __restrict__ cursor) {

@@ -38,8 +38,8 @@ extern "C" {
 #define FSW_F64 1
 
 /* Number of buckets of the segment plan (section 3). */
-#define FSW_PLAN_EXACT 65                         /* buckets 0..64: exact n_eff                    */
-#define FSW_PLAN_BUCKETS_PER_KIND 72              /* 65..71: n_eff <=128,256,512,1024,2048,4096,>4096 */
+#define FSW_PLAN_EXACT 513                        /* buckets 0..512: exact n_eff                   */
+#define FSW_PLAN_BUCKETS_PER_KIND 517             /* 513..516: n_eff <=1024, <=2048, <=4096, >4096  */
 #define FSW_PLAN_BUCKETS (2 * FSW_PLAN_BUCKETS_PER_KIND) /* kind 0 = uniform weights, 1 = general   */
 
 /* ------------------------------------------------------------------------------------------------
@@ -117,7 +117,7 @@ int fsw_edge_weights(int dtype, const int32_t* rowptr, const int32_t* col, const
  *   mass [S] float64 = total mass T_s (fsw_embedding.py:778-784);
  *   info [S] int32   = n_eff | (uniform << 30), n_eff = n + (T < thresh) (deficit pad, :787-815),
  *                      uniform = all weights of the segment equal and T >= thresh;
- *   order [S] int32  = segments sorted by plan bucket (kind * 72 + size bucket);
+ *   order [S] int32  = segments sorted by plan bucket (kind * FSW_PLAN_BUCKETS_PER_KIND + size bucket);
  *   bucket_offsets [FSW_PLAN_BUCKETS + 2] int32 (device) = start of each bucket inside `order`,
  *                      then S, then max n_eff;
  *   bucket_elems [FSW_PLAN_BUCKETS] int64 (device, may be NULL) = sum of n_eff over each bucket

@@ -334,18 +334,21 @@ def test_plan_buckets():
     assert np.array_equal((info >> 30) & 1, uni.astype(np.int64))
     assert np.array_equal(np.sort(order), np.arange(len(lens)))
     bo = np.array(list(plan.bucket_offsets))
-    assert bo[144] == len(lens) and bo[145] == n_eff.max() and plan.max_n_eff == n_eff.max()
+    NB = 2 * 517
+    assert bo[NB] == len(lens) and bo[NB + 1] == n_eff.max() and plan.max_n_eff == n_eff.max()
 
     def bucket(ne):
-        if ne <= 64:
+        if ne <= 512:
             return ne
-        for i, c in enumerate([128, 256, 512, 1024, 2048, 4096]):
+        for i, c in enumerate([1024, 2048, 4096]):
             if ne <= c:
-                return 65 + i
-        return 71
-    for b in range(144):
+                return 513 + i
+        return 516
+    for b in range(NB):
         for s in order[bo[b]:bo[b + 1]]:
-            assert (0 if uni[s] else 72) + bucket(n_eff[s]) == b
+            assert (0 if uni[s] else 517) + bucket(n_eff[s]) == b
+    assert plan.bucket_counts == [int(bo[b + 1] - bo[b]) for b in range(NB)]
+    assert sum(plan.bucket_elems) == int(n_eff.sum())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -391,6 +394,15 @@ def test_random_graph_vs_oracle(tag, weighted):
     np.testing.assert_allclose(dX, rb["dX"], **gtol(tag, rb["dX"]))
     np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), rb["dtheta"], **gtol(tag, rb["dtheta"]))
     np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], **gtol(tag, rb["dxi"]))
+
+
+def test_hub_segments_vs_oracle():
+    """very large segments (global-scratch merge path; > 32768 elements switches the payload to int32)"""
+    degs = np.array([3, 5000, 40000, 17, 700])
+    out, ref, dX, rb, mod = _random_graph_case(21, 3000, degs, 3, 7, False, torch.float32)
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(dX, rb["dX"], **gtol("f32", rb["dX"]))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], **gtol("f32", rb["dxi"]))
 
 
 def test_high_pad_threshold_vs_oracle():
