@@ -101,14 +101,17 @@ class ClockSampler:
 
 
 def label_buckets(label):
-    """buckets of the segment plan covered by a profiled kernel label (fwd_small_u32_f32 -> uniform 17..32)."""
+    """buckets of the segment plan covered by a profiled kernel label, e.g. fwdr_small_u24_f32 -> uniform 17..24,
+    bwd_rank_u64_f32 -> uniform 0..64, fwd_medium_u128_f32 -> uniform 65..128."""
     parts = label.split("_")
     kind = 0 if parts[2][0] == "u" else 1
     size = int(parts[2][1:])
     base = kind * 517
     if parts[1] == "small":
-        lo = {4: 0, 8: 5, 16: 9, 32: 17, 64: 33}[size]
+        lo = ({4: 0, 8: 5, 12: 9, 16: 13, 24: 17, 32: 25, 48: 33, 64: 49} if kind == 0 else {4: 0, 8: 5, 16: 9, 32: 17, 64: 33})[size]
         return [base + b for b in range(lo, size + 1)]
+    if parts[1] == "rank" and size <= 64:
+        return [base + b for b in range(0, size + 1)]
     ranges = {64: (33, 64), 128: (65, 128), 256: (129, 256), 512: (257, 512), 1024: (513, 513), 2048: (514, 514), 4096: (515, 515)}
     lo, hi = ranges.get(size, (516, 516))
     return [base + b for b in range(lo, hi + 1)]
@@ -339,7 +342,7 @@ def main():
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     peaks, peak_kind = measured_peaks()
-    kern = {k: v for k, v in prof.items() if k.startswith(("fwd_", "bwd_"))}
+    kern = {k: v for k, v in prof.items() if k.startswith(("fwd", "bwd"))}
     breakdown = {k: round(v[1] / nprof, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     if kern:
         top = max(kern, key=lambda k: kern[k][1])
@@ -351,7 +354,7 @@ def main():
                     "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": tot_ms / cnt,
                     "share_of_step": (tot_ms / nprof) / ms_step}
         # the whole fused forward family (all size classes) for the north-star 70 % target
-        fwd = {k: v for k, v in kern.items() if k.startswith("fwd_")}
+        fwd = {k: v for k, v in kern.items() if k.startswith("fwd")}
         fb = sum(algorithmic_bytes(k, plan, K) * v[0] for k, v in fwd.items())
         ft = sum(v[1] for v in fwd.values()) * 1e-3
         roofline["fused_forward_all_classes"] = {"achieved": fb / ft / 1e9, "frac": fb / ft / 1e9 / peaks["hbm_gbs"]}

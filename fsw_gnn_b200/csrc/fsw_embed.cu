@@ -702,20 +702,33 @@ SegArgs<T> make_args(const void* Xp, int64_t ldp, const void* Ep, const int32_t*
     return a;
 }
 
+// size classes of the uniform-weight small path (exact merge-exchange networks of these sizes)
+const ClassRange kSmallU[] = {{0, 4, 4}, {5, 8, 8}, {9, 12, 12}, {13, 16, 16}, {17, 24, 24}, {25, 32, 32}, {33, 48, 48}, {49, 64, 64}};
+
 template <typename T>
 int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
-                    int64_t max_n_eff, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                    int64_t max_n_eff, void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr,
+                    cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int msn = max_small_np<T>();
     for (int kind = 0; kind < 2; ++kind) {
         const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
-        for (const ClassRange& c : kSmall) {
-            if (c.np > msn) continue;
-            const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
-            if (hi <= lo) continue;
-            int rc = kind == 0 ? dispatch_fwd_small<T, true>(a, c.np, lo, hi, out, ld_out, out_col0, bias, st)
-                               : dispatch_fwd_small<T, false>(a, c.np, lo, hi, out, ld_out, out_col0, bias, st);
-            if (rc) return rc;
+        if (kind == 0) {
+            for (const ClassRange& c : kSmallU) {
+                if (c.np > msn) continue;
+                const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
+                if (hi <= lo) continue;
+                int rc = fsw_small_forward_u<T>(a, c.np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+                if (rc) return rc;
+            }
+        } else {
+            for (const ClassRange& c : kSmall) {
+                if (c.np > msn) continue;
+                const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
+                if (hi <= lo) continue;
+                int rc = dispatch_fwd_small<T, false>(a, c.np, lo, hi, out, ld_out, out_col0, bias, st);
+                if (rc) return rc;
+            }
         }
         SizeRange rr[12];
         const int nr = generic_ranges(msn, max_n_eff, rr);
@@ -725,7 +738,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
                 if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 64 elements
-                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, st);
+                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, st);
                     if (rc) return rc;
                     continue;
                 }
@@ -763,12 +776,43 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
 
 template <typename T, bool NEED_DXI>
 int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp,
-                     double* dfreqs, int64_t max_n_eff, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                     double* dfreqs, int64_t max_n_eff, void* scratch, size_t scratch_bytes, const unsigned short* ranks,
+                     int64_t ldr, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int msn = max_small_np<T>();
     for (int kind = 0; kind < 2; ++kind) {
         const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
+        if (kind == 0 && ranks != nullptr) {
+            // rank-based backward: no sorting.  One launch for all small classes, one per medium class that
+            // recorded ranks in the forward (fp32, <= 512 elements); anything larger re-sorts below.
+            if constexpr (sizeof(T) == 4) {
+                // n <= 128: global coefficient tables (first bytes of the scratch), independent warps, v4 atomics
+                const size_t tb = fsw_rank_tables_bytes(a.ldp);
+                if (scratch_bytes < tb) return fsw_fail(FSW_ERR_WORKSPACE, "embed scratch too small for the rank tables");
+                const int lo0 = bo[base + 0], hi0 = bo[base + 128 + 1];
+                if (hi0 > lo0) {
+                    int rc = fsw_rank_backward_g128(a, lo0, hi0, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, st);
+                    if (rc) return rc;
+                }
+                scratch = (unsigned char*)scratch + tb;
+                scratch_bytes -= tb;
+                struct { int lo, hi, cap; } rk[2] = {{129, 256, 256}, {257, 512, 512}};
+                for (int i = 0; i < 2; ++i) {
+                    const int lo = bo[base + rk[i].lo], hi = bo[base + rk[i].hi + 1];
+                    if (hi <= lo) continue;
+                    int rc = fsw_rank_backward_u<T>(a, lo, hi, rk[i].cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+                    if (rc) return rc;
+                }
+            } else {
+                const int lo = bo[base + 0], hi = bo[base + msn + 1];
+                if (hi > lo) {
+                    int rc = fsw_rank_backward_u<T>(a, lo, hi, msn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+                    if (rc) return rc;
+                }
+            }
+        }
         for (const ClassRange& c : kSmall) {
+            if (kind == 0 && ranks != nullptr) break;
             if (c.np > msn) continue;
             const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
             if (hi <= lo) continue;
@@ -783,6 +827,7 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             const int cap = rr[ri].cap;
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
+                if (kind == 0 && cap >= 128 && cap <= 512 && ranks != nullptr) continue;  // done by the rank kernel
                 if (kind == 0 && cap >= 128) {
                     int rc = fsw_medium_backward_f32(a, lo, hi, cap, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, st);
                     if (rc) return rc;
@@ -824,6 +869,7 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
 
 extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t K, int64_t max_n_eff, int backward) {
     // worst case over the non-empty generic ranges of grid * tile_bytes, only for tiles beyond the smem budget
+    // (+ the coefficient tables of the rank-based backward, which sit in front of the tiles)
     size_t need = 0;
     const size_t es = dtype == FSW_F64 ? 8 : 4;
     const int msn = dtype == FSW_F64 ? 32 : 64;
@@ -837,7 +883,7 @@ extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t 
             if (cnt <= 0) continue;
             int64_t ntiles = (int64_t)cnt * nchunks;
             if (dtype == FSW_F32 && kind == 0 && rr[ri].cap >= 128) {  // medium / large path
-                const size_t tb = fsw_medium_tile_bytes(rr[ri].cap, backward != 0);
+                const size_t tb = fsw_medium_tile_bytes(rr[ri].cap, backward ? 2 : 1);
                 size_t grid = (size_t)(ntiles < fsw_medium_grid() ? ntiles : fsw_medium_grid());
                 size_t want = grid * tb;
                 const size_t cap_bytes = (size_t)2 << 30;  // never ask for more than 2 GiB: fewer resident CTAs instead
@@ -852,6 +898,7 @@ extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t 
             if (grid * tb > need) need = grid * tb;
         }
     }
+    if (backward && dtype == FSW_F32) need += fsw_rank_tables_bytes((K + 7) / 8 * 8);
     return need;
 }
 
@@ -860,7 +907,7 @@ extern "C" int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const v
                                  const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host,
                                  int64_t S, int64_t K, const void* freqs, double thresh, void* out, int64_t ld_out,
                                  int64_t out_col0, const void* bias, int64_t max_n_eff, void* scratch,
-                                 size_t scratch_bytes, void* stream) {
+                                 size_t scratch_bytes, void* ranks_out, int64_t ldr, void* stream) {
     if (S == 0 || K == 0) return FSW_OK;
     if (!Xp || !mass || !info || !bucket_offsets_host || !freqs || !out)
         return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: null argument");
@@ -868,10 +915,10 @@ extern "C" int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const v
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FSW_F32) {
         auto a = make_args<float>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
-        return embed_forward_t<float>(a, bucket_offsets_host, (float*)out, ld_out, out_col0, (const float*)bias, max_n_eff, scratch, scratch_bytes, st);
+        return embed_forward_t<float>(a, bucket_offsets_host, (float*)out, ld_out, out_col0, (const float*)bias, max_n_eff, scratch, scratch_bytes, (unsigned short*)ranks_out, ldr, st);
     } else if (dtype == FSW_F64) {
         auto a = make_args<double>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
-        return embed_forward_t<double>(a, bucket_offsets_host, (double*)out, ld_out, out_col0, (const double*)bias, max_n_eff, scratch, scratch_bytes, st);
+        return embed_forward_t<double>(a, bucket_offsets_host, (double*)out, ld_out, out_col0, (const double*)bias, max_n_eff, scratch, scratch_bytes, (unsigned short*)ranks_out, ldr, st);
     }
     return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: dtype %d", dtype);
 }
@@ -881,7 +928,8 @@ extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const 
                                   const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host,
                                   int64_t S, int64_t K, const void* freqs, double thresh, const void* g, int64_t ld_g,
                                   int64_t g_col0, void* dXp, void* dEp, double* dfreqs_acc, void* dW,
-                                  int64_t max_n_eff, void* scratch, size_t scratch_bytes, void* stream) {
+                                  int64_t max_n_eff, void* scratch, size_t scratch_bytes, const void* ranks, int64_t ldr,
+                                  void* stream) {
     if (S == 0 || K == 0) return FSW_OK;
     if (dW != nullptr)
         return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_embed_backward: gradient w.r.t. the weights W is not implemented");
@@ -892,13 +940,13 @@ extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const 
     if (dtype == FSW_F32) {
         auto a = make_args<float>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
         if (dfreqs_acc)
-            return embed_backward_t<float, true>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, st);
-        return embed_backward_t<float, false>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, st);
+            return embed_backward_t<float, true>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
+        return embed_backward_t<float, false>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
     } else if (dtype == FSW_F64) {
         auto a = make_args<double>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
         if (dfreqs_acc)
-            return embed_backward_t<double, true>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, st);
-        return embed_backward_t<double, false>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, st);
+            return embed_backward_t<double, true>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
+        return embed_backward_t<double, false>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
     }
     return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: dtype %d", dtype);
 }

@@ -46,24 +46,34 @@ template <>
 __device__ __forceinline__ float fsw_inf<float>() { return __int_as_float(0x7f800000); }
 
 // ---------------------------------------------------------------------------------------------------
-template <typename T, typename IdxT, int W, bool BWD, bool NEED_DXI, bool GLOBAL>
+// MODE 0: forward, keys only.  MODE 1: forward that also records the sorted position of every element
+// (uint16 ranks, consumed by the rank-based backward).  MODE 2: backward that re-sorts (no saved ranks).
+template <int MODE, bool USE_TABLE, typename T, typename IdxT>
+__host__ __device__ constexpr size_t fsw_medium_tile_bytes_t(int cap) {
+    return (size_t)cap * 32 * (2 * sizeof(T) + (MODE >= 1 ? 2 * sizeof(IdxT) : 0) + (USE_TABLE ? sizeof(T) : 0));
+}
+
+template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE>
 __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks, int cap,
                                                             int64_t nwork, T* __restrict__ out, int64_t ld_out,
                                                             int64_t out_col0, const T* __restrict__ bias,
                                                             const T* __restrict__ g, int64_t ld_g, int64_t g_col0,
                                                             T* __restrict__ dXp, T* __restrict__ dEp,
-                                                            double* __restrict__ dfreqs, unsigned char* gscratch) {
+                                                            double* __restrict__ dfreqs, unsigned char* gscratch,
+                                                            unsigned short* __restrict__ ranks, int64_t ldr) {
     extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
     __shared__ double red[W][32];
     __shared__ double red2[W][32];
-    constexpr bool USE_TABLE = !BWD && !GLOBAL;
-    const size_t tile_bytes = (size_t)cap * 32 * (BWD ? 2 * (sizeof(T) + sizeof(IdxT)) : (USE_TABLE ? 3 : 2) * sizeof(T));
+    constexpr bool BWD = MODE == 2;
+    constexpr bool PAY = MODE >= 1;
+    const size_t tile_bytes = fsw_medium_tile_bytes_t<MODE, USE_TABLE, T, IdxT>(cap);
     unsigned char* basep = GLOBAL ? gscratch + (size_t)blockIdx.x * tile_bytes : fsw_smem_raw;
     T* bufA = reinterpret_cast<T*>(basep);
     T* bufB = bufA + (size_t)cap * 32;
-    T* table = bufB + (size_t)cap * 32;                                     // forward, shared-memory tiles only
-    IdxT* idxA = reinterpret_cast<IdxT*>(bufB + (size_t)cap * 32);          // backward only
+    IdxT* idxA = reinterpret_cast<IdxT*>(bufB + (size_t)cap * 32);          // payload (MODE >= 1)
     IdxT* idxB = idxA + (size_t)cap * 32;
+    T* table = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(bufB + (size_t)cap * 32) +
+                                    (PAY ? 2 * (size_t)cap * 32 * sizeof(IdxT) : 0));  // forward, when it fits
     (void)table;
     (void)idxA;
     (void)idxB;
@@ -121,11 +131,11 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
             int idx[32];
             (void)idx;
             fsw_gather_keys<T, 32>(a, e0 + base, cnt, kk, lane, key, c0, c1);
-            if (BWD) {
+            if (PAY) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) idx[j] = base + j;
             }
-            if (BWD) {
+            if (PAY) {
                 fsw_sort_network<32>([&](int i, int l) {
                     T x = key[i], y = key[l];
                     int px = idx[i], py = idx[l];
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 bufA[(base + j) * 32 + lane] = key[j];
-                if (BWD) idxA[(base + j) * 32 + lane] = (IdxT)idx[j];
+                if (PAY) idxA[(base + j) * 32 + lane] = (IdxT)idx[j];
             }
         }
         __syncthreads();
@@ -193,12 +203,17 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                     }
                     if (!final_pass) {
                         dst[pos * 32 + lane] = v;
-                        if (BWD) idst[pos * 32 + lane] = isrc[(p0 + src_row) * 32 + lane];
+                        if (PAY) idst[pos * 32 + lane] = isrc[(p0 + src_row) * 32 + lane];
                     } else if (!BWD) {
                         if (USE_TABLE)
                             acc += (double)(v * table[pos * 32 + lane]);
                         else if (pos < n)
                             acc += (double)(v * Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * pos + 1))));
+                        if (MODE == 1 && pos < n) {
+                            // un-permute through the free ping-pong buffer; stored coalesced after the pass
+                            const int id = isrc[(p0 + src_row) * 32 + lane];
+                            dst[id * 32 + lane] = __int_as_float(pos);
+                        }
                     } else if (pos < n) {
                         const T r = Num<T>::reduce(u * (double)(2 * pos + 1));
                         const T c = Num<T>::cospi_(r);
@@ -230,6 +245,10 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
             idst = ti;
         }
 
+        if (MODE == 1) {
+            for (int r = warp; r < n; r += W)
+                if (act) ranks[(e0 + r) * ldr + k] = (unsigned short)__float_as_int(dst[r * 32 + lane]);
+        }
         if (!BWD) {
             red[warp][lane] = acc;
             __syncthreads();
@@ -274,19 +293,18 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
 
 const int kPersistentGrid = 148 * 2;
 
-template <typename T, typename IdxT, int W, bool BWD, bool NEED_DXI, bool GLOBAL>
+template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE>
 int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
                   const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, void* scratch,
-                  size_t scratch_bytes, cudaStream_t st) {
+                  size_t scratch_bytes, unsigned short* ranks, int64_t ldr, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int64_t cnt = hi - lo;
     int64_t G = GLOBAL ? 1 : cnt * nchunks / (148 * 8);
     if (G < 1) G = 1;
     if (G > 16) G = 16;
     const int64_t nwork = fsw_cdiv(cnt, G) * nchunks;
-    constexpr bool USE_TABLE = !BWD && !GLOBAL;
-    const size_t tile = (size_t)cap * 32 * (BWD ? 2 * (sizeof(T) + sizeof(IdxT)) : (USE_TABLE ? 3 : 2) * sizeof(T));
-    auto kern = fsw_medium_kernel<T, IdxT, W, BWD, NEED_DXI, GLOBAL>;
+    const size_t tile = fsw_medium_tile_bytes_t<MODE, USE_TABLE, T, IdxT>(cap);
+    auto kern = fsw_medium_kernel<T, IdxT, W, MODE, NEED_DXI, GLOBAL, USE_TABLE>;
     int64_t blocks = nwork;
     size_t smem = tile;
     if (GLOBAL) {
@@ -297,51 +315,58 @@ int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t 
     } else {
         FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const std::string label = std::string(BWD ? "bwd_medium_u" : "fwd_medium_u") + std::to_string(cap) + "_f32";
+    static const char* names[3] = {"fwd_medium_u", "fwdr_medium_u", "bwd_medium_u"};
+    const std::string label = std::string(names[MODE]) + std::to_string(cap) + "_f32";
     fsw_prof_begin(label.c_str(), st);
     kern<<<(unsigned)blocks, W * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, cap, nwork, out, ld_out, out_col0, bias, g, ld_g, g_col0,
-                                                  dXp, dEp, dfreqs, (unsigned char*)scratch);
+                                                  dXp, dEp, dfreqs, (unsigned char*)scratch, ranks, ldr);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_medium_kernel");
     return FSW_OK;
 }
 
-template <bool BWD, bool NEED_DXI>
+template <int MODE, bool NEED_DXI>
 int dispatch_medium(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
                     const float* bias, const float* g, int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs,
-                    void* scratch, size_t scratch_bytes, cudaStream_t st) {
-#define FSW_MED(IDX, W, GLOBAL) \
-    launch_medium<float, IDX, W, BWD, NEED_DXI, GLOBAL>(a, lo, hi, cap, out, ld_out, out_col0, bias, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, st)
-    if (cap <= 128) return FSW_MED(unsigned short, 4, false);
-    if (cap <= 256) return FSW_MED(unsigned short, 8, false);
-    if (cap <= 512) return FSW_MED(unsigned short, 16, false);
-    if (cap <= 32768) return FSW_MED(unsigned short, 16, true);
-    return FSW_MED(int, 16, true);
+                    void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+#define FSW_MED(IDX, W, GLOBAL, TABLE) \
+    launch_medium<float, IDX, W, MODE, NEED_DXI, GLOBAL, TABLE>(a, lo, hi, cap, out, ld_out, out_col0, bias, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, ranks, ldr, st)
+    constexpr bool FWD = MODE != 2;
+    if (cap <= 128) return FSW_MED(unsigned short, 4, false, FWD);
+    if (cap <= 256) return FSW_MED(unsigned short, 8, false, FWD);
+    if (cap <= 512) return FSW_MED(unsigned short, 16, false, (MODE == 0));  // with a payload the table no longer fits
+    if (cap <= 32768) return FSW_MED(unsigned short, 16, true, false);
+    return FSW_MED(int, 16, true, false);
 #undef FSW_MED
 }
 
 }  // namespace
 
-size_t fsw_medium_tile_bytes(int cap, bool backward) {
-    if (cap <= 512) return 0;  // shared-memory tiles
+// global scratch per CTA (0: shared-memory tile).  mode: 0 forward, 1 forward + ranks, 2 backward (re-sort)
+size_t fsw_medium_tile_bytes(int cap, int mode) {
+    if (cap <= 512) return 0;
     const size_t idx = cap <= 32768 ? 2 : 4;
-    return (size_t)cap * 32 * (backward ? 2 * (4 + idx) : 2 * 4);
+    return (size_t)cap * 32 * (2 * 4 + (mode >= 1 ? 2 * idx : 0));
 }
 
 int fsw_medium_grid() { return kPersistentGrid; }
 
-// uniform-weight fp32 segments order[lo, hi) whose size class is `cap` (>= 128)
+// uniform-weight fp32 segments order[lo, hi) whose size class is `cap` (>= 128); ranks != NULL records positions
 int fsw_medium_forward_f32(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
-                           const float* bias, void* scratch, size_t scratch_bytes, cudaStream_t st) {
-    return dispatch_medium<false, false>(a, lo, hi, cap, out, ld_out, out_col0, bias, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                         scratch, scratch_bytes, st);
+                           const float* bias, void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr,
+                           cudaStream_t st) {
+    if (ranks != nullptr && cap <= 32768)
+        return dispatch_medium<1, false>(a, lo, hi, cap, out, ld_out, out_col0, bias, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                         scratch, scratch_bytes, ranks, ldr, st);
+    return dispatch_medium<0, false>(a, lo, hi, cap, out, ld_out, out_col0, bias, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                     scratch, scratch_bytes, nullptr, 0, st);
 }
 
 int fsw_medium_backward_f32(const SegArgs<float>& a, int lo, int hi, int cap, const float* g, int64_t ld_g, int64_t g_col0,
                             float* dXp, float* dEp, double* dfreqs, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     if (dfreqs != nullptr)
-        return dispatch_medium<true, true>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
-                                           scratch_bytes, st);
-    return dispatch_medium<true, false>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
-                                        scratch_bytes, st);
+        return dispatch_medium<2, true>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
+                                        scratch_bytes, nullptr, 0, st);
+    return dispatch_medium<2, false>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
+                                     scratch_bytes, nullptr, 0, st);
 }

@@ -1,0 +1,773 @@
+// K2 / K3, uniform-weight fast path for small segments (n <= 64 fp32, <= 32 fp64) and the rank-based
+// backward used for every uniform-weight segment.
+//
+//   fsw_small_fwd_kernel<T, NP, HAS_COL, SAVE_RANK>
+//     one THREAD per (segment, slice), lanes = 32 consecutive slices, keys in registers, merge-exchange
+//     network of exactly NP in {4, 8, 12, 16, 24, 32, 48, 64} slots.  Per element the gather costs
+//     SHFL + IMAD.WIDE + LDG + select; segment metadata (order -> rowptr -> col) is prefetched two
+//     segments ahead so that only the key gather itself is an exposed memory round trip.  The Fourier
+//     coefficients cos(pi xi (2j+1)/n) live in a per-warp shared-memory table that is rebuilt only when
+//     n changes (segments arrive sorted by n).
+//     SAVE_RANK: the network carries the element index; the sorted position of every ORIGINAL element
+//     is un-permuted through shared memory and written as uint16 rank[(e0+i), k] - the analogue of the
+//     compressed permutation the reference saves for its backward (fsw_embedding.py:2041-2050).
+//   fsw_rank_bwd_kernel<T, HAS_COL, NEED_DXI>
+//     backward without any sorting: dL/dp_i = g (1+xi) A0(n) cos(pi xi (2 r_i + 1)/n) with r_i read back;
+//     streaming, one coalesced 128-byte row per element (red.add for graphs, plain store for dense
+//     batches); d/dxi from the same table pass.
+#include "fsw_sortnet.cuh"
+
+namespace {
+
+struct SegMeta {
+    int s;
+    int n;
+    int64_t e0;
+};
+
+template <typename T>
+__device__ __forceinline__ int fsw_ld_order(const SegArgs<T>& a, int q, int last) {
+    const int qq = (q < last) ? q : last - 1;
+    return a.order ? __ldg(a.order + qq) : qq;
+}
+
+template <typename T>
+__device__ __forceinline__ void fsw_ld_range(const SegArgs<T>& a, int s, int64_t& e0, int& n) {
+    if (a.rowptr) {
+        const int lo = __ldg(a.rowptr + s);
+        const int hi = __ldg(a.rowptr + s + 1);
+        e0 = lo;
+        n = hi - lo;
+    } else {
+        e0 = (int64_t)s * a.n_fixed;
+        n = (int)a.n_fixed;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int NP, bool HAS_COL, bool SAVE_RANK>
+__global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks,
+                                                            T* __restrict__ out, int64_t ld_out, int64_t out_col0,
+                                                            const T* __restrict__ bias, unsigned short* __restrict__ ranks,
+                                                            int64_t ldr) {
+    extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // per warp: coefficient table [NP][32] T  (+ rank scratch [NP][32] int when SAVE_RANK)
+    constexpr size_t kWarpBytes = (size_t)NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(int) : 0));
+    T* tab = reinterpret_cast<T*>(fsw_smem_raw + warp * kWarpBytes);
+    int* srank = reinterpret_cast<int*>(tab + NP * 32);
+    (void)srank;
+
+    const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t item = wglobal / nchunks;
+    const int chunk = (int)(wglobal - item * nchunks);
+    const int64_t first64 = (int64_t)seg_lo + item * G;
+    if (first64 >= seg_hi) return;
+    const int first = (int)first64;
+    const int last = (int)((first64 + G < seg_hi) ? first64 + G : seg_hi);
+    const int k = chunk * 32 + lane;
+    const bool act = k < a.K;
+    const int kk = act ? k : a.K - 1;
+    const T xi = __ldg(a.freqs + kk);
+    const double xid = (double)xi;
+    const T bk = (bias != nullptr) ? __ldg(bias + kk) : (T)0;
+    const int ldb = (int)(a.ldp * (int64_t)sizeof(T));
+    const char* xp_bytes = reinterpret_cast<const char*>(a.Xp + kk);
+    const char* ep_bytes = a.Ep ? reinterpret_cast<const char*>(a.Ep + kk) : nullptr;
+
+    // ---- software pipeline over segments: order two ahead, row range one ahead, column ids one ahead ----
+    SegMeta cur, nx1;
+    int s2;
+    int c0, c1;
+    cur.s = fsw_ld_order(a, first, last);
+    fsw_ld_range(a, cur.s, cur.e0, cur.n);
+    fsw_load_cols<NP, HAS_COL>(a.col, cur.e0, cur.n, lane, c0, c1);
+    nx1.s = fsw_ld_order(a, first + 1, last);
+    fsw_ld_range(a, nx1.s, nx1.e0, nx1.n);
+    s2 = fsw_ld_order(a, first + 2, last);
+
+    int n_prev = -1;
+    T A = (T)0;
+
+    for (int q = first; q < last; ++q) {
+        const int n = cur.n;
+        T key[NP];
+        fsw_gather_lean<T, NP, HAS_COL>(xp_bytes, ldb, ep_bytes, cur.e0, n, c0, c1, key);
+        // prefetches for the following segments (their addresses were loaded one iteration ago)
+        int c0n, c1n;
+        fsw_load_cols<NP, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c0n, c1n);
+        SegMeta nx2;
+        nx2.s = s2;
+        fsw_ld_range(a, s2, nx2.e0, nx2.n);
+        const int s3 = fsw_ld_order(a, q + 3, last);
+
+        if (n != n_prev) {
+            const double u = xid / (double)n;
+#pragma unroll 1
+            for (int j = 0; j < NP; ++j)
+                tab[j * 32 + lane] = (j < n) ? Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * j + 1))) : (T)0;
+            T a0, a0p;
+            fsw_amplitude<T, false>(u, (T)(1.0 / (double)n), xi, a0, a0p);
+            A = ((T)1 + xi) * a0;
+            n_prev = n;
+        }
+
+        if constexpr (SAVE_RANK) {
+            int idx[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) idx[j] = j;
+            fsw_sort_network<NP>([&](int i, int l) {
+                const T x = key[i], y = key[l];
+                const int px = idx[i], py = idx[l];
+                const bool sw = x > y;
+                key[i] = sw ? y : x;
+                key[l] = sw ? x : y;
+                idx[i] = sw ? py : px;
+                idx[l] = sw ? px : py;
+            });
+#pragma unroll
+            for (int j = 0; j < NP; ++j) srank[idx[j] * 32 + lane] = j;
+        } else {
+            fsw_sort_network<NP>([&](int i, int l) {
+                const T x = key[i], y = key[l];
+                key[i] = fmin(x, y);
+                key[l] = fmax(x, y);
+            });
+        }
+        T acc = (T)0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) acc = fma(key[j], tab[j * 32 + lane], acc);
+        if (act) out[(int64_t)cur.s * ld_out + out_col0 + k] = A * acc + bk;
+        if constexpr (SAVE_RANK) {
+            unsigned short* rp = ranks + cur.e0 * ldr + k;
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+                if (i < n && act) rp[(int64_t)i * ldr] = (unsigned short)srank[i * 32 + lane];
+        }
+        // rotate the pipeline
+        cur = nx1;
+        c0 = c0n;
+        c1 = c1n;
+        nx1 = nx2;
+        s2 = s3;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Rank-based backward.  CTA = W warps working on the same (segment, slice chunk): the warps split the
+// elements of the segment; the coefficient tables are shared by the CTA.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int W, bool HAS_COL, bool NEED_DXI>
+__global__ void __launch_bounds__(W * 32) fsw_rank_bwd_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks, int cap,
+                                                              const unsigned short* __restrict__ ranks, int64_t ldr,
+                                                              const T* __restrict__ g, int64_t ld_g, int64_t g_col0,
+                                                              T* __restrict__ dXp, T* __restrict__ dEp,
+                                                              double* __restrict__ dfreqs) {
+    extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
+    __shared__ double red[W][32];
+    T* tab_c = reinterpret_cast<T*>(fsw_smem_raw);
+    T* tab_t = tab_c + (size_t)cap * 32;  // only when NEED_DXI
+    (void)tab_t;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - item * nchunks;
+    const int64_t first64 = (int64_t)seg_lo + (int64_t)item * G;
+    if (first64 >= seg_hi) return;
+    const int first = (int)first64;
+    const int last = (int)((first64 + G < seg_hi) ? first64 + G : seg_hi);
+    const int k = chunk * 32 + lane;
+    const bool act = k < a.K;
+    const int kk = act ? k : a.K - 1;
+    const T xi = __ldg(a.freqs + kk);
+    const double xid = (double)xi;
+    const int ldb = (int)(a.ldp * (int64_t)sizeof(T));
+    const char* xp_bytes = reinterpret_cast<const char*>(a.Xp + kk);
+
+    int n_prev = -1;
+    T A0 = (T)0, A0p = (T)0;
+    double dxi_acc = 0.0;
+    (void)A0p;
+
+    for (int q = first; q < last; ++q) {
+        const int s = fsw_ld_order(a, q, last);
+        int64_t e0;
+        int n;
+        fsw_ld_range(a, s, e0, n);
+        const T wn = (T)(1.0 / (double)n);
+        const double u = xid / (double)n;
+        if (n != n_prev) {
+            __syncthreads();  // everyone is done with the previous tables
+            fsw_amplitude<T, NEED_DXI>(u, wn, xi, A0, A0p);
+            for (int r = warp; r < n; r += W) {
+                const T rr = Num<T>::reduce(u * (double)(2 * r + 1));
+                tab_c[r * 32 + lane] = Num<T>::cospi_(rr);
+                if (NEED_DXI) tab_t[r * 32 + lane] = (T)M_PI * wn * (T)(2 * r + 1) * Num<T>::sinpi_(rr);
+            }
+            __syncthreads();
+            n_prev = n;
+        }
+        const T gk = act ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
+        const T GA = gk * ((T)1 + xi) * A0;
+        T Sc = (T)0, Ss = (T)0;
+        const unsigned short* rp = ranks + e0 * ldr + kk;
+        for (int i = warp; i < n; i += W) {
+            const int r = rp[(int64_t)i * ldr];
+            const T c = tab_c[r * 32 + lane];
+            const T v = GA * c;
+            int64_t row = e0 + i;
+            if (HAS_COL) row = __ldg(a.col + e0 + i);
+            if (NEED_DXI) {
+                const T p = __ldg(reinterpret_cast<const T*>(xp_bytes + row * ldb)) +
+                            (a.Ep ? __ldg(a.Ep + (e0 + i) * a.ldp + kk) : (T)0);
+                Sc = fma(p, c, Sc);
+                Ss = fma(p, tab_t[r * 32 + lane], Ss);
+            }
+            if (act) {
+                if (HAS_COL)
+                    atomicAdd(dXp + row * a.ldp + k, v);
+                else
+                    dXp[row * a.ldp + k] = v;
+                if (dEp) dEp[(e0 + i) * a.ldp + k] = v;
+            }
+        }
+        if (NEED_DXI) dxi_acc += (double)gk * ((double)A0 * (double)Sc + (1.0 + xid) * ((double)A0p * (double)Sc - (double)A0 * (double)Ss));
+    }
+    if (NEED_DXI) {
+        red[warp][lane] = dxi_acc;
+        __syncthreads();
+        if (warp == 0 && act) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < W; ++w2) tot += red[w2][lane];
+            atomicAdd(dfreqs + k, tot);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 rank-based backward, V consecutive slices per thread (a warp covers 32*V slices): the scatter is
+// one red.global.add.v4.f32 (REDG.E.ADD.F32x4) per element and thread instead of four scalar atomics -
+// the scalar version was bound by the L2 atomic rate (~1.8e11 lane-atomics/s measured, profiles/r1).
+// Tables are laid out [rank][q][lane] so that every shared-memory access is conflict free.
+// ---------------------------------------------------------------------------------------------------
+template <int V>
+struct FswVec;
+template <>
+struct FswVec<1> {
+    using rank_t = unsigned short;
+    using val_t = float;
+};
+template <>
+struct FswVec<2> {
+    using rank_t = unsigned int;
+    using val_t = float2;
+};
+template <>
+struct FswVec<4> {
+    using rank_t = uint2;
+    using val_t = float4;
+};
+
+template <int V>
+__device__ __forceinline__ void fsw_unpack_ranks(const unsigned short* p, int (&r)[V]) {
+    if constexpr (V == 1) {
+        r[0] = *p;
+    } else if constexpr (V == 2) {
+        const unsigned int w = *reinterpret_cast<const unsigned int*>(p);
+        r[0] = w & 0xffff;
+        r[1] = w >> 16;
+    } else {
+        const uint2 w = *reinterpret_cast<const uint2*>(p);
+        r[0] = w.x & 0xffff;
+        r[1] = w.x >> 16;
+        r[2] = w.y & 0xffff;
+        r[3] = w.y >> 16;
+    }
+}
+
+template <int V>
+__device__ __forceinline__ void fsw_red_add(float* p, const float (&v)[V]) {
+    if constexpr (V == 1) {
+        atomicAdd(p, v[0]);
+    } else if constexpr (V == 2) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    }
+}
+
+template <int V>
+__device__ __forceinline__ void fsw_store_vec(float* p, const float (&v)[V]) {
+    if constexpr (V == 1) {
+        *p = v[0];
+    } else if constexpr (V == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+template <int V>
+__device__ __forceinline__ void fsw_load_vec(const float* p, float (&v)[V]) {
+    if constexpr (V == 1) {
+        v[0] = __ldg(p);
+    } else if constexpr (V == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    } else {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+        v[2] = t.z;
+        v[3] = t.w;
+    }
+}
+
+template <int V, int W, bool HAS_COL, bool NEED_DXI>
+__global__ void __launch_bounds__(W * 32) fsw_rank_bwdv_kernel(SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks, int cap,
+                                                               const unsigned short* __restrict__ ranks, int64_t ldr,
+                                                               const float* __restrict__ g, int64_t ld_g, int64_t g_col0,
+                                                               float* __restrict__ dXp, float* __restrict__ dEp,
+                                                               double* __restrict__ dfreqs) {
+    extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
+    __shared__ double red[W][32];
+    float* tab_c = reinterpret_cast<float*>(fsw_smem_raw);
+    float* tab_t = tab_c + (size_t)cap * V * 32;  // only when NEED_DXI
+    (void)tab_t;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - item * nchunks;
+    const int64_t first64 = (int64_t)seg_lo + (int64_t)item * G;
+    if (first64 >= seg_hi) return;
+    const int first = (int)first64;
+    const int last = (int)((first64 + G < seg_hi) ? first64 + G : seg_hi);
+    const int k0 = (chunk * 32 + lane) * V;
+    const bool lane_in_row = k0 < a.ldp;  // rows are padded to a multiple of 8 >= K: a vector never straddles a row end
+    float xi[V];
+    double xid[V];
+    bool act[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        act[q] = k0 + q < a.K;
+        xi[q] = __ldg(a.freqs + (act[q] ? k0 + q : a.K - 1));
+        xid[q] = (double)xi[q];
+    }
+    int n_prev = -1;
+    float A0[V], A0p[V];
+    double dxi_acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        A0[q] = 0.f;
+        A0p[q] = 0.f;
+        dxi_acc[q] = 0.0;
+    }
+
+    for (int qs = first; qs < last; ++qs) {
+        const int s = fsw_ld_order(a, qs, last);
+        int64_t e0;
+        int n;
+        fsw_ld_range(a, s, e0, n);
+        const float wn = (float)(1.0 / (double)n);
+        if (n != n_prev) {
+            __syncthreads();  // everyone is done with the previous tables
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const double u = xid[q] / (double)n;
+                fsw_amplitude<float, NEED_DXI>(u, wn, xi[q], A0[q], A0p[q]);
+                for (int r = warp; r < n; r += W) {
+                    const float rr = Num<float>::reduce(u * (double)(2 * r + 1));
+                    tab_c[(r * V + q) * 32 + lane] = cospif(rr);
+                    if (NEED_DXI) tab_t[(r * V + q) * 32 + lane] = (float)M_PI * wn * (float)(2 * r + 1) * sinpif(rr);
+                }
+            }
+            __syncthreads();
+            n_prev = n;
+        }
+        float gk[V], GA[V], Sc[V], Ss[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            gk[q] = act[q] ? g[(int64_t)s * ld_g + g_col0 + k0 + q] : 0.f;
+            GA[q] = gk[q] * (1.f + xi[q]) * A0[q];
+            Sc[q] = 0.f;
+            Ss[q] = 0.f;
+        }
+        if (lane_in_row) {
+            const unsigned short* rp = ranks + e0 * ldr + k0;
+#pragma unroll 2
+            for (int i = warp; i < n; i += W) {
+                int r[V];
+                fsw_unpack_ranks<V>(rp + (int64_t)i * ldr, r);
+                int64_t row = e0 + i;
+                if (HAS_COL) row = __ldg(a.col + e0 + i);
+                float c[V], v[V];
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    if (!act[q]) r[q] = 0;  // padding columns of the rank matrix are never written
+                    c[q] = tab_c[(r[q] * V + q) * 32 + lane];
+                    v[q] = GA[q] * c[q];
+                }
+                if (NEED_DXI) {
+                    float p[V];
+                    fsw_load_vec<V>(a.Xp + row * a.ldp + k0, p);
+                    if (a.Ep) {
+                        float pe[V];
+                        fsw_load_vec<V>(a.Ep + (e0 + i) * a.ldp + k0, pe);
+#pragma unroll
+                        for (int q = 0; q < V; ++q) p[q] += pe[q];
+                    }
+#pragma unroll
+                    for (int q = 0; q < V; ++q) {
+                        Sc[q] = fmaf(p[q], c[q], Sc[q]);
+                        Ss[q] = fmaf(p[q], tab_t[(r[q] * V + q) * 32 + lane], Ss[q]);
+                    }
+                }
+                if (HAS_COL)
+                    fsw_red_add<V>(dXp + row * a.ldp + k0, v);
+                else
+                    fsw_store_vec<V>(dXp + row * a.ldp + k0, v);
+                if (dEp) fsw_store_vec<V>(dEp + (e0 + i) * a.ldp + k0, v);
+            }
+        }
+        if (NEED_DXI) {
+#pragma unroll
+            for (int q = 0; q < V; ++q)
+                dxi_acc[q] += (double)gk[q] * ((double)A0[q] * (double)Sc[q] + (1.0 + xid[q]) * ((double)A0p[q] * (double)Sc[q] - (double)A0[q] * (double)Ss[q]));
+        }
+    }
+    if (NEED_DXI) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            __syncthreads();
+            red[warp][lane] = dxi_acc[q];
+            __syncthreads();
+            if (warp == 0 && act[q]) {
+                double tot = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < W; ++w2) tot += red[w2][lane];
+                atomicAdd(dfreqs + k0 + q, tot);
+            }
+        }
+    }
+}
+
+template <int V, int W, bool HAS_COL, bool NEED_DXI>
+int launch_rank_bwdv(const SegArgs<float>& a, int lo, int hi, int cap, const unsigned short* ranks, int64_t ldr, const float* g,
+                     int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, cudaStream_t st) {
+    const int nchunks = (a.K + 32 * V - 1) / (32 * V);
+    int64_t G = (int64_t)(hi - lo) * nchunks / (148 * 16);
+    if (G < 1) G = 1;
+    if (G > 64) G = 64;
+    const int64_t blocks = fsw_cdiv(hi - lo, G) * nchunks;
+    const size_t smem = (size_t)cap * V * 32 * sizeof(float) * (NEED_DXI ? 2 : 1);
+    auto kern = fsw_rank_bwdv_kernel<V, W, HAS_COL, NEED_DXI>;
+    if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const std::string label = std::string("bwd_rank_u") + std::to_string(cap) + "_f32";
+    fsw_prof_begin(label.c_str(), st);
+    kern<<<(unsigned)blocks, W * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_rank_bwdv_kernel");
+    return FSW_OK;
+}
+
+template <int V, int W>
+int dispatch_rank_bwdv(const SegArgs<float>& a, int lo, int hi, int cap, const unsigned short* ranks, int64_t ldr, const float* g,
+                       int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, cudaStream_t st) {
+    const bool has_col = a.col != nullptr;
+    if (dfreqs)
+        return has_col ? launch_rank_bwdv<V, W, true, true>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
+                       : launch_rank_bwdv<V, W, false, true>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+    return has_col ? launch_rank_bwdv<V, W, true, false>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
+                   : launch_rank_bwdv<V, W, false, false>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 rank-based backward for n <= FSW_GTAB_NMAX with the coefficient tables in GLOBAL memory
+// (a few MB, L1/L2 resident, rebuilt once per backward call by fsw_build_rank_tables_kernel):
+//   tab[(n*(n-1)/2 + r) * ldp + k]   for n = 1..NMAX, r = 0..n-1
+// No shared memory, no barriers: every WARP is independent (segment run x 128-slice chunk), so occupancy is
+// set by registers only, and U elements are in flight per warp.  4 slices per thread -> REDG.E.ADD.F32x4.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FSW_GTAB_NMAX = 128;
+constexpr int64_t FSW_GTAB_ROWS = (int64_t)FSW_GTAB_NMAX * (FSW_GTAB_NMAX + 1) / 2;
+
+__global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float* __restrict__ freqs, int K, int ldp,
+                                                                    float* __restrict__ tab_c, float* __restrict__ tab_t,
+                                                                    float* __restrict__ tab_A, float* __restrict__ tab_Ap) {
+    // grid.x = n (1..NMAX), threads over (r, k)
+    const int n = blockIdx.x + 1;
+    const float wn = (float)(1.0 / (double)n);
+    const int64_t off = (int64_t)n * (n - 1) / 2;
+    for (int idx = threadIdx.x; idx < n * ldp; idx += blockDim.x) {
+        const int r = idx / ldp, k = idx - r * ldp;
+        float c = 0.f, t = 0.f;
+        if (k < K) {
+            const double u = (double)freqs[k] / (double)n;
+            const float rr = Num<float>::reduce(u * (double)(2 * r + 1));
+            c = cospif(rr);
+            t = (float)M_PI * wn * (float)(2 * r + 1) * sinpif(rr);
+        }
+        tab_c[(off + r) * ldp + k] = c;
+        if (tab_t) tab_t[(off + r) * ldp + k] = t;
+    }
+    for (int k = threadIdx.x; k < ldp; k += blockDim.x) {
+        float A0 = 0.f, A0p = 0.f;
+        if (k < K) {
+            const float xi = freqs[k];
+            fsw_amplitude<float, true>((double)xi / (double)n, wn, xi, A0, A0p);
+        }
+        tab_A[(int64_t)(n - 1) * ldp + k] = A0;
+        tab_Ap[(int64_t)(n - 1) * ldp + k] = A0p;
+    }
+}
+
+template <bool HAS_COL, bool NEED_DXI>
+__global__ void __launch_bounds__(128) fsw_rank_bwdg_kernel(SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks,
+                                                            const unsigned short* __restrict__ ranks, int64_t ldr,
+                                                            const float* __restrict__ g, int64_t ld_g, int64_t g_col0,
+                                                            float* __restrict__ dXp, float* __restrict__ dEp,
+                                                            double* __restrict__ dfreqs, const float* __restrict__ tab_c,
+                                                            const float* __restrict__ tab_t, const float* __restrict__ tab_A,
+                                                            const float* __restrict__ tab_Ap) {
+    constexpr int V = 4, U = 4;
+    const int lane = threadIdx.x & 31;
+    const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t item = wglobal / nchunks;
+    const int chunk = (int)(wglobal - item * nchunks);
+    const int64_t first64 = (int64_t)seg_lo + item * G;
+    if (first64 >= seg_hi) return;
+    const int first = (int)first64;
+    const int last = (int)((first64 + G < seg_hi) ? first64 + G : seg_hi);
+    const int k0 = (chunk * 32 + lane) * V;
+    if (k0 >= a.ldp) return;  // rows are padded to a multiple of 8 >= K: a 4-vector never straddles a row end
+    const int ldp = (int)a.ldp;
+    float xi[V];
+    bool act[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        act[q] = k0 + q < a.K;
+        xi[q] = __ldg(a.freqs + (act[q] ? k0 + q : a.K - 1));
+    }
+    double dxi_acc[V] = {0.0, 0.0, 0.0, 0.0};
+
+    for (int qs = first; qs < last; ++qs) {
+        const int s = fsw_ld_order(a, qs, last);
+        int64_t e0;
+        int n;
+        fsw_ld_range(a, s, e0, n);
+        float A0[V], A0p[V], gk[V], GA[V], Sc[V], Ss[V];
+        fsw_load_vec<V>(tab_A + (int64_t)(n - 1) * ldp + k0, A0);
+        if (NEED_DXI) fsw_load_vec<V>(tab_Ap + (int64_t)(n - 1) * ldp + k0, A0p);
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            gk[q] = act[q] ? __ldg(g + (int64_t)s * ld_g + g_col0 + k0 + q) : 0.f;
+            GA[q] = gk[q] * (1.f + xi[q]) * A0[q];
+            Sc[q] = 0.f;
+            Ss[q] = 0.f;
+        }
+        const float* tc = tab_c + ((int64_t)n * (n - 1) / 2) * ldp + k0;
+        const float* tt = NEED_DXI ? tab_t + ((int64_t)n * (n - 1) / 2) * ldp + k0 : nullptr;
+        const unsigned short* rp = ranks + e0 * ldr + k0;
+        for (int i0 = 0; i0 < n; i0 += U) {
+            int64_t row[U];
+            int r[U][V];
+            float p[U][V];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {  // column ids: warp-uniform addresses (one broadcast transaction each)
+                const int i = min(i0 + j, n - 1);  // clamped: the tail re-reads the last element, masked below
+                row[j] = HAS_COL ? (int64_t)__ldg(a.col + e0 + i) : e0 + i;
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int i = min(i0 + j, n - 1);
+                fsw_unpack_ranks<V>(rp + (int64_t)i * ldr, r[j]);
+                if (NEED_DXI) fsw_load_vec<V>(a.Xp + row[j] * ldp + k0, p[j]);
+            }
+            if (NEED_DXI && a.Ep) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    float pe[V];
+                    fsw_load_vec<V>(a.Ep + (e0 + min(i0 + j, n - 1)) * ldp + k0, pe);
+#pragma unroll
+                    for (int q = 0; q < V; ++q) p[j][q] += pe[q];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                if (i0 + j < n) {
+                    float c[V], v[V];
+#pragma unroll
+                    for (int q = 0; q < V; ++q) {
+                        const int rq = act[q] ? r[j][q] : 0;  // padding columns of the rank matrix are never written
+                        c[q] = __ldg(tc + (int64_t)rq * ldp + q);
+                        v[q] = GA[q] * c[q];
+                        if (NEED_DXI) {
+                            Sc[q] = fmaf(p[j][q], c[q], Sc[q]);
+                            Ss[q] = fmaf(p[j][q], __ldg(tt + (int64_t)rq * ldp + q), Ss[q]);
+                        }
+                    }
+                    if (HAS_COL)
+                        fsw_red_add<V>(dXp + row[j] * ldp + k0, v);
+                    else
+                        fsw_store_vec<V>(dXp + row[j] * ldp + k0, v);
+                    if (dEp) fsw_store_vec<V>(dEp + (e0 + i0 + j) * ldp + k0, v);
+                }
+            }
+        }
+        if (NEED_DXI) {
+#pragma unroll
+            for (int q = 0; q < V; ++q)
+                dxi_acc[q] += (double)gk[q] * ((double)A0[q] * (double)Sc[q] + (1.0 + (double)xi[q]) * ((double)A0p[q] * (double)Sc[q] - (double)A0[q] * (double)Ss[q]));
+        }
+    }
+    if (NEED_DXI) {
+#pragma unroll
+        for (int q = 0; q < V; ++q)
+            if (act[q]) atomicAdd(dfreqs + k0 + q, dxi_acc[q]);
+    }
+}
+
+template <bool HAS_COL, bool NEED_DXI>
+int launch_rank_bwdg(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g, int64_t ld_g,
+                     int64_t g_col0, float* dXp, float* dEp, double* dfreqs, float* tables, cudaStream_t st) {
+    const int ldp = (int)a.ldp;
+    float* tab_c = tables;
+    float* tab_t = tab_c + FSW_GTAB_ROWS * ldp;
+    float* tab_A = tab_t + FSW_GTAB_ROWS * ldp;
+    float* tab_Ap = tab_A + (int64_t)FSW_GTAB_NMAX * ldp;
+    fsw_prof_begin("bwd_rank_tables", st);
+    fsw_build_rank_tables_kernel<<<FSW_GTAB_NMAX, 256, 0, st>>>(a.freqs, a.K, ldp, tab_c, NEED_DXI ? tab_t : nullptr, tab_A, tab_Ap);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_build_rank_tables_kernel");
+    const int nchunks = (a.K + 127) / 128;
+    int64_t G = (int64_t)(hi - lo) * nchunks / (148 * 64);
+    if (G < 1) G = 1;
+    if (G > 64) G = 64;
+    const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
+    const int64_t blocks = fsw_cdiv(warps, 4);
+    fsw_prof_begin("bwd_rank_u128_f32", st);
+    fsw_rank_bwdg_kernel<HAS_COL, NEED_DXI><<<(unsigned)blocks, 128, 0, st>>>(a, lo, hi, (int)G, nchunks, ranks, ldr, g, ld_g, g_col0, dXp, dEp,
+                                                                               dfreqs, tab_c, tab_t, tab_A, tab_Ap);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_rank_bwdg_kernel");
+    return FSW_OK;
+}
+
+int pick_G(int64_t cnt, int nchunks, int64_t target_warps, int maxG) {
+    int64_t g = cnt * nchunks / target_warps;
+    if (g < 1) g = 1;
+    if (g > maxG) g = maxG;
+    return (int)g;
+}
+
+template <typename T, int NP, bool HAS_COL, bool SAVE_RANK>
+int launch_small_fwd(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
+                     unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+    const int nchunks = (a.K + 31) / 32;
+    const int G = pick_G(hi - lo, nchunks, 148 * 32, 32);
+    const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
+    const int64_t blocks = fsw_cdiv(warps, 4);
+    const size_t smem = (size_t)4 * NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(int) : 0));
+    auto kern = fsw_small_fwd_kernel<T, NP, HAS_COL, SAVE_RANK>;
+    if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const std::string label = std::string(SAVE_RANK ? "fwdr_small_u" : "fwd_small_u") + std::to_string(NP) + (sizeof(T) == 4 ? "_f32" : "_f64");
+    fsw_prof_begin(label.c_str(), st);
+    kern<<<(unsigned)blocks, 128, smem, st>>>(a, lo, hi, G, nchunks, out, ld_out, out_col0, bias, ranks, ldr);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_small_fwd_kernel");
+    return FSW_OK;
+}
+
+template <typename T, int NP>
+int launch_small_fwd_np(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
+                        unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+    const bool has_col = a.col != nullptr;
+    if (ranks) {
+        return has_col ? launch_small_fwd<T, NP, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st)
+                       : launch_small_fwd<T, NP, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+    }
+    return has_col ? launch_small_fwd<T, NP, true, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st)
+                   : launch_small_fwd<T, NP, false, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+}
+
+template <typename T, bool HAS_COL, bool NEED_DXI>
+int launch_rank_bwd(const SegArgs<T>& a, int lo, int hi, int cap, const unsigned short* ranks, int64_t ldr, const T* g,
+                    int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, cudaStream_t st) {
+    constexpr int W = 4;
+    const int nchunks = (a.K + 31) / 32;
+    const int G = pick_G(hi - lo, nchunks, 148 * 16, 64);
+    const int64_t blocks = fsw_cdiv(hi - lo, G) * nchunks;
+    const size_t smem = (size_t)cap * 32 * sizeof(T) * (NEED_DXI ? 2 : 1);
+    auto kern = fsw_rank_bwd_kernel<T, W, HAS_COL, NEED_DXI>;
+    if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const std::string label = std::string("bwd_rank_u") + std::to_string(cap) + (sizeof(T) == 4 ? "_f32" : "_f64");
+    fsw_prof_begin(label.c_str(), st);
+    kern<<<(unsigned)blocks, W * 32, smem, st>>>(a, lo, hi, G, nchunks, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_rank_bwd_kernel");
+    return FSW_OK;
+}
+
+}  // namespace
+
+// uniform-weight segments order[lo, hi) with n <= np, np in {4, 8, 12, 16, 24, 32, 48, 64}
+template <typename T>
+int fsw_small_forward_u(const SegArgs<T>& a, int np, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
+                        unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+    switch (np) {
+        case 4: return launch_small_fwd_np<T, 4>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        case 8: return launch_small_fwd_np<T, 8>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        case 12: return launch_small_fwd_np<T, 12>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        case 16: return launch_small_fwd_np<T, 16>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        case 24: return launch_small_fwd_np<T, 24>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        case 32: return launch_small_fwd_np<T, 32>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        case 48:
+            if constexpr (sizeof(T) == 4) return launch_small_fwd_np<T, 48>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+            break;
+        case 64:
+            if constexpr (sizeof(T) == 4) return launch_small_fwd_np<T, 64>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+            break;
+    }
+    return fsw_fail(FSW_ERR_INVALID, "fsw_small_forward_u: class %d", np);
+}
+
+// uniform-weight segments order[lo, hi) with n <= cap (cap <= 512: tables in shared memory)
+template <typename T>
+int fsw_rank_backward_u(const SegArgs<T>& a, int lo, int hi, int cap, const unsigned short* ranks, int64_t ldr, const T* g,
+                        int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        // tables must fit shared memory: cap * V * 128 B (x2 with d/dxi)
+        if (cap <= 128) return dispatch_rank_bwdv<4, 4>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+        if (cap <= 256) return dispatch_rank_bwdv<2, 8>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+        return dispatch_rank_bwdv<1, 8>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+    }
+    const bool has_col = a.col != nullptr;
+    if (dfreqs) {
+        return has_col ? launch_rank_bwd<T, true, true>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
+                       : launch_rank_bwd<T, false, true>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+    }
+    return has_col ? launch_rank_bwd<T, true, false>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
+                   : launch_rank_bwd<T, false, false>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+}
+
+template int fsw_small_forward_u<float>(const SegArgs<float>&, int, int, int, float*, int64_t, int64_t, const float*, unsigned short*, int64_t, cudaStream_t);
+template int fsw_small_forward_u<double>(const SegArgs<double>&, int, int, int, double*, int64_t, int64_t, const double*, unsigned short*, int64_t, cudaStream_t);
+template int fsw_rank_backward_u<float>(const SegArgs<float>&, int, int, int, const unsigned short*, int64_t, const float*, int64_t, int64_t, float*, float*, double*, cudaStream_t);
+template int fsw_rank_backward_u<double>(const SegArgs<double>&, int, int, int, const unsigned short*, int64_t, const double*, int64_t, int64_t, double*, double*, double*, cudaStream_t);
+
+// fp32, uniform-weight segments order[lo, hi) with n <= 128: rank-based backward with global coefficient tables
+size_t fsw_rank_tables_bytes(int64_t ldp) { return (size_t)((2 * FSW_GTAB_ROWS + 2 * FSW_GTAB_NMAX) * ldp) * sizeof(float); }
+
+int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g,
+                           int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, void* tables, cudaStream_t st) {
+    const bool has_col = a.col != nullptr;
+    float* tb = (float*)tables;
+    if (dfreqs)
+        return has_col ? launch_rank_bwdg<true, true>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st)
+                       : launch_rank_bwdg<false, true>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st);
+    return has_col ? launch_rank_bwdg<true, false>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st)
+                   : launch_rank_bwdg<false, false>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st);
+}

@@ -9,7 +9,7 @@
 #define FSW_FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------------------------------
-// Batcher odd-even merge sort network over NP compile-time indexed slots (NP power of two).
+// Merge-exchange sorting network over NP compile-time indexed slots (any NP).
 // ---------------------------------------------------------------------------------------------------
 // The comparator list is produced at compile time and applied through a fold expression, so every
 // index is a constant and the arrays stay in registers whatever NP is.
@@ -21,18 +21,30 @@ struct FswNet {
         int b[kMax];
         int n;
     };
+    // Knuth, TAOCP 5.2.2 Algorithm M (merge exchange): valid for every NP, equals Batcher's odd-even
+    // merge sort for powers of two (191 comparators at 32, 543 at 64; 127 at 24, 367 at 48).
     static constexpr Pairs make() {
         Pairs P{};
         int c = 0;
-        for (int p = 1; p < NP; p <<= 1)
-            for (int k = p; k >= 1; k >>= 1)
-                for (int j = k % p; j <= NP - 1 - k; j += 2 * k)
-                    for (int i = 0; i <= ((k - 1) < (NP - j - k - 1) ? (k - 1) : (NP - j - k - 1)); ++i)
-                        if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-                            P.a[c] = i + j;
-                            P.b[c] = i + j + k;
+        if (NP >= 2) {
+            int t = 0;
+            while ((1 << t) < NP) ++t;
+            for (int p = 1 << (t - 1); p > 0; p >>= 1) {
+                int q = 1 << (t - 1), r = 0, d = p;
+                while (true) {
+                    for (int i = 0; i < NP - d; ++i)
+                        if ((i & p) == r) {
+                            P.a[c] = i;
+                            P.b[c] = i + d;
                             ++c;
                         }
+                    if (q == p) break;
+                    d = q - p;
+                    q >>= 1;
+                    r = p;
+                }
+            }
+        }
         P.n = c;
         return P;
     }
@@ -107,4 +119,51 @@ __device__ __forceinline__ void fsw_gather_keys(const SegArgs<T>& a, int64_t eba
 #pragma unroll
         for (int j = 0; j < NP; ++j) key[j] += ep[j];  // +big stays +big (finite + 0)
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lean gather used by the uniform-weight kernels: 5 instructions per element
+//   SHFL (column id) + IMAD.WIDE (byte address) + LDG + ISETP/FSEL (mask slots >= cnt to +big).
+// Column ids are loaded with a clamped index, so every lane holds a valid row and the loads need no
+// predicates (slots >= cnt re-read the last element's row, an L1 hit).  Requires cnt >= 1.
+// ---------------------------------------------------------------------------------------------------
+template <int NP, bool HAS_COL>
+__device__ __forceinline__ void fsw_load_cols(const int32_t* __restrict__ col, int64_t ebase, int cnt, int lane, int& c0, int& c1) {
+    c0 = 0;
+    c1 = 0;
+    if (HAS_COL) {
+        c0 = __ldg(col + ebase + min(lane, cnt - 1));
+        if (NP > 32) c1 = __ldg(col + ebase + min(lane + 32, cnt - 1));
+    }
+}
+
+template <typename T, int NP, bool HAS_COL>
+__device__ __forceinline__ void fsw_gather_lean(const char* __restrict__ xp_bytes, int ldb, const char* __restrict__ ep_bytes,
+                                                int64_t ebase, int cnt, int c0, int c1, T (&key)[NP]) {
+    if (HAS_COL) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const int row = __shfl_sync(FSW_FULL, (j < 32) ? c0 : c1, j & 31);
+            key[j] = __ldg(reinterpret_cast<const T*>(xp_bytes + (int64_t)row * ldb));
+        }
+    } else {
+        const char* __restrict__ base = xp_bytes + ebase * ldb;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            T v = (T)0;
+            if (j < cnt) v = __ldg(reinterpret_cast<const T*>(base + (int64_t)j * ldb));
+            key[j] = v;
+        }
+    }
+    if (ep_bytes != nullptr) {  // edge features: per-slot additive projection (rare path)
+        const char* __restrict__ eb = ep_bytes + ebase * ldb;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            T v = (T)0;
+            if (j < cnt) v = __ldg(reinterpret_cast<const T*>(eb + (int64_t)j * ldb));
+            key[j] += v;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; ++j) key[j] = (j < cnt) ? key[j] : Num<T>::big();
 }

@@ -99,7 +99,7 @@ def project(X, theta_part, ldp):
     return gemm(0, X, theta_part, Nrows, K, d, X.stride(0), theta_part.stride(0), out=out, ldc=ldp)
 
 
-def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias):
+def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks=None):
     lib = _lib.load()
     K = freqs.numel()
     scratch = plan.scratch(K, False)
@@ -107,10 +107,11 @@ def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias):
                                 ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
                                 plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(out), ld_out, out_col0,
                                 ptr(bias), plan.max_n_eff, ptr(scratch), 0 if scratch is None else scratch.numel(),
-                                stream_ptr(plan.device)), "fsw_embed_forward")
+                                ptr(ranks), 0 if ranks is None else ranks.stride(0), stream_ptr(plan.device)),
+          "fsw_embed_forward")
 
 
-def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_acc):
+def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_acc, ranks=None):
     lib = _lib.load()
     K = freqs.numel()
     scratch = plan.scratch(K, True)
@@ -118,7 +119,8 @@ def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_a
                                  ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
                                  plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(g), ld_g, g_col0,
                                  ptr(dXp), ptr(dEp), ptr(dfreqs_acc), None, plan.max_n_eff, ptr(scratch),
-                                 0 if scratch is None else scratch.numel(), stream_ptr(plan.device)),
+                                 0 if scratch is None else scratch.numel(), ptr(ranks),
+                                 0 if ranks is None else ranks.stride(0), stream_ptr(plan.device)),
           "fsw_embed_backward")
 
 
@@ -131,6 +133,11 @@ def total_mass_function(T, name):
     if name == "log":
         return torch.log1p(T)
     raise RuntimeError("This should not happen")
+
+
+# Rank saving (see include/fsw_embedding.h, fsw_embed_forward): on by default, bounded by free memory.
+SAVE_RANKS = True
+RANK_MEMORY_FRACTION = 0.35
 
 
 class FSWEmbedFunction(torch.autograd.Function):
@@ -161,7 +168,20 @@ class FSWEmbedFunction(torch.autograd.Function):
         if bias is not None:
             bias = bias.contiguous()
             bias_core = bias[tm_dim:]
-        embed_forward(plan, Xp, ldp, Ep, freqs.contiguous(), out, d_out, tm_dim, bias_core)
+        # training: record each element's sorted position per slice (uint16) so that the backward needs no sort.
+        # 2 bytes per (element, slice); skipped when that would not fit comfortably (then the backward re-sorts).
+        ranks = None
+        needs_grad = any(ctx.needs_input_grad[:6])
+        if needs_grad and SAVE_RANKS and plan.E > 0 and K > 0:
+            nbytes = plan.E * ldp * 2
+            ok = nbytes < (256 << 20)  # small buffers never need the (slow) driver query
+            if not ok:
+                free_b, _total = torch.cuda.mem_get_info(X.device)
+                ok = nbytes < RANK_MEMORY_FRACTION * free_b
+            if ok:
+                ranks = torch.empty((plan.E, ldp), dtype=torch.int16, device=X.device)
+        embed_forward(plan, Xp, ldp, Ep, freqs.contiguous(), out, d_out, tm_dim, bias_core, ranks)
+        ctx.ranks = ranks
         fT = None
         if tm_dim:
             fT = total_mass_function(plan.mass_as(X.dtype), tm_function)
@@ -196,7 +216,7 @@ class FSWEmbedFunction(torch.autograd.Function):
                 dXp.zero_()
             dEp = torch.zeros((plan.E, ldp), dtype=X.dtype, device=X.device) if ctx.has_E else None
             dxi_acc = torch.zeros(K, dtype=torch.float64, device=X.device) if need_xi else None
-            embed_backward(plan, Xp, ldp, Ep, freqs.contiguous(), g, g.shape[1], tm_dim, dXp, dEp, dxi_acc)
+            embed_backward(plan, Xp, ldp, Ep, freqs.contiguous(), g, g.shape[1], tm_dim, dXp, dEp, dxi_acc, ctx.ranks)
             if need_xi:
                 dxi = dxi_acc.to(X.dtype)
             if need_X:

@@ -150,6 +150,9 @@ int fsw_gemm(int dtype, int op, int64_t M, int64_t N, int64_t Kd, const void* A,
  *  freqs [K]
  *  out  [S, ld_out]: out[s, out_col0 + k] = (1 + xi_k) * sum_j p_(j) D_j  (+ bias[k] if bias != NULL)
  *  scratch: only needed when a segment does not fit shared memory; size from fsw_embed_scratch_bytes.
+ *  ranks_out [E, ldr] uint16 or NULL: when given (training), the forward also records the sorted position
+ *       of every element per slice for the uniform-weight segments of up to 512 elements - the analogue of
+ *       the compressed permutation the reference saves for its backward (fsw_embedding.py:2041-2050).
  * ---------------------------------------------------------------------------------------------- */
 size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bucket_offsets_host, int64_t K, int64_t max_n_eff,
                                int backward);
@@ -157,7 +160,8 @@ int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, co
                       int64_t n_fixed, const int32_t* col, const void* W, const double* mass, const int32_t* info,
                       const int32_t* order, const int32_t* bucket_offsets_host, int64_t S, int64_t K,
                       const void* freqs, double thresh, void* out, int64_t ld_out, int64_t out_col0,
-                      const void* bias, int64_t max_n_eff, void* scratch, size_t scratch_bytes, void* stream);
+                      const void* bias, int64_t max_n_eff, void* scratch, size_t scratch_bytes, void* ranks_out,
+                      int64_t ldr, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 6. K3: fused backward of section 5 (ag.*.backward fsw_embedding.py:1286-2258)
@@ -167,13 +171,15 @@ int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, co
  *  dEp  [E, ldp] or NULL: same value per element (no atomics)
  *  dfreqs_acc [K] float64 or NULL: += dL/dxi_k (atomics; caller zero-initialises)
  *  dW   [E] or NULL: dL/dW (raw weights) - written, not accumulated
+ *  ranks [E, ldr] uint16 or NULL: positions recorded by fsw_embed_forward; with them the backward of the
+ *        covered segments is a streaming pass without any sort, otherwise everything is re-sorted.
  * ---------------------------------------------------------------------------------------------- */
 int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,
                        int64_t n_fixed, const int32_t* col, const void* W, const double* mass,
                        const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host, int64_t S,
                        int64_t K, const void* freqs, double thresh, const void* g, int64_t ld_g, int64_t g_col0,
                        void* dXp, void* dEp, double* dfreqs_acc, void* dW, int64_t max_n_eff, void* scratch,
-                       size_t scratch_bytes, void* stream);
+                       size_t scratch_bytes, const void* ranks, int64_t ldr, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 7. Counters and per-kernel timers (the reference has only unused wall-clock globals,
