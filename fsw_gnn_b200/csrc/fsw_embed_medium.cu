@@ -46,6 +46,43 @@ template <>
 __device__ __forceinline__ float fsw_inf<float>() { return __int_as_float(0x7f800000); }
 
 // ---------------------------------------------------------------------------------------------------
+// One merge work unit: UNIT outputs of merge(A, B) starting after (ia, ib) elements were consumed.
+// A and B are runs in the same buffer `src` (element r of the buffer at src[r * 32 + lane]); rows are
+// addressed with 32-bit indices ga / gb, limits ea / eb.  Branch-free: every lane runs the same UNIT steps.
+// emit(t, value, payload) is called once per output in sorted order.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, typename IdxT, bool PAY, typename F>
+__device__ __forceinline__ void fsw_merge_unit(const T* __restrict__ src, const IdxT* __restrict__ isrc, int ga, int ea, int gb,
+                                               int eb, int lane, T INF, F&& emit) {
+    T av = (ga < ea) ? src[ga * 32 + lane] : INF;
+    T bv = (gb < eb) ? src[gb * 32 + lane] : INF;
+    int ai = 0, bi = 0;
+    if (PAY) {
+        ai = (ga < ea) ? (int)isrc[ga * 32 + lane] : 0;
+        bi = (gb < eb) ? (int)isrc[gb * 32 + lane] : 0;
+    }
+#pragma unroll 8
+    for (int t = 0; t < UNIT; ++t) {
+        const bool ta = av <= bv;
+        emit(t, ta ? av : bv, ta ? ai : bi);
+        if (ta) ++ga; else ++gb;
+        const int gn = ta ? ga : gb;
+        const bool ok = gn < (ta ? ea : eb);
+        T nv = INF;
+        int ni = 0;
+        if (ok) {
+            nv = src[gn * 32 + lane];
+            if (PAY) ni = (int)isrc[gn * 32 + lane];
+        }
+        av = ta ? nv : av;
+        bv = ta ? bv : nv;
+        if (PAY) {
+            ai = ta ? ni : ai;
+            bi = ta ? bi : ni;
+        }
+    }
+}
+
 // MODE 0: forward, keys only.  MODE 1: forward that also records the sorted position of every element
 // (uint16 ranks, consumed by the rank-based backward).  MODE 2: backward that re-sorts (no saved ranks).
 template <int MODE, bool USE_TABLE, typename T, typename IdxT>
@@ -85,6 +122,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
     T A0 = (T)0, A0p = (T)0;
     (void)A0p;
     const T INF = fsw_inf<T>();
+    const int ldb = (int)(a.ldp * (int64_t)sizeof(T));
 
   for (int64_t work = blockIdx.x; work < nwork; work += gridDim.x) {   // persistent over (item, chunk) work groups
     const int item = (int)(work / nchunks);
@@ -99,6 +137,8 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
     const T xi = fsw_ldg(a.freqs + kk);
     const double xid = (double)xi;
     const T bk = (!BWD && bias != nullptr) ? fsw_ldg(bias + kk) : (T)0;
+    const char* xp_bytes = reinterpret_cast<const char*>(a.Xp + kk);
+    const char* ep_bytes = a.Ep ? reinterpret_cast<const char*>(a.Ep + kk) : nullptr;
     double dxi_acc = 0.0;
     (void)dxi_acc;
 
@@ -130,12 +170,15 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
             T key[32];
             int idx[32];
             (void)idx;
-            fsw_gather_keys<T, 32>(a, e0 + base, cnt, kk, lane, key, c0, c1);
+            if (a.col) {
+                fsw_load_cols<32, true>(a.col, e0 + base, cnt, lane, c0, c1);
+                fsw_gather_lean<T, 32, true>(xp_bytes, ldb, ep_bytes, e0 + base, cnt, c0, c1, key);
+            } else {
+                fsw_gather_lean<T, 32, false>(xp_bytes, ldb, ep_bytes, e0 + base, cnt, 0, 0, key);
+            }
             if (PAY) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) idx[j] = base + j;
-            }
-            if (PAY) {
                 fsw_sort_network<32>([&](int i, int l) {
                     T x = key[i], y = key[l];
                     int px = idx[i], py = idx[l];
@@ -160,90 +203,90 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
         }
         __syncthreads();
 
-        // ---- 2./3. merge passes; the last one is consumed instead of stored ----
+        // ---- 2. merge passes that store their output ----
         T* src = bufA;
         T* dst = bufB;
         IdxT* isrc = idxA;
         IdxT* idst = idxB;
         const int nunits = Ntot / UNIT;
-        const T gk = (BWD && act) ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
-        const T GA = gk * ((T)1 + xi) * A0;
-        double acc = 0.0, Sc = 0.0, Ss = 0.0;
-        (void)GA;
-        (void)Sc;
-        (void)Ss;
-        for (int len = 32;; len <<= 1) {
-            const bool final_pass = (len << 1) >= Ntot;
+        int len = 32;
+        while ((len << 1) < Ntot) {
             const int iters = 33 - __clz(len);
             for (int un = warp; un < nunits; un += W) {
                 const int o = un * UNIT;
-                const int pair = o / (2 * len);
-                const int p0 = pair * 2 * len;
+                const int p0 = (o / (2 * len)) * 2 * len;
                 const int La = min(len, Ntot - p0);
                 const int Lb = min(len, max(0, Ntot - p0 - len));
                 const int oo = o - p0;
-                const T* Aq = src + (size_t)p0 * 32;
-                const T* Bq = Aq + (size_t)La * 32;
-                int ia = (oo > 0) ? fsw_merge_path(Aq, La, Bq, Lb, oo, iters, lane) : 0;
-                int ib = oo - ia;
-                T av = (ia < La) ? Aq[ia * 32 + lane] : INF;
-                T bv = (ib < Lb) ? Bq[ib * 32 + lane] : INF;
-#pragma unroll 4
-                for (int t = 0; t < UNIT; ++t) {
-                    const bool takeA = av <= bv;
-                    const T v = takeA ? av : bv;
-                    const int pos = o + t;
-                    int src_row;  // row (inside the pair) the value came from
-                    if (takeA) {
-                        src_row = ia;
-                        ++ia;
-                    } else {
-                        src_row = La + ib;
-                        ++ib;
-                    }
-                    if (!final_pass) {
-                        dst[pos * 32 + lane] = v;
-                        if (PAY) idst[pos * 32 + lane] = isrc[(p0 + src_row) * 32 + lane];
-                    } else if (!BWD) {
-                        if (USE_TABLE)
-                            acc += (double)(v * table[pos * 32 + lane]);
-                        else if (pos < n)
-                            acc += (double)(v * Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * pos + 1))));
-                        if (MODE == 1 && pos < n) {
-                            // un-permute through the free ping-pong buffer; stored coalesced after the pass
-                            const int id = isrc[(p0 + src_row) * 32 + lane];
-                            dst[id * 32 + lane] = __int_as_float(pos);
-                        }
-                    } else if (pos < n) {
-                        const T r = Num<T>::reduce(u * (double)(2 * pos + 1));
-                        const T c = Num<T>::cospi_(r);
-                        const int id = isrc[(p0 + src_row) * 32 + lane];
-                        dst[id * 32 + lane] = GA * c;
-                        if (NEED_DXI) {
-                            Sc += (double)(v * c);
-                            Ss += (double)(v * ((T)M_PI * wn * (T)(2 * pos + 1) * Num<T>::sinpi_(r)));
-                        }
-                    }
-                    // refill the head that was consumed
-                    const int nxt = takeA ? ia : ib;
-                    const int lim = takeA ? La : Lb;
-                    const T* base_ptr = takeA ? Aq : Bq;
-                    const T nv = (nxt < lim) ? base_ptr[nxt * 32 + lane] : INF;
-                    if (takeA)
-                        av = nv;
-                    else
-                        bv = nv;
-                }
+                const int ia = (oo > 0) ? fsw_merge_path(src + (size_t)p0 * 32, La, src + (size_t)(p0 + La) * 32, Lb, oo, iters, lane) : 0;
+                T* dk = dst + o * 32 + lane;
+                IdxT* di = idst + o * 32 + lane;
+                fsw_merge_unit<T, IdxT, PAY>(src, isrc, p0 + ia, p0 + La, p0 + La + (oo - ia), p0 + La + Lb, lane, INF,
+                                             [&](int t, T v, int id) {
+                                                 dk[t * 32] = v;
+                                                 if (PAY) di[t * 32] = (IdxT)id;
+                                             });
             }
             __syncthreads();
-            if (final_pass) break;
             T* tk = src;
             src = dst;
             dst = tk;
             IdxT* ti = isrc;
             isrc = idst;
             idst = ti;
+            len <<= 1;
         }
+
+        // ---- 3. last pass: the merged stream is consumed, not stored ----
+        const T gk = (BWD && act) ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
+        const T GA = gk * ((T)1 + xi) * A0;
+        (void)GA;
+        double acc = 0.0, Sc = 0.0, Ss = 0.0;
+        (void)Sc;
+        (void)Ss;
+        {
+            const int iters = 33 - __clz(len);
+            const int La = min(len, Ntot);
+            const int Lb = Ntot - La;
+            for (int un = warp; un < nunits; un += W) {
+                const int o = un * UNIT;
+                const int ia = (o > 0) ? fsw_merge_path(src, La, src + (size_t)La * 32, Lb, o, iters, lane) : 0;
+                T facc = (T)0, fSc = (T)0, fSs = (T)0;
+                (void)fSc;
+                (void)fSs;
+                fsw_merge_unit<T, IdxT, PAY>(src, isrc, ia, La, La + (o - ia), Ntot, lane, INF, [&](int t, T v, int id) {
+                    const int pos = o + t;
+                    if (MODE != 2) {
+                        T c;
+                        if (USE_TABLE)
+                            c = table[pos * 32 + lane];
+                        else
+                            c = (pos < n) ? Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * pos + 1))) : (T)0;
+                        facc = fma(v, c, facc);
+                        // un-permute the position through the free ping-pong buffer (rows >= n are padding, never read back)
+                        if (MODE == 1) dst[id * 32 + lane] = __int_as_float(pos);
+                    } else {
+                        T c = (T)0, sn = (T)0;
+                        if (pos < n) {
+                            const T r = Num<T>::reduce(u * (double)(2 * pos + 1));
+                            c = Num<T>::cospi_(r);
+                            if (NEED_DXI) sn = Num<T>::sinpi_(r);
+                        }
+                        dst[id * 32 + lane] = GA * c;
+                        if (NEED_DXI) {
+                            fSc = fma(v, c, fSc);
+                            fSs = fma(v, (T)M_PI * wn * (T)(2 * pos + 1) * sn, fSs);
+                        }
+                    }
+                });
+                acc += (double)facc;
+                if (NEED_DXI) {
+                    Sc += (double)fSc;
+                    Ss += (double)fSs;
+                }
+            }
+        }
+        __syncthreads();
 
         if (MODE == 1) {
             for (int r = warp; r < n; r += W)

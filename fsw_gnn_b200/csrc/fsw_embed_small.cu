@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float*
 }
 
 template <bool HAS_COL, bool NEED_DXI>
-__global__ void __launch_bounds__(128) fsw_rank_bwdg_kernel(SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks,
+__global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks,
                                                             const unsigned short* __restrict__ ranks, int64_t ldr,
                                                             const float* __restrict__ g, int64_t ld_g, int64_t g_col0,
                                                             float* __restrict__ dXp, float* __restrict__ dEp,
@@ -558,15 +558,17 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdg_kernel(SegArgs<float> a, in
         int64_t e0;
         int n;
         fsw_ld_range(a, s, e0, n);
-        float A0[V], A0p[V], gk[V], GA[V], Sc[V], Ss[V];
-        fsw_load_vec<V>(tab_A + (int64_t)(n - 1) * ldp + k0, A0);
-        if (NEED_DXI) fsw_load_vec<V>(tab_Ap + (int64_t)(n - 1) * ldp + k0, A0p);
+        float GA[V], Sc[V], Ss[V];
+        {
+            float A0[V];
+            fsw_load_vec<V>(tab_A + (int64_t)(n - 1) * ldp + k0, A0);
 #pragma unroll
-        for (int q = 0; q < V; ++q) {
-            gk[q] = act[q] ? __ldg(g + (int64_t)s * ld_g + g_col0 + k0 + q) : 0.f;
-            GA[q] = gk[q] * (1.f + xi[q]) * A0[q];
-            Sc[q] = 0.f;
-            Ss[q] = 0.f;
+            for (int q = 0; q < V; ++q) {
+                const float gk = act[q] ? __ldg(g + (int64_t)s * ld_g + g_col0 + k0 + q) : 0.f;
+                GA[q] = gk * (1.f + xi[q]) * A0[q];
+                Sc[q] = 0.f;
+                Ss[q] = 0.f;
+            }
         }
         const float* tc = tab_c + ((int64_t)n * (n - 1) / 2) * ldp + k0;
         const float* tt = NEED_DXI ? tab_t + ((int64_t)n * (n - 1) / 2) * ldp + k0 : nullptr;
@@ -618,9 +620,15 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdg_kernel(SegArgs<float> a, in
             }
         }
         if (NEED_DXI) {
+            // amplitudes and g are re-read here (L1 hits) instead of being kept live across the element loop
+            float A0[V], A0p[V];
+            fsw_load_vec<V>(tab_A + (int64_t)(n - 1) * ldp + k0, A0);
+            fsw_load_vec<V>(tab_Ap + (int64_t)(n - 1) * ldp + k0, A0p);
 #pragma unroll
-            for (int q = 0; q < V; ++q)
-                dxi_acc[q] += (double)gk[q] * ((double)A0[q] * (double)Sc[q] + (1.0 + (double)xi[q]) * ((double)A0p[q] * (double)Sc[q] - (double)A0[q] * (double)Ss[q]));
+            for (int q = 0; q < V; ++q) {
+                const float gk = act[q] ? __ldg(g + (int64_t)s * ld_g + g_col0 + k0 + q) : 0.f;
+                dxi_acc[q] += (double)gk * ((double)A0[q] * (double)Sc[q] + (1.0 + (double)xi[q]) * ((double)A0p[q] * (double)Sc[q] - (double)A0[q] * (double)Ss[q]));
+            }
         }
     }
     if (NEED_DXI) {
