@@ -134,7 +134,7 @@ struct SegArgs {
 // medium / large path (fsw_embed_medium.cu): uniform-weight fp32 segments of more than 64 elements
 int fsw_medium_forward_f32(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
                            const float* bias, void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr,
-                           cudaStream_t st);
+                           float* dxi_out, int64_t ld_dxi, cudaStream_t st);
 int fsw_medium_backward_f32(const SegArgs<float>& a, int lo, int hi, int cap, const float* g, int64_t ld_g, int64_t g_col0,
                             float* dXp, float* dEp, double* dfreqs, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t fsw_medium_tile_bytes(int cap, int mode);  // global scratch per CTA (0: shared-memory tile)
@@ -143,7 +143,7 @@ int fsw_medium_grid();
 // uniform-weight small path + rank-based backward (fsw_embed_small.cu)
 template <typename T>
 int fsw_small_forward_u(const SegArgs<T>& a, int np, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
-                        unsigned short* ranks, int64_t ldr, cudaStream_t st);
+                        unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, cudaStream_t st);
 template <typename T>
 int fsw_rank_backward_u(const SegArgs<T>& a, int lo, int hi, int cap, const unsigned short* ranks, int64_t ldr, const T* g,
                         int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, cudaStream_t st);
@@ -151,6 +151,10 @@ int fsw_rank_backward_u(const SegArgs<T>& a, int lo, int hi, int cap, const unsi
 size_t fsw_rank_tables_bytes(int64_t ldp);
 int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g,
                            int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, void* tables, cudaStream_t st);
+
+int fsw_rank_backward_T(const SegArgs<float>& a, int64_t Nrows, const int32_t* tptr, const int32_t* tseg, const int32_t* tslot,
+                        const int32_t* tn, const unsigned short* ranks, int64_t ldr, const float* g, int64_t ld_g, int64_t g_col0,
+                        float* dXp, float* dEp, void* tables, cudaStream_t st);
 
 template <typename T>
 __device__ __forceinline__ void fsw_seg_range(const SegArgs<T>& a, int s, int64_t& e0, int& n) {

@@ -708,7 +708,7 @@ const ClassRange kSmallU[] = {{0, 4, 4}, {5, 8, 8}, {9, 12, 12}, {13, 16, 16}, {
 template <typename T>
 int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
                     int64_t max_n_eff, void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr,
-                    cudaStream_t st) {
+                    T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int msn = max_small_np<T>();
     for (int kind = 0; kind < 2; ++kind) {
@@ -718,7 +718,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 if (c.np > msn) continue;
                 const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
                 if (hi <= lo) continue;
-                int rc = fsw_small_forward_u<T>(a, c.np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+                int rc = fsw_small_forward_u<T>(a, c.np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
                 if (rc) return rc;
             }
         } else {
@@ -738,7 +738,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
                 if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 64 elements
-                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, st);
+                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, st);
                     if (rc) return rc;
                     continue;
                 }
@@ -774,24 +774,41 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
     return FSW_OK;
 }
 
-template <typename T, bool NEED_DXI>
+// Transposed segment structure for the source-major backward (optional; graphs only)
+struct TransposeArgs {
+    const int32_t* tptr;
+    const int32_t* tseg;
+    const int32_t* tslot;
+    const int32_t* tn;
+    int64_t nrows;
+};
+
+// `dxi_fwd`: the forward already produced d out / d xi for the uniform-weight classes it ran with rank
+// recording (all small classes; fp32 medium classes up to 32768 elements), so their backward runs without the
+// frequency gradient; every other class accumulates it into `dfreqs` (when requested).
+template <typename T>
 int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp,
-                     double* dfreqs, int64_t max_n_eff, void* scratch, size_t scratch_bytes, const unsigned short* ranks,
-                     int64_t ldr, cudaStream_t st) {
+                     double* dfreqs, bool dxi_fwd, int64_t max_n_eff, void* scratch, size_t scratch_bytes,
+                     const unsigned short* ranks, int64_t ldr, const TransposeArgs& tr, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int msn = max_small_np<T>();
+    const bool have_ranks = ranks != nullptr;
+    double* dfreqs_cov = (have_ranks && dxi_fwd) ? nullptr : dfreqs;  // for classes covered by the forward d/dxi
     for (int kind = 0; kind < 2; ++kind) {
         const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
-        if (kind == 0 && ranks != nullptr) {
-            // rank-based backward: no sorting.  One launch for all small classes, one per medium class that
-            // recorded ranks in the forward (fp32, <= 512 elements); anything larger re-sorts below.
+        if (kind == 0 && have_ranks) {
+            // rank-based backward: no sorting
             if constexpr (sizeof(T) == 4) {
-                // n <= 128: global coefficient tables (first bytes of the scratch), independent warps, v4 atomics
                 const size_t tb = fsw_rank_tables_bytes(a.ldp);
                 if (scratch_bytes < tb) return fsw_fail(FSW_ERR_WORKSPACE, "embed scratch too small for the rank tables");
                 const int lo0 = bo[base + 0], hi0 = bo[base + 128 + 1];
                 if (hi0 > lo0) {
-                    int rc = fsw_rank_backward_g128(a, lo0, hi0, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, st);
+                    int rc;
+                    if (a.col != nullptr && tr.tptr != nullptr && dfreqs_cov == nullptr)
+                        // graphs: source-major, one plain store per row of dXp (must precede every atomic kernel)
+                        rc = fsw_rank_backward_T(a, tr.nrows, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, st);
+                    else
+                        rc = fsw_rank_backward_g128(a, lo0, hi0, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, scratch, st);
                     if (rc) return rc;
                 }
                 scratch = (unsigned char*)scratch + tb;
@@ -800,24 +817,29 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
                 for (int i = 0; i < 2; ++i) {
                     const int lo = bo[base + rk[i].lo], hi = bo[base + rk[i].hi + 1];
                     if (hi <= lo) continue;
-                    int rc = fsw_rank_backward_u<T>(a, lo, hi, rk[i].cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+                    int rc = fsw_rank_backward_u<T>(a, lo, hi, rk[i].cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, st);
                     if (rc) return rc;
                 }
             } else {
                 const int lo = bo[base + 0], hi = bo[base + msn + 1];
                 if (hi > lo) {
-                    int rc = fsw_rank_backward_u<T>(a, lo, hi, msn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+                    int rc = fsw_rank_backward_u<T>(a, lo, hi, msn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, st);
                     if (rc) return rc;
                 }
             }
         }
         for (const ClassRange& c : kSmall) {
-            if (kind == 0 && ranks != nullptr) break;
+            if (kind == 0 && have_ranks) break;
             if (c.np > msn) continue;
             const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
             if (hi <= lo) continue;
-            int rc = kind == 0 ? dispatch_bwd_small<T, true, NEED_DXI>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
-                               : dispatch_bwd_small<T, false, NEED_DXI>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+            int rc;
+            if (dfreqs)
+                rc = kind == 0 ? dispatch_bwd_small<T, true, true>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
+                               : dispatch_bwd_small<T, false, true>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
+            else
+                rc = kind == 0 ? dispatch_bwd_small<T, true, false>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st)
+                               : dispatch_bwd_small<T, false, false>(a, c.np, lo, hi, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
             if (rc) return rc;
         }
         SizeRange rr[12];
@@ -827,9 +849,11 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             const int cap = rr[ri].cap;
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
-                if (kind == 0 && cap >= 128 && cap <= 512 && ranks != nullptr) continue;  // done by the rank kernel
+                if (kind == 0 && cap >= 128 && cap <= 512 && have_ranks) continue;  // done by the rank kernel
                 if (kind == 0 && cap >= 128) {
-                    int rc = fsw_medium_backward_f32(a, lo, hi, cap, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, st);
+                    // re-sorting backward; the forward produced d/dxi for these when it recorded ranks (cap <= 32768)
+                    double* df = (have_ranks && cap <= 32768) ? dfreqs_cov : dfreqs;
+                    int rc = fsw_medium_backward_f32(a, lo, hi, cap, g, ld_g, g_col0, dXp, dEp, df, scratch, scratch_bytes, st);
                     if (rc) return rc;
                     continue;
                 }
@@ -849,15 +873,18 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             }
             const std::string label = std::string("bwd_generic_") + (kind == 0 ? "u" : "g") + std::to_string(cap) + (sizeof(T) == 4 ? "_f32" : "_f64");
             fsw_prof_begin(label.c_str(), st);
+#define FSW_GEN_BWD(UNI, DXI)                                                                                      \
+    do {                                                                                                         \
+        auto kern = fsw_bwd_generic_kernel<T, UNI, DXI>;                                                         \
+        if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);        \
+    } while (0)
             if (kind == 0) {
-                auto kern = fsw_bwd_generic_kernel<T, true, NEED_DXI>;
-                if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);
+                if (dfreqs) FSW_GEN_BWD(true, true); else FSW_GEN_BWD(true, false);
             } else {
-                auto kern = fsw_bwd_generic_kernel<T, false, NEED_DXI>;
-                if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<grid, 256, smem, st>>>(a, lo, nchunks, ntiles, g, ld_g, g_col0, dXp, dEp, dfreqs, cap, gs);
+                if (dfreqs) FSW_GEN_BWD(false, true); else FSW_GEN_BWD(false, false);
             }
+#undef FSW_GEN_BWD
             fsw_prof_end(st);
             FSW_CHECK_LAUNCH("fsw_bwd_generic_kernel");
         }
@@ -907,7 +934,8 @@ extern "C" int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const v
                                  const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host,
                                  int64_t S, int64_t K, const void* freqs, double thresh, void* out, int64_t ld_out,
                                  int64_t out_col0, const void* bias, int64_t max_n_eff, void* scratch,
-                                 size_t scratch_bytes, void* ranks_out, int64_t ldr, void* stream) {
+                                 size_t scratch_bytes, void* ranks_out, int64_t ldr, void* dxi_out, int64_t ld_dxi,
+                                 void* stream) {
     if (S == 0 || K == 0) return FSW_OK;
     if (!Xp || !mass || !info || !bucket_offsets_host || !freqs || !out)
         return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: null argument");
@@ -915,10 +943,10 @@ extern "C" int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const v
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FSW_F32) {
         auto a = make_args<float>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
-        return embed_forward_t<float>(a, bucket_offsets_host, (float*)out, ld_out, out_col0, (const float*)bias, max_n_eff, scratch, scratch_bytes, (unsigned short*)ranks_out, ldr, st);
+        return embed_forward_t<float>(a, bucket_offsets_host, (float*)out, ld_out, out_col0, (const float*)bias, max_n_eff, scratch, scratch_bytes, (unsigned short*)ranks_out, ldr, (float*)dxi_out, ld_dxi, st);
     } else if (dtype == FSW_F64) {
         auto a = make_args<double>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
-        return embed_forward_t<double>(a, bucket_offsets_host, (double*)out, ld_out, out_col0, (const double*)bias, max_n_eff, scratch, scratch_bytes, (unsigned short*)ranks_out, ldr, st);
+        return embed_forward_t<double>(a, bucket_offsets_host, (double*)out, ld_out, out_col0, (const double*)bias, max_n_eff, scratch, scratch_bytes, (unsigned short*)ranks_out, ldr, (double*)dxi_out, ld_dxi, st);
     }
     return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: dtype %d", dtype);
 }
@@ -929,7 +957,8 @@ extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const 
                                   int64_t S, int64_t K, const void* freqs, double thresh, const void* g, int64_t ld_g,
                                   int64_t g_col0, void* dXp, void* dEp, double* dfreqs_acc, void* dW,
                                   int64_t max_n_eff, void* scratch, size_t scratch_bytes, const void* ranks, int64_t ldr,
-                                  void* stream) {
+                                  int dxi_from_forward, const int32_t* tptr, const int32_t* tseg, const int32_t* tslot,
+                                  const int32_t* tn, int64_t nrows, void* stream) {
     if (S == 0 || K == 0) return FSW_OK;
     if (dW != nullptr)
         return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_embed_backward: gradient w.r.t. the weights W is not implemented");
@@ -937,16 +966,15 @@ extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const 
         return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: null argument");
     if (!rowptr && n_fixed <= 0) return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: rowptr == NULL needs n_fixed > 0");
     cudaStream_t st = (cudaStream_t)stream;
+    TransposeArgs tr{tptr, tseg, tslot, tn, nrows};
     if (dtype == FSW_F32) {
         auto a = make_args<float>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
-        if (dfreqs_acc)
-            return embed_backward_t<float, true>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
-        return embed_backward_t<float, false>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
+        return embed_backward_t<float>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, dfreqs_acc,
+                                       dxi_from_forward != 0, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, tr, st);
     } else if (dtype == FSW_F64) {
         auto a = make_args<double>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
-        if (dfreqs_acc)
-            return embed_backward_t<double, true>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, dfreqs_acc, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
-        return embed_backward_t<double, false>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, nullptr, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, st);
+        return embed_backward_t<double>(a, bucket_offsets_host, (const double*)g, ld_g, g_col0, (double*)dXp, (double*)dEp, dfreqs_acc,
+                                        dxi_from_forward != 0, max_n_eff, scratch, scratch_bytes, (const unsigned short*)ranks, ldr, tr, st);
     }
     return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: dtype %d", dtype);
 }

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                                                             const T* __restrict__ g, int64_t ld_g, int64_t g_col0,
                                                             T* __restrict__ dXp, T* __restrict__ dEp,
                                                             double* __restrict__ dfreqs, unsigned char* gscratch,
-                                                            unsigned short* __restrict__ ranks, int64_t ldr) {
+                                                            unsigned short* __restrict__ ranks, int64_t ldr,
+                                                            T* __restrict__ dxi_out, int64_t ld_dxi) {
     extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
     __shared__ double red[W][32];
     __shared__ double red2[W][32];
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
         const T wn = (T)(1.0 / (double)n);
 
         if (n != n_prev) {
-            fsw_amplitude<T, NEED_DXI>(u, wn, xi, A0, A0p);
+            fsw_amplitude<T, (NEED_DXI || MODE == 1)>(u, wn, xi, A0, A0p);
             if (USE_TABLE) {
                 // coefficient table for this (n, slice): first read happens after the barrier below
                 for (int r = warp; r < Ntot; r += W)
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
         }
 
         // ---- 3. last pass: the merged stream is consumed, not stored ----
+        const bool want_dxi = (MODE == 1) && (dxi_out != nullptr);
+        (void)want_dxi;
         const T gk = (BWD && act) ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
         const T GA = gk * ((T)1 + xi) * A0;
         (void)GA;
@@ -258,10 +261,21 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                     const int pos = o + t;
                     if (MODE != 2) {
                         T c;
-                        if (USE_TABLE)
+                        if (MODE == 1 && want_dxi) {
+                            // training with learnable frequencies: d out / d xi needs the sine as well
+                            T sn = (T)0;
+                            c = (T)0;
+                            if (pos < n) {
+                                const T r = Num<T>::reduce(u * (double)(2 * pos + 1));
+                                c = Num<T>::cospi_(r);
+                                sn = Num<T>::sinpi_(r);
+                            }
+                            fSs = fma(v, (T)M_PI * wn * (T)(2 * pos + 1) * sn, fSs);
+                        } else if (USE_TABLE) {
                             c = table[pos * 32 + lane];
-                        else
+                        } else {
                             c = (pos < n) ? Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * pos + 1))) : (T)0;
+                        }
                         facc = fma(v, c, facc);
                         // un-permute the position through the free ping-pong buffer (rows >= n are padding, never read back)
                         if (MODE == 1) dst[id * 32 + lane] = __int_as_float(pos);
@@ -284,6 +298,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                     Sc += (double)fSc;
                     Ss += (double)fSs;
                 }
+                if (MODE == 1) Ss += (double)fSs;
             }
         }
         __syncthreads();
@@ -294,12 +309,18 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
         }
         if (!BWD) {
             red[warp][lane] = acc;
+            if (MODE == 1) red2[warp][lane] = Ss;
             __syncthreads();
             if (warp == 0 && act) {
-                double tot = 0.0;
+                double tot = 0.0, tots = 0.0;
 #pragma unroll
-                for (int w2 = 0; w2 < W; ++w2) tot += red[w2][lane];
+                for (int w2 = 0; w2 < W; ++w2) {
+                    tot += red[w2][lane];
+                    if (MODE == 1) tots += red2[w2][lane];
+                }
                 out[(int64_t)s * ld_out + out_col0 + k] = ((T)1 + xi) * A0 * (T)tot + bk;
+                if (MODE == 1 && want_dxi)
+                    dxi_out[(int64_t)s * ld_dxi + k] = (T)((double)A0 * tot + (1.0 + xid) * ((double)A0p * tot - (double)A0 * tots));
             }
         } else {
             // dst now holds dL/dp in ORIGINAL row order
@@ -339,7 +360,7 @@ const int kPersistentGrid = 148 * 2;
 template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE>
 int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
                   const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, void* scratch,
-                  size_t scratch_bytes, unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+                  size_t scratch_bytes, unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int64_t cnt = hi - lo;
     int64_t G = GLOBAL ? 1 : cnt * nchunks / (148 * 8);
@@ -362,7 +383,7 @@ int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t 
     const std::string label = std::string(names[MODE]) + std::to_string(cap) + "_f32";
     fsw_prof_begin(label.c_str(), st);
     kern<<<(unsigned)blocks, W * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, cap, nwork, out, ld_out, out_col0, bias, g, ld_g, g_col0,
-                                                  dXp, dEp, dfreqs, (unsigned char*)scratch, ranks, ldr);
+                                                  dXp, dEp, dfreqs, (unsigned char*)scratch, ranks, ldr, dxi_out, ld_dxi);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_medium_kernel");
     return FSW_OK;
@@ -371,9 +392,10 @@ int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t 
 template <int MODE, bool NEED_DXI>
 int dispatch_medium(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
                     const float* bias, const float* g, int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs,
-                    void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+                    void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi,
+                    cudaStream_t st) {
 #define FSW_MED(IDX, W, GLOBAL, TABLE) \
-    launch_medium<float, IDX, W, MODE, NEED_DXI, GLOBAL, TABLE>(a, lo, hi, cap, out, ld_out, out_col0, bias, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, ranks, ldr, st)
+    launch_medium<float, IDX, W, MODE, NEED_DXI, GLOBAL, TABLE>(a, lo, hi, cap, out, ld_out, out_col0, bias, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, st)
     constexpr bool FWD = MODE != 2;
     if (cap <= 128) return FSW_MED(unsigned short, 4, false, FWD);
     if (cap <= 256) return FSW_MED(unsigned short, 8, false, FWD);
@@ -397,19 +419,19 @@ int fsw_medium_grid() { return kPersistentGrid; }
 // uniform-weight fp32 segments order[lo, hi) whose size class is `cap` (>= 128); ranks != NULL records positions
 int fsw_medium_forward_f32(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
                            const float* bias, void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr,
-                           cudaStream_t st) {
+                           float* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     if (ranks != nullptr && cap <= 32768)
         return dispatch_medium<1, false>(a, lo, hi, cap, out, ld_out, out_col0, bias, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                         scratch, scratch_bytes, ranks, ldr, st);
+                                         scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, st);
     return dispatch_medium<0, false>(a, lo, hi, cap, out, ld_out, out_col0, bias, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                     scratch, scratch_bytes, nullptr, 0, st);
+                                     scratch, scratch_bytes, nullptr, 0, nullptr, 0, st);
 }
 
 int fsw_medium_backward_f32(const SegArgs<float>& a, int lo, int hi, int cap, const float* g, int64_t ld_g, int64_t g_col0,
                             float* dXp, float* dEp, double* dfreqs, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     if (dfreqs != nullptr)
         return dispatch_medium<2, true>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
-                                        scratch_bytes, nullptr, 0, st);
+                                        scratch_bytes, nullptr, 0, nullptr, 0, st);
     return dispatch_medium<2, false>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
-                                     scratch_bytes, nullptr, 0, st);
+                                     scratch_bytes, nullptr, 0, nullptr, 0, st);
 }

@@ -49,15 +49,18 @@ template <typename T, int NP, bool HAS_COL, bool SAVE_RANK>
 __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks,
                                                             T* __restrict__ out, int64_t ld_out, int64_t out_col0,
                                                             const T* __restrict__ bias, unsigned short* __restrict__ ranks,
-                                                            int64_t ldr) {
+                                                            int64_t ldr, T* __restrict__ dxi_out, int64_t ld_dxi) {
     extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // per warp: coefficient table [NP][32] T  (+ rank scratch [NP][32] int when SAVE_RANK)
-    constexpr size_t kWarpBytes = (size_t)NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(int) : 0));
+    // per warp: coefficient table [NP][32] T; when SAVE_RANK (training) also the d/dxi table [NP][32] T and the
+    // rank scratch [NP][32] int
+    constexpr size_t kWarpBytes = (size_t)NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + sizeof(int) : 0));
     T* tab = reinterpret_cast<T*>(fsw_smem_raw + warp * kWarpBytes);
-    int* srank = reinterpret_cast<int*>(tab + NP * 32);
+    T* tabt = tab + NP * 32;
+    int* srank = reinterpret_cast<int*>(tabt + NP * 32);
     (void)srank;
+    (void)tabt;
 
     const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const int64_t item = wglobal / nchunks;
@@ -88,7 +91,9 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
     s2 = fsw_ld_order(a, first + 2, last);
 
     int n_prev = -1;
-    T A = (T)0;
+    T A = (T)0, A0 = (T)0, A0p = (T)0;
+    (void)A0;
+    (void)A0p;
 
     for (int q = first; q < last; ++q) {
         const int n = cur.n;
@@ -104,12 +109,15 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
 
         if (n != n_prev) {
             const double u = xid / (double)n;
+            const T wn = (T)(1.0 / (double)n);
 #pragma unroll 1
-            for (int j = 0; j < NP; ++j)
-                tab[j * 32 + lane] = (j < n) ? Num<T>::cospi_(Num<T>::reduce(u * (double)(2 * j + 1))) : (T)0;
-            T a0, a0p;
-            fsw_amplitude<T, false>(u, (T)(1.0 / (double)n), xi, a0, a0p);
-            A = ((T)1 + xi) * a0;
+            for (int j = 0; j < NP; ++j) {
+                const T rr = Num<T>::reduce(u * (double)(2 * j + 1));
+                tab[j * 32 + lane] = (j < n) ? Num<T>::cospi_(rr) : (T)0;
+                if (SAVE_RANK) tabt[j * 32 + lane] = (j < n) ? (T)M_PI * wn * (T)(2 * j + 1) * Num<T>::sinpi_(rr) : (T)0;
+            }
+            fsw_amplitude<T, SAVE_RANK>(u, wn, xi, A0, A0p);
+            A = ((T)1 + xi) * A0;
             n_prev = n;
         }
 
@@ -139,6 +147,14 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
 #pragma unroll
         for (int j = 0; j < NP; ++j) acc = fma(key[j], tab[j * 32 + lane], acc);
         if (act) out[(int64_t)cur.s * ld_out + out_col0 + k] = A * acc + bk;
+        if constexpr (SAVE_RANK) {
+            if (dxi_out != nullptr) {  // d out / d xi of this (segment, slice), summed against g in the backward
+                T acc2 = (T)0;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) acc2 = fma(key[j], tabt[j * 32 + lane], acc2);
+                if (act) dxi_out[(int64_t)cur.s * ld_dxi + k] = A0 * acc + ((T)1 + xi) * (A0p * acc - A0 * acc2);
+            }
+        }
         if constexpr (SAVE_RANK) {
             unsigned short* rp = ranks + cur.e0 * ldr + k;
 #pragma unroll
@@ -638,6 +654,77 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// SOURCE-major rank backward (graphs): warp = (point row j, 128-slice chunk).  It walks the transposed
+// structure (all (segment, slot) pairs that reference row j), accumulates g (1+xi) A0(n) cos(...) in
+// registers and writes dXp[j] ONCE with a plain 128-bit store: no atomics, no read-modify-write of dXp.
+// Measured (profiles/micro/atomic_bw.cu): scattered red.add to a 1.9 GB matrix sustains 2.3 TB/s of
+// payload (each update is a DRAM read + write) while gathers run at 5.7 TB/s.
+// Pairs whose segment is not eligible (tn == 0: more than 128 elements or non-uniform weights) are
+// skipped here and added afterwards by the destination-major kernels (atomics).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
+                                                            const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
+                                                            const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
+                                                            const unsigned short* __restrict__ ranks, int64_t ldr,
+                                                            const float* __restrict__ g, int64_t ld_g, int64_t g_col0,
+                                                            float* __restrict__ dXp, float* __restrict__ dEp,
+                                                            const float* __restrict__ tab_c, const float* __restrict__ tab_A) {
+    constexpr int V = 4, U = 4;
+    const int lane = threadIdx.x & 31;
+    const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t j = wglobal / nchunks;
+    const int chunk = (int)(wglobal - j * nchunks);
+    if (j >= Nrows) return;
+    const int k0 = (chunk * 32 + lane) * V;
+    if (k0 >= a.ldp) return;
+    const int ldp = (int)a.ldp;
+    float xi1[V];
+    bool act[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        act[q] = k0 + q < a.K;
+        xi1[q] = act[q] ? 1.f + __ldg(a.freqs + k0 + q) : 0.f;
+    }
+    float acc[V] = {0.f, 0.f, 0.f, 0.f};
+    const int t_beg = __ldg(tptr + j), t_end = __ldg(tptr + j + 1);
+    for (int t0 = t_beg; t0 < t_end; t0 += U) {
+        int seg[U], slot[U], nn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // warp-uniform addresses
+            const int t = min(t0 + u, t_end - 1);
+            seg[u] = __ldg(tseg + t);
+            slot[u] = __ldg(tslot + t);
+            nn[u] = (t0 + u < t_end) ? __ldg(tn + t) : 0;
+        }
+        int r[U][V];
+        float gv[U][V], A0[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            fsw_unpack_ranks<V>(ranks + (int64_t)slot[u] * ldr + k0, r[u]);
+            const float* gp = g + (int64_t)seg[u] * ld_g + g_col0 + k0;
+#pragma unroll
+            for (int q = 0; q < V; ++q) gv[u][q] = act[q] ? __ldg(gp + q) : 0.f;
+            fsw_load_vec<V>(tab_A + (int64_t)max(nn[u] - 1, 0) * ldp + k0, A0[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (nn[u] > 0) {
+                const float* tc = tab_c + ((int64_t)nn[u] * (nn[u] - 1) / 2) * ldp + k0;
+                float v[V];
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    const int rq = act[q] ? r[u][q] : 0;
+                    v[q] = gv[u][q] * xi1[q] * A0[u][q] * __ldg(tc + (int64_t)rq * ldp + q);
+                    acc[q] += v[q];
+                }
+                if (dEp) fsw_store_vec<V>(dEp + (int64_t)slot[u] * ldp + k0, v);
+            }
+        }
+    }
+    fsw_store_vec<V>(dXp + j * ldp + k0, acc);
+}
+
 template <bool HAS_COL, bool NEED_DXI>
 int launch_rank_bwdg(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g, int64_t ld_g,
                      int64_t g_col0, float* dXp, float* dEp, double* dfreqs, float* tables, cudaStream_t st) {
@@ -673,17 +760,17 @@ int pick_G(int64_t cnt, int nchunks, int64_t target_warps, int maxG) {
 
 template <typename T, int NP, bool HAS_COL, bool SAVE_RANK>
 int launch_small_fwd(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
-                     unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+                     unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int G = pick_G(hi - lo, nchunks, 148 * 32, 32);
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
-    const size_t smem = (size_t)4 * NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(int) : 0));
+    const size_t smem = (size_t)4 * NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + sizeof(int) : 0));
     auto kern = fsw_small_fwd_kernel<T, NP, HAS_COL, SAVE_RANK>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const std::string label = std::string(SAVE_RANK ? "fwdr_small_u" : "fwd_small_u") + std::to_string(NP) + (sizeof(T) == 4 ? "_f32" : "_f64");
     fsw_prof_begin(label.c_str(), st);
-    kern<<<(unsigned)blocks, 128, smem, st>>>(a, lo, hi, G, nchunks, out, ld_out, out_col0, bias, ranks, ldr);
+    kern<<<(unsigned)blocks, 128, smem, st>>>(a, lo, hi, G, nchunks, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_small_fwd_kernel");
     return FSW_OK;
@@ -691,14 +778,14 @@ int launch_small_fwd(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out
 
 template <typename T, int NP>
 int launch_small_fwd_np(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
-                        unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+                        unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     const bool has_col = a.col != nullptr;
     if (ranks) {
-        return has_col ? launch_small_fwd<T, NP, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st)
-                       : launch_small_fwd<T, NP, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        return has_col ? launch_small_fwd<T, NP, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st)
+                       : launch_small_fwd<T, NP, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
     }
-    return has_col ? launch_small_fwd<T, NP, true, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st)
-                   : launch_small_fwd<T, NP, false, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+    return has_col ? launch_small_fwd<T, NP, true, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, nullptr, 0, st)
+                   : launch_small_fwd<T, NP, false, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, nullptr, 0, st);
 }
 
 template <typename T, bool HAS_COL, bool NEED_DXI>
@@ -724,19 +811,19 @@ int launch_rank_bwd(const SegArgs<T>& a, int lo, int hi, int cap, const unsigned
 // uniform-weight segments order[lo, hi) with n <= np, np in {4, 8, 12, 16, 24, 32, 48, 64}
 template <typename T>
 int fsw_small_forward_u(const SegArgs<T>& a, int np, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
-                        unsigned short* ranks, int64_t ldr, cudaStream_t st) {
+                        unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     switch (np) {
-        case 4: return launch_small_fwd_np<T, 4>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
-        case 8: return launch_small_fwd_np<T, 8>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
-        case 12: return launch_small_fwd_np<T, 12>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
-        case 16: return launch_small_fwd_np<T, 16>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
-        case 24: return launch_small_fwd_np<T, 24>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
-        case 32: return launch_small_fwd_np<T, 32>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+        case 4: return launch_small_fwd_np<T, 4>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
+        case 8: return launch_small_fwd_np<T, 8>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
+        case 12: return launch_small_fwd_np<T, 12>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
+        case 16: return launch_small_fwd_np<T, 16>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
+        case 24: return launch_small_fwd_np<T, 24>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
+        case 32: return launch_small_fwd_np<T, 32>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
         case 48:
-            if constexpr (sizeof(T) == 4) return launch_small_fwd_np<T, 48>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+            if constexpr (sizeof(T) == 4) return launch_small_fwd_np<T, 48>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
             break;
         case 64:
-            if constexpr (sizeof(T) == 4) return launch_small_fwd_np<T, 64>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, st);
+            if constexpr (sizeof(T) == 4) return launch_small_fwd_np<T, 64>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
             break;
     }
     return fsw_fail(FSW_ERR_INVALID, "fsw_small_forward_u: class %d", np);
@@ -761,8 +848,8 @@ int fsw_rank_backward_u(const SegArgs<T>& a, int lo, int hi, int cap, const unsi
                    : launch_rank_bwd<T, false, false>(a, lo, hi, cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, st);
 }
 
-template int fsw_small_forward_u<float>(const SegArgs<float>&, int, int, int, float*, int64_t, int64_t, const float*, unsigned short*, int64_t, cudaStream_t);
-template int fsw_small_forward_u<double>(const SegArgs<double>&, int, int, int, double*, int64_t, int64_t, const double*, unsigned short*, int64_t, cudaStream_t);
+template int fsw_small_forward_u<float>(const SegArgs<float>&, int, int, int, float*, int64_t, int64_t, const float*, unsigned short*, int64_t, float*, int64_t, cudaStream_t);
+template int fsw_small_forward_u<double>(const SegArgs<double>&, int, int, int, double*, int64_t, int64_t, const double*, unsigned short*, int64_t, double*, int64_t, cudaStream_t);
 template int fsw_rank_backward_u<float>(const SegArgs<float>&, int, int, int, const unsigned short*, int64_t, const float*, int64_t, int64_t, float*, float*, double*, cudaStream_t);
 template int fsw_rank_backward_u<double>(const SegArgs<double>&, int, int, int, const unsigned short*, int64_t, const double*, int64_t, int64_t, double*, double*, double*, cudaStream_t);
 
@@ -778,4 +865,29 @@ int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsign
                        : launch_rank_bwdg<false, true>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st);
     return has_col ? launch_rank_bwdg<true, false>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st)
                    : launch_rank_bwdg<false, false>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st);
+}
+
+// fp32 graphs: source-major rank backward over the transposed structure (eligible: uniform weights, n <= 128).
+// Writes EVERY row of dXp (plain stores); must run before the kernels that add with atomics.
+int fsw_rank_backward_T(const SegArgs<float>& a, int64_t Nrows, const int32_t* tptr, const int32_t* tseg, const int32_t* tslot,
+                        const int32_t* tn, const unsigned short* ranks, int64_t ldr, const float* g, int64_t ld_g, int64_t g_col0,
+                        float* dXp, float* dEp, void* tables, cudaStream_t st) {
+    const int ldp = (int)a.ldp;
+    float* tab_c = (float*)tables;
+    float* tab_t = tab_c + FSW_GTAB_ROWS * ldp;
+    float* tab_A = tab_t + FSW_GTAB_ROWS * ldp;
+    float* tab_Ap = tab_A + (int64_t)FSW_GTAB_NMAX * ldp;
+    fsw_prof_begin("bwd_rank_tables", st);
+    fsw_build_rank_tables_kernel<<<FSW_GTAB_NMAX, 256, 0, st>>>(a.freqs, a.K, ldp, tab_c, nullptr, tab_A, tab_Ap);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_build_rank_tables_kernel");
+    const int nchunks = (a.K + 127) / 128;
+    const int64_t warps = Nrows * nchunks;
+    const int64_t blocks = fsw_cdiv(warps, 4);
+    fsw_prof_begin("bwd_rankT_u128_f32", st);
+    fsw_rank_bwdT_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp,
+                                                          tab_c, tab_A);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_rank_bwdT_kernel");
+    return FSW_OK;
 }

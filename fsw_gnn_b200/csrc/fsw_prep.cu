@@ -268,7 +268,63 @@ __global__ void __launch_bounds__(256) plan_scatter(const int32_t* __restrict__ 
     if (b >= 0) order[base[b] + local] = (int32_t)s;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Transpose of the segment structure: for every point row j the list of (segment, slot) pairs that
+// reference it.  Used by the source-major backward (fsw_embed_small.cu) which replaces the scatter of
+// atomics into dXp by one register accumulation + one plain store per row.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_count(const int32_t* __restrict__ col, int64_t E, int* __restrict__ counts) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) atomicAdd(counts + col[e], 1);
+}
+
+__global__ void __launch_bounds__(256) transpose_fill(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                      const int32_t* __restrict__ info, int64_t S, int nmax, int* __restrict__ cursor,
+                                                      int32_t* __restrict__ tseg, int32_t* __restrict__ tslot, int32_t* __restrict__ tn) {
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= S) return;
+    const int lo = rowptr[s], hi = rowptr[s + 1];
+    const int w = info[s];
+    const int n = hi - lo;
+    const int elig = ((w & FSW_INFO_UNIFORM) && n <= nmax) ? n : 0;
+    for (int e = lo + lane; e < hi; e += 32) {
+        const int pos = atomicAdd(cursor + col[e], 1);
+        tseg[pos] = (int32_t)s;
+        tslot[pos] = e;
+        tn[pos] = elig;
+    }
+}
+
 }  // namespace
+
+extern "C" size_t fsw_transpose_workspace_bytes(int64_t Nrows) {
+    return (size_t)(2 * (Nrows + 1) + fsw_cdiv(Nrows + 1, SCAN_BLOCK) + 64) * sizeof(int);
+}
+
+extern "C" int fsw_csr_transpose(const int32_t* rowptr, const int32_t* col, const int32_t* info, int64_t S, int64_t Nrows,
+                                 int64_t E, int nmax_eligible, int32_t* tptr, int32_t* tseg, int32_t* tslot, int32_t* tn,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    if (!rowptr || !col || !info || !tptr) return fsw_fail(FSW_ERR_INVALID, "fsw_csr_transpose: null argument");
+    if (workspace_bytes < fsw_transpose_workspace_bytes(Nrows)) return fsw_fail(FSW_ERR_WORKSPACE, "fsw_csr_transpose: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* counts = (int*)workspace;
+    int* cursor = counts + (Nrows + 1);
+    int* btmp = cursor + (Nrows + 1);
+    FSW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(Nrows + 1) * sizeof(int), st));
+    if (E > 0) {
+        transpose_count<<<(unsigned)fsw_cdiv(E, 256), 256, 0, st>>>(col, E, counts);
+        FSW_CHECK_LAUNCH("transpose_count");
+    }
+    int rc = exclusive_scan_i32(counts, Nrows + 1, tptr, btmp, st);
+    if (rc) return rc;
+    FSW_CUDA(cudaMemcpyAsync(cursor, tptr, (size_t)(Nrows + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (E > 0 && S > 0) {
+        transpose_fill<<<(unsigned)fsw_cdiv(S * 32, 256), 256, 0, st>>>(rowptr, col, info, S, nmax_eligible, cursor, tseg, tslot, tn);
+        FSW_CHECK_LAUNCH("transpose_fill");
+    }
+    return FSW_OK;
+}
 
 extern "C" size_t fsw_csr_workspace_bytes(int64_t N) {
     // counts [N+1] + cursor [N+1] + block sums

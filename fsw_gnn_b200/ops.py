@@ -69,6 +69,25 @@ class SegmentPlan:
             self._scratch[key] = _ws(nbytes, self.device) if nbytes > 0 else None
         return self._scratch[key]
 
+    def transpose(self, nrows):
+        """(tptr, tseg, tslot, tn) of fsw_csr_transpose, built lazily and cached (graphs with explicit columns)."""
+        if self.col is None or self.rowptr is None:
+            return None
+        key = int(nrows)
+        if getattr(self, "_transpose", None) is None or self._transpose[0] != key:
+            lib = _lib.load()
+            dev = self.device
+            tptr = torch.empty(key + 1, dtype=torch.int32, device=dev)
+            tseg = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+            tslot = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+            tn = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+            ws = _ws(lib.fsw_transpose_workspace_bytes(key), dev)
+            check(lib.fsw_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E, 128,
+                                        ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev)),
+                  "fsw_csr_transpose")
+            self._transpose = (key, tptr, tseg, tslot, tn)
+        return self._transpose[1:]
+
     def uniform_fraction(self):
         bo = list(self.bucket_offsets)
         return (bo[_lib.PLAN_BUCKETS_PER_KIND] - bo[0]) / max(self.S, 1)
@@ -99,7 +118,7 @@ def project(X, theta_part, ldp):
     return gemm(0, X, theta_part, Nrows, K, d, X.stride(0), theta_part.stride(0), out=out, ldc=ldp)
 
 
-def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks=None):
+def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks=None, dxi_out=None):
     lib = _lib.load()
     K = freqs.numel()
     scratch = plan.scratch(K, False)
@@ -107,11 +126,13 @@ def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks=N
                                 ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
                                 plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(out), ld_out, out_col0,
                                 ptr(bias), plan.max_n_eff, ptr(scratch), 0 if scratch is None else scratch.numel(),
-                                ptr(ranks), 0 if ranks is None else ranks.stride(0), stream_ptr(plan.device)),
+                                ptr(ranks), 0 if ranks is None else ranks.stride(0),
+                                ptr(dxi_out), 0 if dxi_out is None else dxi_out.stride(0), stream_ptr(plan.device)),
           "fsw_embed_forward")
 
 
-def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_acc, ranks=None):
+def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_acc, ranks=None, dxi_from_forward=False,
+                   transpose=None, nrows=0):
     lib = _lib.load()
     K = freqs.numel()
     scratch = plan.scratch(K, True)
@@ -120,7 +141,10 @@ def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_a
                                  plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(g), ld_g, g_col0,
                                  ptr(dXp), ptr(dEp), ptr(dfreqs_acc), None, plan.max_n_eff, ptr(scratch),
                                  0 if scratch is None else scratch.numel(), ptr(ranks),
-                                 0 if ranks is None else ranks.stride(0), stream_ptr(plan.device)),
+                                 0 if ranks is None else ranks.stride(0), 1 if dxi_from_forward else 0,
+                                 ptr(transpose[0]) if transpose else None, ptr(transpose[1]) if transpose else None,
+                                 ptr(transpose[2]) if transpose else None, ptr(transpose[3]) if transpose else None,
+                                 int(nrows), stream_ptr(plan.device)),
           "fsw_embed_backward")
 
 
@@ -180,8 +204,13 @@ class FSWEmbedFunction(torch.autograd.Function):
                 ok = nbytes < RANK_MEMORY_FRACTION * free_b
             if ok:
                 ranks = torch.empty((plan.E, ldp), dtype=torch.int16, device=X.device)
-        embed_forward(plan, Xp, ldp, Ep, freqs.contiguous(), out, d_out, tm_dim, bias_core, ranks)
+        # with learnable frequencies the forward also emits d out / d xi per (segment, slice)
+        dxi_out = None
+        if ranks is not None and ctx.needs_input_grad[2]:
+            dxi_out = torch.zeros((plan.S, K), dtype=X.dtype, device=X.device)
+        embed_forward(plan, Xp, ldp, Ep, freqs.contiguous(), out, d_out, tm_dim, bias_core, ranks, dxi_out)
         ctx.ranks = ranks
+        ctx.dxi_out = dxi_out
         fT = None
         if tm_dim:
             fT = total_mass_function(plan.mass_as(X.dtype), tm_function)
@@ -216,9 +245,16 @@ class FSWEmbedFunction(torch.autograd.Function):
                 dXp.zero_()
             dEp = torch.zeros((plan.E, ldp), dtype=X.dtype, device=X.device) if ctx.has_E else None
             dxi_acc = torch.zeros(K, dtype=torch.float64, device=X.device) if need_xi else None
-            embed_backward(plan, Xp, ldp, Ep, freqs.contiguous(), g, g.shape[1], tm_dim, dXp, dEp, dxi_acc, ctx.ranks)
+            dxi_fwd = ctx.dxi_out is not None
+            transpose = None
+            if ctx.ranks is not None and X.dtype == torch.float32 and plan.col is not None and (dxi_fwd or not need_xi):
+                transpose = plan.transpose(Nrows)
+            embed_backward(plan, Xp, ldp, Ep, freqs.contiguous(), g, g.shape[1], tm_dim, dXp, dEp, dxi_acc, ctx.ranks,
+                           dxi_from_forward=(dxi_fwd or not need_xi), transpose=transpose, nrows=Nrows)
             if need_xi:
                 dxi = dxi_acc.to(X.dtype)
+                if dxi_fwd:
+                    dxi = dxi + (g[:, tm_dim:tm_dim + K] * ctx.dxi_out).sum(dim=0)
             if need_X:
                 dX = gemm(1, dXp, projVecs, Nrows, d, K, ldp, projVecs.stride(0))
             if need_theta:

@@ -112,6 +112,15 @@ int fsw_rowptr_from_sorted_rows(const int64_t* rows, int64_t nnz, int64_t S, int
 int fsw_edge_weights(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* eid, int64_t N, int64_t E,
                      int self_loops, double self_loop_weight, int gcn, void* deg_out, void* w_out, void* stream);
 
+/* Transpose of a CSR segment structure with explicit columns: for every point row j (0 <= j < Nrows) the
+ * (segment, slot) pairs that reference it: tptr [Nrows+1], tseg [E], tslot [E], tn [E] = number of elements of
+ * that segment when it is eligible for the source-major backward (uniform weights, n <= nmax_eligible), else 0.
+ * `info` comes from fsw_segment_plan.  workspace: fsw_transpose_workspace_bytes(Nrows). */
+size_t fsw_transpose_workspace_bytes(int64_t Nrows);
+int fsw_csr_transpose(const int32_t* rowptr, const int32_t* col, const int32_t* info, int64_t S, int64_t Nrows, int64_t E,
+                      int nmax_eligible, int32_t* tptr, int32_t* tseg, int32_t* tslot, int32_t* tn, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* Segment statistics + plan.
  *   rowptr [S+1] (or NULL: S segments of n_fixed elements each), W [E] raw weights or NULL (unit).
  *   mass [S] float64 = total mass T_s (fsw_embedding.py:778-784);
@@ -153,6 +162,8 @@ int fsw_gemm(int dtype, int op, int64_t M, int64_t N, int64_t Kd, const void* A,
  *  ranks_out [E, ldr] uint16 or NULL: when given (training), the forward also records the sorted position
  *       of every element per slice for the uniform-weight segments of up to 512 elements - the analogue of
  *       the compressed permutation the reference saves for its backward (fsw_embedding.py:2041-2050).
+ *  dxi_out [S, ld_dxi] or NULL (only with ranks_out): d out[s, k] / d xi_k for the same segments; the caller
+ *       zero-initialises it and forms dL/dxi_k = sum_s g[s, k] * dxi_out[s, k] (+ what fsw_embed_backward adds).
  * ---------------------------------------------------------------------------------------------- */
 size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bucket_offsets_host, int64_t K, int64_t max_n_eff,
                                int backward);
@@ -161,7 +172,7 @@ int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, co
                       const int32_t* order, const int32_t* bucket_offsets_host, int64_t S, int64_t K,
                       const void* freqs, double thresh, void* out, int64_t ld_out, int64_t out_col0,
                       const void* bias, int64_t max_n_eff, void* scratch, size_t scratch_bytes, void* ranks_out,
-                      int64_t ldr, void* stream);
+                      int64_t ldr, void* dxi_out, int64_t ld_dxi, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 6. K3: fused backward of section 5 (ag.*.backward fsw_embedding.py:1286-2258)
@@ -173,13 +184,18 @@ int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, co
  *  dW   [E] or NULL: dL/dW (raw weights) - written, not accumulated
  *  ranks [E, ldr] uint16 or NULL: positions recorded by fsw_embed_forward; with them the backward of the
  *        covered segments is a streaming pass without any sort, otherwise everything is re-sorted.
+ *  dxi_from_forward != 0: the forward was given dxi_out, so the covered segments skip the frequency gradient.
+ *  tptr/tseg/tslot/tn (fsw_csr_transpose) or NULL: with them (fp32 graphs, ranks, dxi_from_forward) the segments
+ *        of up to 128 elements run SOURCE-major: every row of dXp is written once with a plain store instead
+ *        of scattered atomics (dXp then needs no zero-initialisation).
  * ---------------------------------------------------------------------------------------------- */
 int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,
                        int64_t n_fixed, const int32_t* col, const void* W, const double* mass,
                        const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host, int64_t S,
                        int64_t K, const void* freqs, double thresh, const void* g, int64_t ld_g, int64_t g_col0,
                        void* dXp, void* dEp, double* dfreqs_acc, void* dW, int64_t max_n_eff, void* scratch,
-                       size_t scratch_bytes, const void* ranks, int64_t ldr, void* stream);
+                       size_t scratch_bytes, const void* ranks, int64_t ldr, int dxi_from_forward, const int32_t* tptr,
+                       const int32_t* tseg, const int32_t* tslot, const int32_t* tn, int64_t nrows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 7. Counters and per-kernel timers (the reference has only unused wall-clock globals,
