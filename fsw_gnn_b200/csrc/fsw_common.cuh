@@ -134,7 +134,7 @@ struct SegArgs {
 // medium / large path (fsw_embed_medium.cu): uniform-weight fp32 segments of more than 64 elements
 int fsw_medium_forward_f32(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
                            const float* bias, void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr,
-                           float* dxi_out, int64_t ld_dxi, cudaStream_t st);
+                           float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t, cudaStream_t st);
 int fsw_medium_backward_f32(const SegArgs<float>& a, int lo, int hi, int cap, const float* g, int64_t ld_g, int64_t g_col0,
                             float* dXp, float* dEp, double* dfreqs, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t fsw_medium_tile_bytes(int cap, int mode);  // global scratch per CTA (0: shared-memory tile)
@@ -148,7 +148,14 @@ template <typename T>
 int fsw_rank_backward_u(const SegArgs<T>& a, int lo, int hi, int cap, const unsigned short* ranks, int64_t ldr, const T* g,
                         int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, cudaStream_t st);
 
+int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* tab_c, float* tab_t, float* tab_A, float* tab_Ap,
+                          cudaStream_t st);
 size_t fsw_rank_tables_bytes(int64_t ldp);
+// forward coefficient tables (cos and d/dxi) for n <= FSW_FWD_TAB_NMAX, in front of the forward scratch when training
+#define FSW_FWD_TAB_NMAX 256
+static inline size_t fsw_fwd_tables_bytes(int64_t ldp) {
+    return (size_t)(2 * ((int64_t)FSW_FWD_TAB_NMAX * (FSW_FWD_TAB_NMAX + 1) / 2) * ldp) * sizeof(float);
+}
 int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g,
                            int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, void* tables, cudaStream_t st);
 

@@ -711,6 +711,22 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                     T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int msn = max_small_np<T>();
+    // training (fp32): coefficient tables for n <= FSW_FWD_TAB_NMAX at the front of the scratch, if any medium class exists
+    const float* gtab_c = nullptr;
+    const float* gtab_t = nullptr;
+    if constexpr (sizeof(T) == 4) {
+        const size_t tb = fsw_fwd_tables_bytes(a.ldp);
+        if (ranks != nullptr && bo[64 + 1] < bo[FSW_FWD_TAB_NMAX + 1] && scratch_bytes >= tb) {
+            float* tc = (float*)scratch;
+            float* tt = tc + (int64_t)FSW_FWD_TAB_NMAX * (FSW_FWD_TAB_NMAX + 1) / 2 * a.ldp;
+            int rc = fsw_build_coef_tables(a.freqs, a.K, (int)a.ldp, FSW_FWD_TAB_NMAX, tc, tt, nullptr, nullptr, st);
+            if (rc) return rc;
+            gtab_c = tc;
+            gtab_t = tt;
+            scratch = (unsigned char*)scratch + tb;
+            scratch_bytes -= tb;
+        }
+    }
     for (int kind = 0; kind < 2; ++kind) {
         const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
         if (kind == 0) {
@@ -738,7 +754,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
                 if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 64 elements
-                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, st);
+                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
                     if (rc) return rc;
                     continue;
                 }
@@ -925,7 +941,7 @@ extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t 
             if (grid * tb > need) need = grid * tb;
         }
     }
-    if (backward && dtype == FSW_F32) need += fsw_rank_tables_bytes((K + 7) / 8 * 8);
+    if (dtype == FSW_F32) need += backward ? fsw_rank_tables_bytes((K + 7) / 8 * 8) : fsw_fwd_tables_bytes((K + 7) / 8 * 8);
     return need;
 }
 

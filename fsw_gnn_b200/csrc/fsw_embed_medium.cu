@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                                                             T* __restrict__ dXp, T* __restrict__ dEp,
                                                             double* __restrict__ dfreqs, unsigned char* gscratch,
                                                             unsigned short* __restrict__ ranks, int64_t ldr,
-                                                            T* __restrict__ dxi_out, int64_t ld_dxi) {
+                                                            T* __restrict__ dxi_out, int64_t ld_dxi,
+                                                            const T* __restrict__ gtab_c, const T* __restrict__ gtab_t) {
     extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
     __shared__ double red[W][32];
     __shared__ double red2[W][32];
@@ -240,7 +241,12 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
 
         // ---- 3. last pass: the merged stream is consumed, not stored ----
         const bool want_dxi = (MODE == 1) && (dxi_out != nullptr);
+        const bool use_gtab = (MODE == 1) && (gtab_c != nullptr) && (n <= FSW_FWD_TAB_NMAX);
+        const T* gtc = use_gtab ? gtab_c + ((int64_t)n * (n - 1) / 2) * a.ldp + kk : nullptr;
+        const T* gtt = use_gtab ? gtab_t + ((int64_t)n * (n - 1) / 2) * a.ldp + kk : nullptr;
         (void)want_dxi;
+        (void)gtc;
+        (void)gtt;
         const T gk = (BWD && act) ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
         const T GA = gk * ((T)1 + xi) * A0;
         (void)GA;
@@ -261,7 +267,14 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                     const int pos = o + t;
                     if (MODE != 2) {
                         T c;
-                        if (MODE == 1 && want_dxi) {
+                        if (MODE == 1 && use_gtab) {
+                            // coefficient tables in global memory (L1/L2 resident, shared by every CTA)
+                            c = (T)0;
+                            if (pos < n) {
+                                c = __ldg(gtc + (int64_t)pos * a.ldp);
+                                if (want_dxi) fSs = fma(v, __ldg(gtt + (int64_t)pos * a.ldp), fSs);
+                            }
+                        } else if (MODE == 1 && want_dxi) {
                             // training with learnable frequencies: d out / d xi needs the sine as well
                             T sn = (T)0;
                             c = (T)0;
@@ -360,7 +373,8 @@ const int kPersistentGrid = 148 * 2;
 template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE>
 int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
                   const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, void* scratch,
-                  size_t scratch_bytes, unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
+                  size_t scratch_bytes, unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, const T* gtab_c,
+                  const T* gtab_t, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int64_t cnt = hi - lo;
     int64_t G = GLOBAL ? 1 : cnt * nchunks / (148 * 8);
@@ -383,7 +397,7 @@ int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t 
     const std::string label = std::string(names[MODE]) + std::to_string(cap) + "_f32";
     fsw_prof_begin(label.c_str(), st);
     kern<<<(unsigned)blocks, W * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, cap, nwork, out, ld_out, out_col0, bias, g, ld_g, g_col0,
-                                                  dXp, dEp, dfreqs, (unsigned char*)scratch, ranks, ldr, dxi_out, ld_dxi);
+                                                  dXp, dEp, dfreqs, (unsigned char*)scratch, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_medium_kernel");
     return FSW_OK;
@@ -393,13 +407,13 @@ template <int MODE, bool NEED_DXI>
 int dispatch_medium(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
                     const float* bias, const float* g, int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs,
                     void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi,
-                    cudaStream_t st) {
+                    const float* gtab_c, const float* gtab_t, cudaStream_t st) {
 #define FSW_MED(IDX, W, GLOBAL, TABLE) \
-    launch_medium<float, IDX, W, MODE, NEED_DXI, GLOBAL, TABLE>(a, lo, hi, cap, out, ld_out, out_col0, bias, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, st)
-    constexpr bool FWD = MODE != 2;
-    if (cap <= 128) return FSW_MED(unsigned short, 4, false, FWD);
-    if (cap <= 256) return FSW_MED(unsigned short, 8, false, FWD);
-    if (cap <= 512) return FSW_MED(unsigned short, 16, false, (MODE == 0));  // with a payload the table no longer fits
+    launch_medium<float, IDX, W, MODE, NEED_DXI, GLOBAL, TABLE>(a, lo, hi, cap, out, ld_out, out_col0, bias, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st)
+    constexpr bool TAB = MODE == 0;  // keys-only forward: coefficient table in shared memory; training: global tables
+    if (cap <= 128) return FSW_MED(unsigned short, 4, false, TAB);
+    if (cap <= 256) return FSW_MED(unsigned short, 8, false, TAB);
+    if (cap <= 512) return FSW_MED(unsigned short, 16, false, TAB);
     if (cap <= 32768) return FSW_MED(unsigned short, 16, true, false);
     return FSW_MED(int, 16, true, false);
 #undef FSW_MED
@@ -419,19 +433,19 @@ int fsw_medium_grid() { return kPersistentGrid; }
 // uniform-weight fp32 segments order[lo, hi) whose size class is `cap` (>= 128); ranks != NULL records positions
 int fsw_medium_forward_f32(const SegArgs<float>& a, int lo, int hi, int cap, float* out, int64_t ld_out, int64_t out_col0,
                            const float* bias, void* scratch, size_t scratch_bytes, unsigned short* ranks, int64_t ldr,
-                           float* dxi_out, int64_t ld_dxi, cudaStream_t st) {
+                           float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t, cudaStream_t st) {
     if (ranks != nullptr && cap <= 32768)
         return dispatch_medium<1, false>(a, lo, hi, cap, out, ld_out, out_col0, bias, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                         scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, st);
+                                         scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
     return dispatch_medium<0, false>(a, lo, hi, cap, out, ld_out, out_col0, bias, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                     scratch, scratch_bytes, nullptr, 0, nullptr, 0, st);
+                                     scratch, scratch_bytes, nullptr, 0, nullptr, 0, nullptr, nullptr, st);
 }
 
 int fsw_medium_backward_f32(const SegArgs<float>& a, int lo, int hi, int cap, const float* g, int64_t ld_g, int64_t g_col0,
                             float* dXp, float* dEp, double* dfreqs, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     if (dfreqs != nullptr)
         return dispatch_medium<2, true>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
-                                        scratch_bytes, nullptr, 0, nullptr, 0, st);
+                                        scratch_bytes, nullptr, 0, nullptr, 0, nullptr, nullptr, st);
     return dispatch_medium<2, false>(a, lo, hi, cap, nullptr, 0, 0, nullptr, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch,
-                                     scratch_bytes, nullptr, 0, nullptr, 0, st);
+                                     scratch_bytes, nullptr, 0, nullptr, 0, nullptr, nullptr, st);
 }

@@ -535,10 +535,24 @@ __global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float*
             const float xi = freqs[k];
             fsw_amplitude<float, true>((double)xi / (double)n, wn, xi, A0, A0p);
         }
-        tab_A[(int64_t)(n - 1) * ldp + k] = A0;
-        tab_Ap[(int64_t)(n - 1) * ldp + k] = A0p;
+        if (tab_A) tab_A[(int64_t)(n - 1) * ldp + k] = A0;
+        if (tab_Ap) tab_Ap[(int64_t)(n - 1) * ldp + k] = A0p;
     }
 }
+
+}  // namespace
+
+// tab_c / tab_t [(n (n-1)/2 + r) * ldp + k] for n = 1..nmax, r < n; tab_A / tab_Ap [(n-1) * ldp + k] (each may be NULL)
+int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* tab_c, float* tab_t, float* tab_A, float* tab_Ap,
+                          cudaStream_t st) {
+    fsw_prof_begin("coef_tables", st);
+    fsw_build_rank_tables_kernel<<<nmax, 256, 0, st>>>(freqs, K, ldp, tab_c, tab_t, tab_A, tab_Ap);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_build_rank_tables_kernel");
+    return FSW_OK;
+}
+
+namespace {
 
 template <bool HAS_COL, bool NEED_DXI>
 __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks,
@@ -733,10 +747,8 @@ int launch_rank_bwdg(const SegArgs<float>& a, int lo, int hi, const unsigned sho
     float* tab_t = tab_c + FSW_GTAB_ROWS * ldp;
     float* tab_A = tab_t + FSW_GTAB_ROWS * ldp;
     float* tab_Ap = tab_A + (int64_t)FSW_GTAB_NMAX * ldp;
-    fsw_prof_begin("bwd_rank_tables", st);
-    fsw_build_rank_tables_kernel<<<FSW_GTAB_NMAX, 256, 0, st>>>(a.freqs, a.K, ldp, tab_c, NEED_DXI ? tab_t : nullptr, tab_A, tab_Ap);
-    fsw_prof_end(st);
-    FSW_CHECK_LAUNCH("fsw_build_rank_tables_kernel");
+    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_GTAB_NMAX, tab_c, NEED_DXI ? tab_t : nullptr, tab_A, tab_Ap, st);
+    if (rc0) return rc0;
     const int nchunks = (a.K + 127) / 128;
     int64_t G = (int64_t)(hi - lo) * nchunks / (148 * 64);
     if (G < 1) G = 1;
@@ -877,10 +889,8 @@ int fsw_rank_backward_T(const SegArgs<float>& a, int64_t Nrows, const int32_t* t
     float* tab_t = tab_c + FSW_GTAB_ROWS * ldp;
     float* tab_A = tab_t + FSW_GTAB_ROWS * ldp;
     float* tab_Ap = tab_A + (int64_t)FSW_GTAB_NMAX * ldp;
-    fsw_prof_begin("bwd_rank_tables", st);
-    fsw_build_rank_tables_kernel<<<FSW_GTAB_NMAX, 256, 0, st>>>(a.freqs, a.K, ldp, tab_c, nullptr, tab_A, tab_Ap);
-    fsw_prof_end(st);
-    FSW_CHECK_LAUNCH("fsw_build_rank_tables_kernel");
+    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_GTAB_NMAX, tab_c, nullptr, tab_A, tab_Ap, st);
+    if (rc0) return rc0;
     const int nchunks = (a.K + 127) / 128;
     const int64_t warps = Nrows * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
