@@ -49,6 +49,7 @@ _SIGNATURES = {
     "fsw_segment_plan": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "fsw_gemm": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp]),
     "fsw_embed_scratch_bytes": (c_sz, [c_i32, c_vp, c_i64, c_i64, c_i32]),
+    "fsw_embed_backward_extra_bytes": (c_sz, [c_i32, c_i64, c_i64]),
     "fsw_embed_forward": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
                                   c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_sz, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "fsw_embed_backward": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,

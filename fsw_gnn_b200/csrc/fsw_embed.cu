@@ -797,6 +797,7 @@ struct TransposeArgs {
     const int32_t* tslot;
     const int32_t* tn;
     int64_t nrows;
+    int64_t S;
 };
 
 // `dxi_fwd`: the forward already produced d out / d xi for the uniform-weight classes it ran with rank
@@ -820,10 +821,15 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
                 const int lo0 = bo[base + 0], hi0 = bo[base + 128 + 1];
                 if (hi0 > lo0) {
                     int rc;
-                    if (a.col != nullptr && tr.tptr != nullptr && dfreqs_cov == nullptr)
+                    // the pre-scaled gradient GA [S, ldp] sits at the END of the scratch
+                    const size_t ga_bytes = (size_t)tr.S * a.ldp * sizeof(float);
+                    if (a.col != nullptr && tr.tptr != nullptr && dfreqs_cov == nullptr && scratch_bytes >= tb + ga_bytes + 256) {
                         // graphs: source-major, one plain store per row of dXp (must precede every atomic kernel)
-                        rc = fsw_rank_backward_T(a, tr.nrows, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, st);
-                    else
+                        const size_t ga_off = (scratch_bytes - ga_bytes) & ~(size_t)255;  // keep 128-bit accesses aligned
+                        float* ga_buf = (float*)((unsigned char*)scratch + ga_off);
+                        scratch_bytes = ga_off;
+                        rc = fsw_rank_backward_T(a, tr.S, tr.nrows, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, ga_buf, st);
+                    } else
                         rc = fsw_rank_backward_g128(a, lo0, hi0, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, scratch, st);
                     if (rc) return rc;
                 }
@@ -945,6 +951,12 @@ extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t 
     return need;
 }
 
+extern "C" size_t fsw_embed_backward_extra_bytes(int dtype, int64_t S, int64_t K) {
+    // pre-scaled gradient buffer of the source-major backward, appended to the scratch by the caller
+    if (dtype != FSW_F32) return 0;
+    return (size_t)S * ((K + 7) / 8 * 8) * sizeof(float) + 256;
+}
+
 extern "C" int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,
                                  int64_t n_fixed, const int32_t* col, const void* W, const double* mass,
                                  const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host,
@@ -982,7 +994,7 @@ extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const 
         return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: null argument");
     if (!rowptr && n_fixed <= 0) return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: rowptr == NULL needs n_fixed > 0");
     cudaStream_t st = (cudaStream_t)stream;
-    TransposeArgs tr{tptr, tseg, tslot, tn, nrows};
+    TransposeArgs tr{tptr, tseg, tslot, tn, nrows, S};
     if (dtype == FSW_F32) {
         auto a = make_args<float>(Xp, ldp, Ep, rowptr, n_fixed, col, W, mass, info, order, freqs, K, thresh);
         return embed_backward_t<float>(a, bucket_offsets_host, (const float*)g, ld_g, g_col0, (float*)dXp, (float*)dEp, dfreqs_acc,

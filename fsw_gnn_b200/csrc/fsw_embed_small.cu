@@ -512,7 +512,8 @@ constexpr int64_t FSW_GTAB_ROWS = (int64_t)FSW_GTAB_NMAX * (FSW_GTAB_NMAX + 1) /
 
 __global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float* __restrict__ freqs, int K, int ldp,
                                                                     float* __restrict__ tab_c, float* __restrict__ tab_t,
-                                                                    float* __restrict__ tab_A, float* __restrict__ tab_Ap) {
+                                                                    float* __restrict__ tab_A, float* __restrict__ tab_Ap,
+                                                                    float2* __restrict__ tab_u) {
     // grid.x = n (1..NMAX), threads over (r, k)
     const int n = blockIdx.x + 1;
     const float wn = (float)(1.0 / (double)n);
@@ -537,6 +538,11 @@ __global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float*
         }
         if (tab_A) tab_A[(int64_t)(n - 1) * ldp + k] = A0;
         if (tab_Ap) tab_Ap[(int64_t)(n - 1) * ldp + k] = A0p;
+        if (tab_u) {  // xi / n as a double-float pair: lets the phase (2r+1) xi / n mod 2 be formed in fp32
+            const double u = (k < K) ? (double)freqs[k] / (double)n : 0.0;
+            const float hi = (float)u;
+            tab_u[(int64_t)(n - 1) * ldp + k] = make_float2(hi, (float)(u - (double)hi));
+        }
     }
 }
 
@@ -544,9 +550,9 @@ __global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float*
 
 // tab_c / tab_t [(n (n-1)/2 + r) * ldp + k] for n = 1..nmax, r < n; tab_A / tab_Ap [(n-1) * ldp + k] (each may be NULL)
 int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* tab_c, float* tab_t, float* tab_A, float* tab_Ap,
-                          cudaStream_t st) {
+                          cudaStream_t st, float2* tab_u) {
     fsw_prof_begin("coef_tables", st);
-    fsw_build_rank_tables_kernel<<<nmax, 256, 0, st>>>(freqs, K, ldp, tab_c, tab_t, tab_A, tab_Ap);
+    fsw_build_rank_tables_kernel<<<nmax, 256, 0, st>>>(freqs, K, ldp, tab_c, tab_t, tab_A, tab_Ap, tab_u);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_build_rank_tables_kernel");
     return FSW_OK;
@@ -670,20 +676,44 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
 
 // ---------------------------------------------------------------------------------------------------
 // SOURCE-major rank backward (graphs): warp = (point row j, 128-slice chunk).  It walks the transposed
-// structure (all (segment, slot) pairs that reference row j), accumulates g (1+xi) A0(n) cos(...) in
-// registers and writes dXp[j] ONCE with a plain 128-bit store: no atomics, no read-modify-write of dXp.
+// structure (all (segment, slot) pairs that reference row j), accumulates GA[seg] * cos(...) in registers
+// and writes dXp[j] ONCE with a plain 128-bit store: no atomics, no read-modify-write of dXp.
 // Measured (profiles/micro/atomic_bw.cu): scattered red.add to a 1.9 GB matrix sustains 2.3 TB/s of
 // payload (each update is a DRAM read + write) while gathers run at 5.7 TB/s.
+//   GA[s, k] = g[s, k] (1 + xi_k) A0(n_s, k) is formed once per segment by fsw_scale_grad_kernel (aligned,
+//   zero for segments that are not eligible), so that one 128-bit gather per pair replaces 4 misaligned
+//   scalar loads of g plus an amplitude lookup.
 // Pairs whose segment is not eligible (tn == 0: more than 128 elements or non-uniform weights) are
 // skipped here and added afterwards by the destination-major kernels (atomics).
 // ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fsw_scale_grad_kernel(SegArgs<float> a, int64_t S, const float* __restrict__ g, int64_t ld_g,
+                                                             int64_t g_col0, const float* __restrict__ tab_A, int nmax,
+                                                             float* __restrict__ GA) {
+    const int ldp = (int)a.ldp;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * ldp) return;
+    const int64_t s = idx / ldp;
+    const int k = (int)(idx - s * ldp);
+    float v = 0.f;
+    if (k < a.K) {
+        const int n = __ldg(a.rowptr + s + 1) - __ldg(a.rowptr + s);
+        const int w = __ldg(a.info + s);
+        if ((w & FSW_INFO_UNIFORM) && n >= 1 && n <= nmax)
+            v = __ldg(g + s * ld_g + g_col0 + k) * (1.f + __ldg(a.freqs + k)) * __ldg(tab_A + (int64_t)(n - 1) * ldp + k);
+    }
+    GA[idx] = v;
+}
+
+struct __align__(16) FswPair4 {
+    int seg, slot, n, pad;
+};
+
 __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
                                                             const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
                                                             const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
                                                             const unsigned short* __restrict__ ranks, int64_t ldr,
-                                                            const float* __restrict__ g, int64_t ld_g, int64_t g_col0,
-                                                            float* __restrict__ dXp, float* __restrict__ dEp,
-                                                            const float* __restrict__ tab_c, const float* __restrict__ tab_A) {
+                                                            const float* __restrict__ GA, float* __restrict__ dXp,
+                                                            float* __restrict__ dEp, const float2* __restrict__ tab_u) {
     constexpr int V = 4, U = 4;
     const int lane = threadIdx.x & 31;
     const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -693,46 +723,75 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
     const int k0 = (chunk * 32 + lane) * V;
     if (k0 >= a.ldp) return;
     const int ldp = (int)a.ldp;
-    float xi1[V];
     bool act[V];
 #pragma unroll
-    for (int q = 0; q < V; ++q) {
-        act[q] = k0 + q < a.K;
-        xi1[q] = act[q] ? 1.f + __ldg(a.freqs + k0 + q) : 0.f;
-    }
+    for (int q = 0; q < V; ++q) act[q] = k0 + q < a.K;
     float acc[V] = {0.f, 0.f, 0.f, 0.f};
     const int t_beg = __ldg(tptr + j), t_end = __ldg(tptr + j + 1);
-    for (int t0 = t_beg; t0 < t_end; t0 += U) {
-        int seg[U], slot[U], nn[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {  // warp-uniform addresses
-            const int t = min(t0 + u, t_end - 1);
-            seg[u] = __ldg(tseg + t);
-            slot[u] = __ldg(tslot + t);
-            nn[u] = (t0 + u < t_end) ? __ldg(tn + t) : 0;
+    const unsigned lanemask = __activemask();  // lanes beyond the padded row width have left
+    const int nlanes = __popc(lanemask);       // active lanes are a prefix 0..nlanes-1
+    for (int tb = t_beg; tb < t_end; tb += nlanes) {
+        // one coalesced load of up to `nlanes` (segment, slot, n) triples, broadcast by shuffles below
+        const int cnt = min(nlanes, t_end - tb);
+        int my_seg = 0, my_slot = 0, my_n = 0;
+        if (lane < cnt) {
+            my_seg = __ldg(tseg + tb + lane);
+            my_slot = __ldg(tslot + tb + lane);
+            my_n = __ldg(tn + tb + lane);
         }
-        int r[U][V];
-        float gv[U][V], A0[U][V];
+        for (int t0 = 0; t0 < cnt; t0 += U) {
+            int seg[U], slot[U], nn[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            fsw_unpack_ranks<V>(ranks + (int64_t)slot[u] * ldr + k0, r[u]);
-            const float* gp = g + (int64_t)seg[u] * ld_g + g_col0 + k0;
+            for (int u = 0; u < U; ++u) {
+                const int src = min(t0 + u, cnt - 1);
+                seg[u] = __shfl_sync(lanemask, my_seg, src);
+                slot[u] = __shfl_sync(lanemask, my_slot, src);
+                nn[u] = __shfl_sync(lanemask, my_n, src);
+                if (t0 + u >= cnt) nn[u] = 0;
+            }
+            int r[U][V];
+            float ga[U][V];
 #pragma unroll
-            for (int q = 0; q < V; ++q) gv[u][q] = act[q] ? __ldg(gp + q) : 0.f;
-            fsw_load_vec<V>(tab_A + (int64_t)max(nn[u] - 1, 0) * ldp + k0, A0[u]);
-        }
+            for (int u = 0; u < U; ++u) {
+                fsw_unpack_ranks<V>(ranks + (int64_t)slot[u] * ldr + k0, r[u]);
+                fsw_load_vec<V>(GA + (int64_t)seg[u] * ldp + k0, ga[u]);
+            }
+            // coefficients cos(pi (2r+1) xi / n) evaluated directly: a table lookup would scatter the 32 lanes of a
+            // warp over 32 cache lines (each lane has its own rank) and bind the kernel on L1 wavefronts.  The phase
+            // is formed in fp32 from the double-float xi/n = hi + lo: (2r+1) hi is split exactly with an FMA.
+            float c[U][V];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (nn[u] > 0) {
-                const float* tc = tab_c + ((int64_t)nn[u] * (nn[u] - 1) / 2) * ldp + k0;
-                float v[V];
+            for (int u = 0; u < U; ++u) {
+                const int n1 = max(nn[u], 1);
+                const float2* up = tab_u + (int64_t)(n1 - 1) * ldp + k0;
+                const float4 u01 = __ldg(reinterpret_cast<const float4*>(up));
+                const float4 u23 = __ldg(reinterpret_cast<const float4*>(up + 2));
+                const float uh[V] = {u01.x, u01.z, u23.x, u23.z};
+                const float ul[V] = {u01.y, u01.w, u23.y, u23.w};
 #pragma unroll
                 for (int q = 0; q < V; ++q) {
-                    const int rq = act[q] ? r[u][q] : 0;
-                    v[q] = gv[u][q] * xi1[q] * A0[u][q] * __ldg(tc + (int64_t)rq * ldp + q);
-                    acc[q] += v[q];
+                    // 2r+1 -> float without an I2F: exact below 2^23 through the mantissa trick
+                    const int ri = (act[q] && nn[u] > 0) ? r[u][q] : 0;
+                    const float m = __uint_as_float(0x4B000000u | (unsigned)(2 * ri + 1)) - 8388608.0f;
+                    const float ph = m * uh[q];
+                    const float pe = fmaf(m, uh[q], -ph);           // exact rounding error of the product
+                    const float pl = fmaf(m, ul[q], pe);
+                    const float hq = (0.5f * ph + 12582912.0f) - 12582912.0f;  // rint(ph / 2) without an FRND
+                    const float red = fmaf(hq, -2.0f, ph);          // exact: ph reduced to [-1, 1]
+                    c[u][q] = fsw_cospi_unit(red + pl);
                 }
-                if (dEp) fsw_store_vec<V>(dEp + (int64_t)slot[u] * ldp + k0, v);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (nn[u] > 0) {
+                    float v[V];
+#pragma unroll
+                    for (int q = 0; q < V; ++q) {
+                        v[q] = ga[u][q] * c[u][q];
+                        acc[q] += v[q];
+                    }
+                    if (dEp) fsw_store_vec<V>(dEp + (int64_t)slot[u] * ldp + k0, v);
+                }
             }
         }
     }
@@ -866,7 +925,7 @@ template int fsw_rank_backward_u<float>(const SegArgs<float>&, int, int, int, co
 template int fsw_rank_backward_u<double>(const SegArgs<double>&, int, int, int, const unsigned short*, int64_t, const double*, int64_t, int64_t, double*, double*, double*, cudaStream_t);
 
 // fp32, uniform-weight segments order[lo, hi) with n <= 128: rank-based backward with global coefficient tables
-size_t fsw_rank_tables_bytes(int64_t ldp) { return (size_t)((2 * FSW_GTAB_ROWS + 2 * FSW_GTAB_NMAX) * ldp) * sizeof(float); }
+size_t fsw_rank_tables_bytes(int64_t ldp) { return (size_t)((2 * FSW_GTAB_ROWS + 4 * FSW_GTAB_NMAX) * ldp) * sizeof(float); }
 
 int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g,
                            int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, void* tables, cudaStream_t st) {
@@ -881,22 +940,27 @@ int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsign
 
 // fp32 graphs: source-major rank backward over the transposed structure (eligible: uniform weights, n <= 128).
 // Writes EVERY row of dXp (plain stores); must run before the kernels that add with atomics.
-int fsw_rank_backward_T(const SegArgs<float>& a, int64_t Nrows, const int32_t* tptr, const int32_t* tseg, const int32_t* tslot,
-                        const int32_t* tn, const unsigned short* ranks, int64_t ldr, const float* g, int64_t ld_g, int64_t g_col0,
-                        float* dXp, float* dEp, void* tables, cudaStream_t st) {
+// `ga_buf` [S, ldp] floats is scratch for the pre-scaled upstream gradient.
+int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, const int32_t* tptr, const int32_t* tseg,
+                        const int32_t* tslot, const int32_t* tn, const unsigned short* ranks, int64_t ldr, const float* g,
+                        int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, void* tables, float* ga_buf, cudaStream_t st) {
     const int ldp = (int)a.ldp;
     float* tab_c = (float*)tables;
     float* tab_t = tab_c + FSW_GTAB_ROWS * ldp;
     float* tab_A = tab_t + FSW_GTAB_ROWS * ldp;
     float* tab_Ap = tab_A + (int64_t)FSW_GTAB_NMAX * ldp;
-    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_GTAB_NMAX, tab_c, nullptr, tab_A, tab_Ap, st);
+    float2* tab_u = reinterpret_cast<float2*>(tab_Ap + (int64_t)FSW_GTAB_NMAX * ldp);
+    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_GTAB_NMAX, tab_c, nullptr, tab_A, tab_Ap, st, tab_u);
     if (rc0) return rc0;
+    fsw_prof_begin("bwd_scale_grad", st);
+    fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S * ldp, 256), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, FSW_GTAB_NMAX, ga_buf);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_scale_grad_kernel");
     const int nchunks = (a.K + 127) / 128;
     const int64_t warps = Nrows * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
     fsw_prof_begin("bwd_rankT_u128_f32", st);
-    fsw_rank_bwdT_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp,
-                                                          tab_c, tab_A);
+    fsw_rank_bwdT_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_rank_bwdT_kernel");
     return FSW_OK;

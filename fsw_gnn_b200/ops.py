@@ -66,6 +66,8 @@ class SegmentPlan:
             lib = _lib.load()
             nbytes = lib.fsw_embed_scratch_bytes(dtype_code(self.dtype), self.bucket_offsets, int(K), self.max_n_eff,
                                                  1 if backward else 0)
+            if backward and self.col is not None:
+                nbytes += lib.fsw_embed_backward_extra_bytes(dtype_code(self.dtype), self.S, int(K))
             self._scratch[key] = _ws(nbytes, self.device) if nbytes > 0 else None
         return self._scratch[key]
 
@@ -201,6 +203,8 @@ class FSWEmbedFunction(torch.autograd.Function):
             ok = nbytes < (256 << 20)  # small buffers never need the (slow) driver query
             if not ok:
                 free_b, _total = torch.cuda.mem_get_info(X.device)
+                # blocks cached by torch's allocator are free for us too
+                free_b += torch.cuda.memory_reserved(X.device) - torch.cuda.memory_allocated(X.device)
                 ok = nbytes < RANK_MEMORY_FRACTION * free_b
             if ok:
                 ranks = torch.empty((plan.E, ldp), dtype=torch.int16, device=X.device)

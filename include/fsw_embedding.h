@@ -167,6 +167,8 @@ int fsw_gemm(int dtype, int op, int64_t M, int64_t N, int64_t Kd, const void* A,
  * ---------------------------------------------------------------------------------------------- */
 size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bucket_offsets_host, int64_t K, int64_t max_n_eff,
                                int backward);
+/* extra bytes to append to the BACKWARD scratch when the transposed structure is passed (pre-scaled gradient) */
+size_t fsw_embed_backward_extra_bytes(int dtype, int64_t S, int64_t K);
 int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,
                       int64_t n_fixed, const int32_t* col, const void* W, const double* mass, const int32_t* info,
                       const int32_t* order, const int32_t* bucket_offsets_host, int64_t S, int64_t K,
