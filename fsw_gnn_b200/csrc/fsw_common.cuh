@@ -68,6 +68,12 @@ struct Num<double> {
     static __device__ __forceinline__ double reduce(double phi) { return phi; }
 };
 
+// row * stride for operands known to fit 32 unsigned bits (node / edge indices of the int32 CSR, padded widths): one
+// IMAD.WIDE.U32 where an int64 stride would cost a full 64x64 multiply (5-7 instructions) per address.
+__device__ __forceinline__ int64_t fsw_rowoff(int64_t row, int64_t ld) {
+    return (int64_t)((unsigned long long)(unsigned int)row * (unsigned int)ld);
+}
+
 // cos(pi t) for |t| <= 1 (phase already reduced): no conversions, no range reduction - fold to [0, 1/2] and
 // evaluate the even Taylor polynomial up to t^12 (truncation error < 1e-8 there).  ~11 full-rate instructions.
 __device__ __forceinline__ float fsw_cospi_unit(float t) {
@@ -163,6 +169,11 @@ int fsw_small_forward_u(const SegArgs<T>& a, int np, int lo, int hi, T* out, int
 template <typename T>
 int fsw_rank_backward_u(const SegArgs<T>& a, int lo, int hi, int cap, const unsigned short* ranks, int64_t ldr, const T* g,
                         int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, cudaStream_t st);
+
+// packed-key register sort (fsw_embed_packed.cu): uniform-weight fp32 segments with n <= np, np in {96, 128}
+int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0,
+                         const float* bias, unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c,
+                         const float* gtab_t, cudaStream_t st);
 
 int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* tab_c, float* tab_t, float* tab_A, float* tab_Ap,
                           cudaStream_t st, float2* tab_u = nullptr);

@@ -716,7 +716,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
     const float* gtab_t = nullptr;
     if constexpr (sizeof(T) == 4) {
         const size_t tb = fsw_fwd_tables_bytes(a.ldp);
-        if (ranks != nullptr && bo[64 + 1] < bo[FSW_FWD_TAB_NMAX + 1] && scratch_bytes >= tb) {
+        if (bo[64 + 1] < bo[FSW_FWD_TAB_NMAX + 1] && scratch_bytes >= tb) {
             float* tc = (float*)scratch;
             float* tt = tc + (int64_t)FSW_FWD_TAB_NMAX * (FSW_FWD_TAB_NMAX + 1) / 2 * a.ldp;
             int rc = fsw_build_coef_tables(a.freqs, a.K, (int)a.ldp, FSW_FWD_TAB_NMAX, tc, tt, nullptr, nullptr, st);
@@ -753,7 +753,12 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
             const int cap = rr[ri].cap;
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
-                if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 64 elements
+                if (kind == 0 && cap <= 256 && gtab_c != nullptr) {  // 65..256 elements: packed keys, cooperating lanes
+                    int rc = fsw_packed_forward_u(a, cap, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+                    if (rc) return rc;
+                    continue;
+                }
+                if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 128 elements
                     int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
                     if (rc) return rc;
                     continue;

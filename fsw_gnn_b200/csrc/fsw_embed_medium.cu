@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
         (void)want_dxi;
         (void)gtc;
         (void)gtt;
-        const T gk = (BWD && act) ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
+        const T gk = (BWD && act) ? g[fsw_rowoff(s, ld_g) + g_col0 + k] : (T)0;
         const T GA = gk * ((T)1 + xi) * A0;
         (void)GA;
         double acc = 0.0, Sc = 0.0, Ss = 0.0;
@@ -271,8 +271,8 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                             // coefficient tables in global memory (L1/L2 resident, shared by every CTA)
                             c = (T)0;
                             if (pos < n) {
-                                c = __ldg(gtc + (int64_t)pos * a.ldp);
-                                if (want_dxi) fSs = fma(v, __ldg(gtt + (int64_t)pos * a.ldp), fSs);
+                                c = __ldg(gtc + fsw_rowoff(pos, a.ldp));
+                                if (want_dxi) fSs = fma(v, __ldg(gtt + fsw_rowoff(pos, a.ldp)), fSs);
                             }
                         } else if (MODE == 1 && want_dxi) {
                             // training with learnable frequencies: d out / d xi needs the sine as well
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
 
         if (MODE == 1) {
             for (int r = warp; r < n; r += W)
-                if (act) ranks[(e0 + r) * ldr + k] = (unsigned short)__float_as_int(dst[r * 32 + lane]);
+                if (act) ranks[fsw_rowoff(e0 + r, ldr) + k] = (unsigned short)__float_as_int(dst[r * 32 + lane]);
         }
         if (!BWD) {
             red[warp][lane] = acc;
@@ -331,9 +331,9 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                     tot += red[w2][lane];
                     if (MODE == 1) tots += red2[w2][lane];
                 }
-                out[(int64_t)s * ld_out + out_col0 + k] = ((T)1 + xi) * A0 * (T)tot + bk;
+                out[fsw_rowoff(s, ld_out) + out_col0 + k] = ((T)1 + xi) * A0 * (T)tot + bk;
                 if (MODE == 1 && want_dxi)
-                    dxi_out[(int64_t)s * ld_dxi + k] = (T)((double)A0 * tot + (1.0 + xid) * ((double)A0p * tot - (double)A0 * tots));
+                    dxi_out[fsw_rowoff(s, ld_dxi) + k] = (T)((double)A0 * tot + (1.0 + xid) * ((double)A0p * tot - (double)A0 * tots));
             }
         } else {
             // dst now holds dL/dp in ORIGINAL row order
@@ -341,10 +341,10 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                 if (act) {
                     const T v = dst[r * 32 + lane];
                     if (a.col)
-                        atomicAdd(dXp + (int64_t)a.col[e0 + r] * a.ldp + k, v);
+                        atomicAdd(dXp + fsw_rowoff(a.col[e0 + r], a.ldp) + k, v);
                     else
-                        dXp[(e0 + r) * a.ldp + k] = v;
-                    if (dEp) dEp[(e0 + r) * a.ldp + k] = v;
+                        dXp[fsw_rowoff(e0 + r, a.ldp) + k] = v;
+                    if (dEp) dEp[fsw_rowoff(e0 + r, a.ldp) + k] = v;
                 }
             }
             if (NEED_DXI) {

@@ -146,20 +146,20 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
         T acc = (T)0;
 #pragma unroll
         for (int j = 0; j < NP; ++j) acc = fma(key[j], tab[j * 32 + lane], acc);
-        if (act) out[(int64_t)cur.s * ld_out + out_col0 + k] = A * acc + bk;
+        if (act) out[fsw_rowoff(cur.s, ld_out) + out_col0 + k] = A * acc + bk;
         if constexpr (SAVE_RANK) {
             if (dxi_out != nullptr) {  // d out / d xi of this (segment, slice), summed against g in the backward
                 T acc2 = (T)0;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) acc2 = fma(key[j], tabt[j * 32 + lane], acc2);
-                if (act) dxi_out[(int64_t)cur.s * ld_dxi + k] = A0 * acc + ((T)1 + xi) * (A0p * acc - A0 * acc2);
+                if (act) dxi_out[fsw_rowoff(cur.s, ld_dxi) + k] = A0 * acc + ((T)1 + xi) * (A0p * acc - A0 * acc2);
             }
         }
         if constexpr (SAVE_RANK) {
-            unsigned short* rp = ranks + cur.e0 * ldr + k;
+            unsigned short* rp = ranks + fsw_rowoff(cur.e0, ldr) + k;
 #pragma unroll
             for (int i = 0; i < NP; ++i)
-                if (i < n && act) rp[(int64_t)i * ldr] = (unsigned short)srank[i * 32 + lane];
+                if (i < n && act) rp[fsw_rowoff(i, ldr)] = (unsigned short)srank[i * 32 + lane];
         }
         // rotate the pipeline
         cur = nx1;
@@ -224,28 +224,28 @@ __global__ void __launch_bounds__(W * 32) fsw_rank_bwd_kernel(SegArgs<T> a, int 
             __syncthreads();
             n_prev = n;
         }
-        const T gk = act ? g[(int64_t)s * ld_g + g_col0 + k] : (T)0;
+        const T gk = act ? g[fsw_rowoff(s, ld_g) + g_col0 + k] : (T)0;
         const T GA = gk * ((T)1 + xi) * A0;
         T Sc = (T)0, Ss = (T)0;
-        const unsigned short* rp = ranks + e0 * ldr + kk;
+        const unsigned short* rp = ranks + fsw_rowoff(e0, ldr) + kk;
         for (int i = warp; i < n; i += W) {
-            const int r = rp[(int64_t)i * ldr];
+            const int r = rp[fsw_rowoff(i, ldr)];
             const T c = tab_c[r * 32 + lane];
             const T v = GA * c;
             int64_t row = e0 + i;
             if (HAS_COL) row = __ldg(a.col + e0 + i);
             if (NEED_DXI) {
                 const T p = __ldg(reinterpret_cast<const T*>(xp_bytes + row * ldb)) +
-                            (a.Ep ? __ldg(a.Ep + (e0 + i) * a.ldp + kk) : (T)0);
+                            (a.Ep ? __ldg(a.Ep + fsw_rowoff(e0 + i, a.ldp) + kk) : (T)0);
                 Sc = fma(p, c, Sc);
                 Ss = fma(p, tab_t[r * 32 + lane], Ss);
             }
             if (act) {
                 if (HAS_COL)
-                    atomicAdd(dXp + row * a.ldp + k, v);
+                    atomicAdd(dXp + fsw_rowoff(row, a.ldp) + k, v);
                 else
-                    dXp[row * a.ldp + k] = v;
-                if (dEp) dEp[(e0 + i) * a.ldp + k] = v;
+                    dXp[fsw_rowoff(row, a.ldp) + k] = v;
+                if (dEp) dEp[fsw_rowoff(e0 + i, a.ldp) + k] = v;
             }
         }
         if (NEED_DXI) dxi_acc += (double)gk * ((double)A0 * (double)Sc + (1.0 + xid) * ((double)A0p * (double)Sc - (double)A0 * (double)Ss));
@@ -406,17 +406,17 @@ __global__ void __launch_bounds__(W * 32) fsw_rank_bwdv_kernel(SegArgs<float> a,
         float gk[V], GA[V], Sc[V], Ss[V];
 #pragma unroll
         for (int q = 0; q < V; ++q) {
-            gk[q] = act[q] ? g[(int64_t)s * ld_g + g_col0 + k0 + q] : 0.f;
+            gk[q] = act[q] ? g[fsw_rowoff(s, ld_g) + g_col0 + k0 + q] : 0.f;
             GA[q] = gk[q] * (1.f + xi[q]) * A0[q];
             Sc[q] = 0.f;
             Ss[q] = 0.f;
         }
         if (lane_in_row) {
-            const unsigned short* rp = ranks + e0 * ldr + k0;
+            const unsigned short* rp = ranks + fsw_rowoff(e0, ldr) + k0;
 #pragma unroll 2
             for (int i = warp; i < n; i += W) {
                 int r[V];
-                fsw_unpack_ranks<V>(rp + (int64_t)i * ldr, r);
+                fsw_unpack_ranks<V>(rp + fsw_rowoff(i, ldr), r);
                 int64_t row = e0 + i;
                 if (HAS_COL) row = __ldg(a.col + e0 + i);
                 float c[V], v[V];
@@ -428,10 +428,10 @@ __global__ void __launch_bounds__(W * 32) fsw_rank_bwdv_kernel(SegArgs<float> a,
                 }
                 if (NEED_DXI) {
                     float p[V];
-                    fsw_load_vec<V>(a.Xp + row * a.ldp + k0, p);
+                    fsw_load_vec<V>(a.Xp + fsw_rowoff(row, a.ldp) + k0, p);
                     if (a.Ep) {
                         float pe[V];
-                        fsw_load_vec<V>(a.Ep + (e0 + i) * a.ldp + k0, pe);
+                        fsw_load_vec<V>(a.Ep + fsw_rowoff(e0 + i, a.ldp) + k0, pe);
 #pragma unroll
                         for (int q = 0; q < V; ++q) p[q] += pe[q];
                     }
@@ -442,10 +442,10 @@ __global__ void __launch_bounds__(W * 32) fsw_rank_bwdv_kernel(SegArgs<float> a,
                     }
                 }
                 if (HAS_COL)
-                    fsw_red_add<V>(dXp + row * a.ldp + k0, v);
+                    fsw_red_add<V>(dXp + fsw_rowoff(row, a.ldp) + k0, v);
                 else
-                    fsw_store_vec<V>(dXp + row * a.ldp + k0, v);
-                if (dEp) fsw_store_vec<V>(dEp + (e0 + i) * a.ldp + k0, v);
+                    fsw_store_vec<V>(dXp + fsw_rowoff(row, a.ldp) + k0, v);
+                if (dEp) fsw_store_vec<V>(dEp + fsw_rowoff(e0 + i, a.ldp) + k0, v);
             }
         }
         if (NEED_DXI) {
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
             fsw_load_vec<V>(tab_A + (int64_t)(n - 1) * ldp + k0, A0);
 #pragma unroll
             for (int q = 0; q < V; ++q) {
-                const float gk = act[q] ? __ldg(g + (int64_t)s * ld_g + g_col0 + k0 + q) : 0.f;
+                const float gk = act[q] ? __ldg(g + fsw_rowoff(s, ld_g) + g_col0 + k0 + q) : 0.f;
                 GA[q] = gk * (1.f + xi[q]) * A0[q];
                 Sc[q] = 0.f;
                 Ss[q] = 0.f;
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
         }
         const float* tc = tab_c + ((int64_t)n * (n - 1) / 2) * ldp + k0;
         const float* tt = NEED_DXI ? tab_t + ((int64_t)n * (n - 1) / 2) * ldp + k0 : nullptr;
-        const unsigned short* rp = ranks + e0 * ldr + k0;
+        const unsigned short* rp = ranks + fsw_rowoff(e0, ldr) + k0;
         for (int i0 = 0; i0 < n; i0 += U) {
             int64_t row[U];
             int r[U][V];
@@ -621,14 +621,14 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const int i = min(i0 + j, n - 1);
-                fsw_unpack_ranks<V>(rp + (int64_t)i * ldr, r[j]);
-                if (NEED_DXI) fsw_load_vec<V>(a.Xp + row[j] * ldp + k0, p[j]);
+                fsw_unpack_ranks<V>(rp + fsw_rowoff(i, ldr), r[j]);
+                if (NEED_DXI) fsw_load_vec<V>(a.Xp + fsw_rowoff(row[j], ldp) + k0, p[j]);
             }
             if (NEED_DXI && a.Ep) {
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
                     float pe[V];
-                    fsw_load_vec<V>(a.Ep + (e0 + min(i0 + j, n - 1)) * ldp + k0, pe);
+                    fsw_load_vec<V>(a.Ep + fsw_rowoff(e0 + min(i0 + j, n - 1), ldp) + k0, pe);
 #pragma unroll
                     for (int q = 0; q < V; ++q) p[j][q] += pe[q];
                 }
@@ -648,10 +648,10 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
                         }
                     }
                     if (HAS_COL)
-                        fsw_red_add<V>(dXp + row[j] * ldp + k0, v);
+                        fsw_red_add<V>(dXp + fsw_rowoff(row[j], ldp) + k0, v);
                     else
-                        fsw_store_vec<V>(dXp + row[j] * ldp + k0, v);
-                    if (dEp) fsw_store_vec<V>(dEp + (e0 + i0 + j) * ldp + k0, v);
+                        fsw_store_vec<V>(dXp + fsw_rowoff(row[j], ldp) + k0, v);
+                    if (dEp) fsw_store_vec<V>(dEp + fsw_rowoff(e0 + i0 + j, ldp) + k0, v);
                 }
             }
         }
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
             fsw_load_vec<V>(tab_Ap + (int64_t)(n - 1) * ldp + k0, A0p);
 #pragma unroll
             for (int q = 0; q < V; ++q) {
-                const float gk = act[q] ? __ldg(g + (int64_t)s * ld_g + g_col0 + k0 + q) : 0.f;
+                const float gk = act[q] ? __ldg(g + fsw_rowoff(s, ld_g) + g_col0 + k0 + q) : 0.f;
                 dxi_acc[q] += (double)gk * ((double)A0[q] * (double)Sc[q] + (1.0 + (double)xi[q]) * ((double)A0p[q] * (double)Sc[q] - (double)A0[q] * (double)Ss[q]));
             }
         }
@@ -708,6 +708,15 @@ struct __align__(16) FswPair4 {
     int seg, slot, n, pad;
 };
 
+// One batch of U (segment, slot) pairs of a source row: packed ranks and pre-scaled gradients of 4 slices per lane.
+template <int U>
+struct FswPairBatch {
+    uint2 rk[U];
+    float4 ga[U];
+    int nn[U];
+    int slot[U];
+};
+
 __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
                                                             const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
                                                             const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
@@ -722,80 +731,85 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
     if (j >= Nrows) return;
     const int k0 = (chunk * 32 + lane) * V;
     if (k0 >= a.ldp) return;
-    const int ldp = (int)a.ldp;
-    bool act[V];
-#pragma unroll
-    for (int q = 0; q < V; ++q) act[q] = k0 + q < a.K;
+    const int ldp = (int)a.ldp, ldri = (int)ldr;
     float acc[V] = {0.f, 0.f, 0.f, 0.f};
     const int t_beg = __ldg(tptr + j), t_end = __ldg(tptr + j + 1);
     const unsigned lanemask = __activemask();  // lanes beyond the padded row width have left
     const int nlanes = __popc(lanemask);       // active lanes are a prefix 0..nlanes-1
-    for (int tb = t_beg; tb < t_end; tb += nlanes) {
-        // one coalesced load of up to `nlanes` (segment, slot, n) triples, broadcast by shuffles below
-        const int cnt = min(nlanes, t_end - tb);
-        int my_seg = 0, my_slot = 0, my_n = 0;
+    const int step = nlanes >= U ? (nlanes & ~(U - 1)) : nlanes;
+    const unsigned short* rbase = ranks + k0;
+    const float* gbase = GA + k0;
+    const float2* ubase = tab_u + k0;
+    int my_seg = 0, my_slot = 0, my_n = 0, cnt = 0;
+
+    // ranks and gradients of the batch starting at triple t0 (loads only: issued one batch ahead of their use)
+    auto load_batch = [&](int t0, FswPairBatch<U>& B) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int src = min(t0 + u, cnt - 1);
+            const int seg = __shfl_sync(lanemask, my_seg, src);
+            B.slot[u] = __shfl_sync(lanemask, my_slot, src);
+            const int n = __shfl_sync(lanemask, my_n, src);
+            B.nn[u] = t0 + u < cnt ? n : 0;
+            B.rk[u] = __ldg(reinterpret_cast<const uint2*>(rbase + fsw_rowoff(B.slot[u], ldri)));
+            B.ga[u] = __ldg(reinterpret_cast<const float4*>(gbase + fsw_rowoff(seg, ldp)));
+        }
+    };
+    // coefficients cos(pi (2r+1) xi / n) evaluated directly: a table lookup would scatter the 32 lanes of a warp over
+    // 32 cache lines (each lane has its own rank) and bind the kernel on L1 wavefronts.  The phase is formed in fp32
+    // from the double-float xi/n = hi + lo: (2r+1) hi is split exactly with an FMA.  Padding columns carry GA = 0
+    // and xi/n = 0, so whatever their (never written) ranks hold contributes exactly 0.
+    auto consume = [&](const FswPairBatch<U>& B) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (B.nn[u] > 0) {
+                const float2* up = ubase + fsw_rowoff(B.nn[u] - 1, ldp);
+                const float4 u01 = __ldg(reinterpret_cast<const float4*>(up));
+                const float4 u23 = __ldg(reinterpret_cast<const float4*>(up + 2));
+                const float uh[V] = {u01.x, u01.z, u23.x, u23.z};
+                const float ul[V] = {u01.y, u01.w, u23.y, u23.w};
+                const unsigned m2[V] = {(B.rk[u].x & 0xffffu) * 2u + 1u, (B.rk[u].x >> 16) * 2u + 1u, (B.rk[u].y & 0xffffu) * 2u + 1u,
+                                        (B.rk[u].y >> 16) * 2u + 1u};
+                const float gq[V] = {B.ga[u].x, B.ga[u].y, B.ga[u].z, B.ga[u].w};
+                float v[V];
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    // 2r+1 -> float without an I2F: exact below 2^23 through the mantissa trick
+                    const float m = __uint_as_float(0x4B000000u | m2[q]) - 8388608.0f;
+                    const float ph = m * uh[q];
+                    const float pe = fmaf(m, uh[q], -ph);  // exact rounding error of the product
+                    const float pl = fmaf(m, ul[q], pe);
+                    const float hq = (0.5f * ph + 12582912.0f) - 12582912.0f;  // rint(ph / 2) without an FRND
+                    const float red = fmaf(hq, -2.0f, ph);                      // exact: ph reduced to [-1, 1]
+                    v[q] = gq[q] * fsw_cospi_unit(red + pl);
+                    acc[q] += v[q];
+                }
+                if (dEp) fsw_store_vec<V>(dEp + fsw_rowoff(B.slot[u], ldp) + k0, v);
+            }
+        }
+    };
+
+    for (int tb = t_beg; tb < t_end; tb += step) {
+        // one coalesced load of up to `step` (segment, slot, n) triples, broadcast by shuffles in load_batch
+        cnt = min(step, t_end - tb);
         if (lane < cnt) {
             my_seg = __ldg(tseg + tb + lane);
             my_slot = __ldg(tslot + tb + lane);
             my_n = __ldg(tn + tb + lane);
         }
-        for (int t0 = 0; t0 < cnt; t0 += U) {
-            int seg[U], slot[U], nn[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int src = min(t0 + u, cnt - 1);
-                seg[u] = __shfl_sync(lanemask, my_seg, src);
-                slot[u] = __shfl_sync(lanemask, my_slot, src);
-                nn[u] = __shfl_sync(lanemask, my_n, src);
-                if (t0 + u >= cnt) nn[u] = 0;
-            }
-            int r[U][V];
-            float ga[U][V];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                fsw_unpack_ranks<V>(ranks + (int64_t)slot[u] * ldr + k0, r[u]);
-                fsw_load_vec<V>(GA + (int64_t)seg[u] * ldp + k0, ga[u]);
-            }
-            // coefficients cos(pi (2r+1) xi / n) evaluated directly: a table lookup would scatter the 32 lanes of a
-            // warp over 32 cache lines (each lane has its own rank) and bind the kernel on L1 wavefronts.  The phase
-            // is formed in fp32 from the double-float xi/n = hi + lo: (2r+1) hi is split exactly with an FMA.
-            float c[U][V];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int n1 = max(nn[u], 1);
-                const float2* up = tab_u + (int64_t)(n1 - 1) * ldp + k0;
-                const float4 u01 = __ldg(reinterpret_cast<const float4*>(up));
-                const float4 u23 = __ldg(reinterpret_cast<const float4*>(up + 2));
-                const float uh[V] = {u01.x, u01.z, u23.x, u23.z};
-                const float ul[V] = {u01.y, u01.w, u23.y, u23.w};
-#pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    // 2r+1 -> float without an I2F: exact below 2^23 through the mantissa trick
-                    const int ri = (act[q] && nn[u] > 0) ? r[u][q] : 0;
-                    const float m = __uint_as_float(0x4B000000u | (unsigned)(2 * ri + 1)) - 8388608.0f;
-                    const float ph = m * uh[q];
-                    const float pe = fmaf(m, uh[q], -ph);           // exact rounding error of the product
-                    const float pl = fmaf(m, ul[q], pe);
-                    const float hq = (0.5f * ph + 12582912.0f) - 12582912.0f;  // rint(ph / 2) without an FRND
-                    const float red = fmaf(hq, -2.0f, ph);          // exact: ph reduced to [-1, 1]
-                    c[u][q] = fsw_cospi_unit(red + pl);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (nn[u] > 0) {
-                    float v[V];
-#pragma unroll
-                    for (int q = 0; q < V; ++q) {
-                        v[q] = ga[u][q] * c[u][q];
-                        acc[q] += v[q];
-                    }
-                    if (dEp) fsw_store_vec<V>(dEp + (int64_t)slot[u] * ldp + k0, v);
-                }
+        FswPairBatch<U> A, B;
+        load_batch(0, A);
+        for (int t0 = 0; t0 < cnt; t0 += 2 * U) {
+            const bool more = t0 + U < cnt;
+            if (more) load_batch(t0 + U, B);
+            consume(A);
+            if (more) {
+                if (t0 + 2 * U < cnt) load_batch(t0 + 2 * U, A);
+                consume(B);
             }
         }
     }
-    fsw_store_vec<V>(dXp + j * ldp + k0, acc);
+    fsw_store_vec<V>(dXp + fsw_rowoff(j, ldp) + k0, acc);
 }
 
 template <bool HAS_COL, bool NEED_DXI>

@@ -15,7 +15,7 @@
 // index is a constant and the arrays stay in registers whatever NP is.
 template <int NP>
 struct FswNet {
-    static constexpr int kMax = (NP <= 4) ? 8 : NP * 10;  // >= number of comparators (543 for NP = 64)
+    static constexpr int kMax = (NP <= 4) ? 8 : NP * 12;  // >= number of comparators (543 for NP = 64, 1471 for 128)
     struct Pairs {
         int a[kMax];
         int b[kMax];
@@ -95,25 +95,25 @@ __device__ __forceinline__ void fsw_gather_keys(const SegArgs<T>& a, int64_t eba
         for (int j = 0; j < NP; ++j) {
             const int row = __shfl_sync(FSW_FULL, (j < 32) ? c0 : c1, j & 31);
             T v = Num<T>::big();
-            if (j < cnt) v = __ldg(xp + (int64_t)row * a.ldp);
+            if (j < cnt) v = __ldg(xp + fsw_rowoff(row, a.ldp));
             key[j] = v;
         }
     } else {
-        const T* __restrict__ xr = xp + ebase * a.ldp;
+        const T* __restrict__ xr = xp + fsw_rowoff(ebase, a.ldp);
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             T v = Num<T>::big();
-            if (j < cnt) v = __ldg(xr + (int64_t)j * a.ldp);
+            if (j < cnt) v = __ldg(xr + fsw_rowoff(j, a.ldp));
             key[j] = v;
         }
     }
     if (a.Ep) {
-        const T* __restrict__ er = a.Ep + ebase * a.ldp + kk;
+        const T* __restrict__ er = a.Ep + fsw_rowoff(ebase, a.ldp) + kk;
         T ep[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             T v = (T)0;
-            if (j < cnt) v = __ldg(er + (int64_t)j * a.ldp);
+            if (j < cnt) v = __ldg(er + fsw_rowoff(j, a.ldp));
             ep[j] = v;
         }
 #pragma unroll
