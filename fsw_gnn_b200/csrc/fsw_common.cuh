@@ -68,10 +68,10 @@ struct Num<double> {
     static __device__ __forceinline__ double reduce(double phi) { return phi; }
 };
 
-// row * stride for operands known to fit 32 unsigned bits (node / edge indices of the int32 CSR, padded widths): one
-// IMAD.WIDE.U32 where an int64 stride would cost a full 64x64 multiply (5-7 instructions) per address.
+// row * stride for operands known to fit 31 bits (node / edge indices of the int32 CSR, padded widths): one
+// IMAD.WIDE where an int64 stride would cost a full 64x64 multiply (5-7 instructions) per address.
 __device__ __forceinline__ int64_t fsw_rowoff(int64_t row, int64_t ld) {
-    return (int64_t)((unsigned long long)(unsigned int)row * (unsigned int)ld);
+    return (int64_t)(int)row * (int64_t)(int)ld;
 }
 
 // cos(pi t) for |t| <= 1 (phase already reduced): no conversions, no range reduction - fold to [0, 1/2] and
@@ -178,11 +178,14 @@ int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float*
 int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* tab_c, float* tab_t, float* tab_A, float* tab_Ap,
                           cudaStream_t st, float2* tab_u = nullptr);
 size_t fsw_rank_tables_bytes(int64_t ldp);
-// forward coefficient tables (cos and d/dxi) for n <= FSW_FWD_TAB_NMAX, in front of the forward scratch when training
+// forward coefficient tables (cos and d/dxi) for n <= FSW_FWD_TAB_NMAX, slice-major [k][n][FSW_FWD_TAB_LD], in front of
+// the forward scratch (fsw_embed_packed.cu)
 #define FSW_FWD_TAB_NMAX 256
-static inline size_t fsw_fwd_tables_bytes(int64_t ldp) {
-    return (size_t)(2 * ((int64_t)FSW_FWD_TAB_NMAX * (FSW_FWD_TAB_NMAX + 1) / 2) * ldp) * sizeof(float);
+#define FSW_FWD_TAB_LD 256
+static inline size_t fsw_fwd_tables_bytes(int64_t K) {
+    return (size_t)(2 * K * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD) * sizeof(float);
 }
+int fsw_build_fwd_tables(const float* freqs, int K, float* tab_c, float* tab_t, cudaStream_t st);
 int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g,
                            int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, void* tables, cudaStream_t st);
 

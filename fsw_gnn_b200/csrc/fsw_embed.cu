@@ -17,6 +17,8 @@
 // weights and reduced mod 2 before it is rounded to fp32; everything else is fp32 for fp32 inputs.
 // The sparse product form D_j = 2 w sinc(xi w) cos(pi xi (2C - w)) (fsw_embedding.py:1047-1075) is
 // used for both value and gradient; it is well conditioned for every xi >= 0.
+#include <cstdlib>
+
 #include "fsw_sortnet.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -711,15 +713,16 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                     T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
     const int msn = max_small_np<T>();
-    // training (fp32): coefficient tables for n <= FSW_FWD_TAB_NMAX at the front of the scratch, if any medium class exists
+    // fp32: slice-major coefficient tables for n <= FSW_FWD_TAB_NMAX at the front of the scratch, when a size class
+    // served by the packed-key kernels is present
     const float* gtab_c = nullptr;
     const float* gtab_t = nullptr;
     if constexpr (sizeof(T) == 4) {
-        const size_t tb = fsw_fwd_tables_bytes(a.ldp);
-        if (bo[64 + 1] < bo[FSW_FWD_TAB_NMAX + 1] && scratch_bytes >= tb) {
+        const size_t tb = fsw_fwd_tables_bytes(a.K);
+        if (bo[32 + 1] < bo[FSW_FWD_TAB_NMAX + 1] && scratch_bytes >= tb) {
             float* tc = (float*)scratch;
-            float* tt = tc + (int64_t)FSW_FWD_TAB_NMAX * (FSW_FWD_TAB_NMAX + 1) / 2 * a.ldp;
-            int rc = fsw_build_coef_tables(a.freqs, a.K, (int)a.ldp, FSW_FWD_TAB_NMAX, tc, tt, nullptr, nullptr, st);
+            float* tt = tc + (int64_t)a.K * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD;
+            int rc = fsw_build_fwd_tables(a.freqs, a.K, tc, tt, st);
             if (rc) return rc;
             gtab_c = tc;
             gtab_t = tt;
@@ -734,6 +737,14 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 if (c.np > msn) continue;
                 const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
                 if (hi <= lo) continue;
+                if constexpr (sizeof(T) == 4) {
+                    if (gtab_c != nullptr && c.np > 32) {  // 33..64: packed keys, 4 cooperating lanes
+                        const int np = c.np == 48 ? 64 : c.np;
+                        int rc = fsw_packed_forward_u(a, np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+                        if (rc) return rc;
+                        continue;
+                    }
+                }
                 int rc = fsw_small_forward_u<T>(a, c.np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
                 if (rc) return rc;
             }
@@ -759,7 +770,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                     continue;
                 }
                 if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 128 elements
-                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+                    int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, nullptr, nullptr, st);
                     if (rc) return rc;
                     continue;
                 }
@@ -952,7 +963,7 @@ extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t 
             if (grid * tb > need) need = grid * tb;
         }
     }
-    if (dtype == FSW_F32) need += backward ? fsw_rank_tables_bytes((K + 7) / 8 * 8) : fsw_fwd_tables_bytes((K + 7) / 8 * 8);
+    if (dtype == FSW_F32) need += backward ? fsw_rank_tables_bytes((K + 7) / 8 * 8) : fsw_fwd_tables_bytes(K);
     return need;
 }
 

@@ -17,6 +17,8 @@
 //       (fsw_build_coef_tables); the L partial sums of a slice are combined with shuffles.
 //     * SAVE_RANK: the slot of each consumed full key is overwritten by its sorted position and streamed out
 //       as uint16 rank[(e0+e), k] for the sort-free backward (fsw_embed_small.cu).
+#include <cstdlib>
+
 #include "fsw_sortnet.cuh"
 
 namespace {
@@ -71,6 +73,56 @@ __device__ __forceinline__ void fsw_pk_cols(const int32_t* __restrict__ col, int
     }
 }
 
+// SW consecutive 32-bit words (SW = 1, 2, 4, 8, 16) at a 4 SW-byte aligned address
+template <int SW>
+__device__ __forceinline__ void fsw_ldg_words(const float* p, float (&v)[SW]) {
+    if constexpr (SW == 1) {
+        v[0] = __ldg(p);
+    } else if constexpr (SW == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < SW / 4; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+            v[4 * q] = t.x;
+            v[4 * q + 1] = t.y;
+            v[4 * q + 2] = t.z;
+            v[4 * q + 3] = t.w;
+        }
+    }
+}
+
+template <int SW>
+__device__ __forceinline__ void fsw_sts_words(float* p, const float (&v)[SW]) {
+    if constexpr (SW == 1) {
+        *p = v[0];
+    } else if constexpr (SW == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < SW / 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+
+// SW sorted positions (ints in shared memory) -> SW uint16 ranks, one vector store
+template <int SW>
+__device__ __forceinline__ void fsw_store_ranks(unsigned short* dst, const int* src) {
+    if constexpr (SW == 1) {
+        *dst = (unsigned short)src[0];
+    } else if constexpr (SW == 2) {
+        const int2 t = *reinterpret_cast<const int2*>(src);
+        *reinterpret_cast<unsigned*>(dst) = (unsigned)t.x | ((unsigned)t.y << 16);
+    } else {
+#pragma unroll
+        for (int q = 0; q < SW / 4; ++q) {
+            const int4 t = reinterpret_cast<const int4*>(src)[q];
+            reinterpret_cast<uint2*>(dst)[q] = make_uint2((unsigned)t.x | ((unsigned)t.y << 16), (unsigned)t.z | ((unsigned)t.w << 16));
+        }
+    }
+}
+
 // compare-exchange of two packed words held by this lane
 #define FSW_PK_CMPX(x, y)        \
     {                            \
@@ -79,17 +131,16 @@ __device__ __forceinline__ void fsw_pk_cols(const int32_t* __restrict__ col, int
         x = lo_;                 \
     }
 
-template <int R, int L, bool HAS_COL, bool SAVE_RANK>
-__global__ void __launch_bounds__(128, 5) fsw_coop_fwd_kernel(SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks,
-                                                           float* __restrict__ out, int64_t ld_out, int64_t out_col0,
-                                                           const float* __restrict__ bias, unsigned short* __restrict__ ranks,
-                                                           int64_t ldr, float* __restrict__ dxi_out, int64_t ld_dxi,
-                                                           const float* __restrict__ gtab_c, const float* __restrict__ gtab_t) {
-    static_assert(L == 1 || (R & (R - 1)) == 0, "bitonic cross-lane merges need a power-of-two run length");
-    static_assert((L & (L - 1)) == 0 && L <= 32, "lanes per slice: power of two");
+template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool LOCK>
+__global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)) fsw_coop_fwd_kernel(
+    SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks, float* __restrict__ out, int64_t ld_out, int64_t out_col0,
+    const float* __restrict__ bias, unsigned short* __restrict__ ranks, int64_t ldr, float* __restrict__ dxi_out, int64_t ld_dxi,
+    const float* __restrict__ gtab_c, const float* __restrict__ gtab_t) {
+    static_assert((R & (R - 1)) == 0 && R >= 4, "bitonic cross-lane merges and float4 table reads need R = 4, 8, 16, 32");
+    static_assert((L & (L - 1)) == 0 && L >= 4 && L <= 32, "lanes per slice: power of two; 32 / L <= 8 slices tile the padded width");
     constexpr int SW = 32 / L;            // slices per warp
     constexpr int NS = R * L;             // element slots per (segment, slice)
-    constexpr int NC = (NS + 31) / 32;    // column-id registers per lane
+    constexpr int NC = NS / 32;           // elements per lane in the row-wise phases (gather, rank store)
     constexpr int IDXB = fsw_clog2(NS);   // low bits that carry the element index
     constexpr int IMASK = (1 << IDXB) - 1;
     constexpr int LOGL = fsw_clog2(L);
@@ -100,28 +151,31 @@ __global__ void __launch_bounds__(128, 5) fsw_coop_fwd_kernel(SegArgs<float> a, 
     const int sl = lane % SW;  // slice within the warp
     float* fkw = reinterpret_cast<float*>(fsw_smem_raw) + (size_t)warp * NS * SW;  // full keys [NS][SW] of this warp
     float* fks = fkw + sl;                                                          // column of this lane's slice
-    float* fkl = fkw + lane;                                                        // element i*L+g of this lane: fkl[i*32]
+    const float* fkl = fkw + lane;                                                  // element i*L+g of this lane: fkl[i*32]
     int* fksi = reinterpret_cast<int*>(fks);
-    const int* fkli = reinterpret_cast<const int*>(fkl);
 
     const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const int64_t item = wglobal / nchunks;
     const int chunk = (int)(wglobal - item * nchunks);
-    const int64_t first64 = (int64_t)seg_lo + item * G;
-    if (first64 >= seg_hi) return;
+    int64_t first64 = (int64_t)seg_lo + item * G;
+    if (!LOCK && first64 >= seg_hi) return;
+    if (first64 > seg_hi) first64 = seg_hi;  // LOCK: idle warps keep meeting the barriers of their group
     const int first = (int)first64;
     const int last = (int)((first64 + G < seg_hi) ? first64 + G : seg_hi);
-    const int k = chunk * SW + sl;
+    const int k0 = chunk * SW;  // the warp's slices k0 .. k0+SW-1 (inside the padded width: SW divides 8 | ldp, or ldp % SW == 0)
+    const int k = k0 + sl;
     const bool act = k < a.K;
     const int kk = act ? k : a.K - 1;
     const float xi = __ldg(a.freqs + kk);
     const double xid = (double)xi;
     const float bk = (bias != nullptr) ? __ldg(bias + kk) : 0.f;
     const int ldp = (int)a.ldp;
-    const int ldb = ldp * (int)sizeof(float);
-    const char* xp_bytes = reinterpret_cast<const char*>(a.Xp + kk);
-    const char* ep_bytes = a.Ep ? reinterpret_cast<const char*>(a.Ep + kk) : nullptr;
+    const float* xp0 = a.Xp + k0;
+    const float* ep0 = a.Ep ? a.Ep + k0 : nullptr;
     const bool want_dxi = SAVE_RANK && dxi_out != nullptr;
+    // this lane's table rows: [kk][n][0 .. FSW_FWD_TAB_LD), positions g R .. g R + R - 1
+    const float* tck = gtab_c + (int64_t)kk * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD + g * R;
+    const float* ttk = gtab_t + (int64_t)kk * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD + g * R;
 
     // software pipeline over segments: order two ahead, row range one ahead, column ids one ahead
     PkMeta cur, nx1;
@@ -136,34 +190,42 @@ __global__ void __launch_bounds__(128, 5) fsw_coop_fwd_kernel(SegArgs<float> a, 
 
     int n_prev = -1;
     float A = 0.f, A0 = 0.f, A0p = 0.f;
-    const float* tc = gtab_c;
-    const float* tt = gtab_t;
+    const float* tc = tck;
+    const float* tt = ttk;
 
-    for (int q = first; q < last; ++q) {
-        const int n = cur.n;
-        int s[R];
-        // ---- gather: lane (g, sl) takes elements e = i L + g; all its loads are in flight together ----
-        if (HAS_COL) {
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int row = __shfl_sync(FSW_FULL, c[(i * L) >> 5], ((i * L) & 31) + g);
-                s[i] = 0;
-                if (i * L + g < n) s[i] = __float_as_int(__ldg(reinterpret_cast<const float*>(xp_bytes + fsw_rowoff(row, ldb))));
-            }
-        } else {
-            const char* __restrict__ base = xp_bytes + (cur.e0 + g) * ldb;
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                s[i] = 0;
-                if (i * L + g < n) s[i] = __float_as_int(__ldg(reinterpret_cast<const float*>(base + fsw_rowoff(i * L, ldb))));
-            }
+#pragma unroll 1
+    for (int q = first; q < (LOCK ? first + G : last); ++q) {
+        if (LOCK) {
+            // the warps that share an SM sub-partition (warp id mod 4) walk the straight-line sort together, so one
+            // instruction fetch serves all of them
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"((int)blockDim.x / 4) : "memory");
+            if (q >= last) continue;
         }
-        if (ep_bytes != nullptr) {  // edge features: per-slot additive projection (rare path)
-            const char* __restrict__ eb = ep_bytes + (cur.e0 + g) * ldb;
+        const int n = cur.n;
+        // ---- gather, row-wise: lane l takes elements e = 32 t + l and reads the SW slices of the row in one vector
+        //      load; the keys go to shared memory as [element][slice].  -0 becomes +0 (zeros tie, torch.sort compares
+        //      values); slots beyond n get a huge finite key whose upper bits differ per slot (their own tie groups).
 #pragma unroll
-            for (int i = 0; i < R; ++i)
-                if (i * L + g < n)
-                    s[i] = __float_as_int(__int_as_float(s[i]) + __ldg(reinterpret_cast<const float*>(eb + fsw_rowoff(i * L, ldb))));
+        for (int t = 0; t < NC; ++t) {
+            const int e = t * 32 + lane;
+            float v[SW];
+            if (e < n) {
+                const int64_t row = HAS_COL ? (int64_t)c[t] : cur.e0 + e;
+                fsw_ldg_words<SW>(xp0 + fsw_rowoff(row, ldp), v);
+                if (ep0 != nullptr) {  // edge features: per-slot additive projection (rare path)
+                    float w[SW];
+                    fsw_ldg_words<SW>(ep0 + fsw_rowoff(cur.e0 + e, ldp), w);
+#pragma unroll
+                    for (int j = 0; j < SW; ++j) v[j] += w[j];
+                }
+#pragma unroll
+                for (int j = 0; j < SW; ++j) v[j] += 0.0f;
+            } else {
+                const float pad = __int_as_float(0x7f000000 | (e << IDXB));
+#pragma unroll
+                for (int j = 0; j < SW; ++j) v[j] = pad;
+            }
+            fsw_sts_words<SW>(fkw + e * SW, v);
         }
         // prefetches for the following segments (their addresses were loaded one iteration ago)
         int cn[NC];
@@ -178,25 +240,20 @@ __global__ void __launch_bounds__(128, 5) fsw_coop_fwd_kernel(SegArgs<float> a, 
             const float wn = (float)(1.0 / (double)n);
             fsw_amplitude<float, SAVE_RANK>(u, wn, xi, A0, A0p);
             A = (1.f + xi) * A0;
-            const int64_t row0 = (int64_t)n * (n - 1) / 2 + g * R;  // table row of this lane's first sorted position
-            tc = gtab_c + row0 * ldp + kk;
-            tt = gtab_t + row0 * ldp + kk;
+            tc = tck + n * FSW_FWD_TAB_LD;
+            tt = ttk + n * FSW_FWD_TAB_LD;
             n_prev = n;
         }
+        __syncwarp();
 
-        // ---- pack: full key to shared memory, sortable image | element index to the register ----
+        // ---- pack: lane (g, sl) takes elements e = i L + g of its slice: sortable image | element index ----
+        int s[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            const int e = i * L + g;
-            const bool valid = e < n;
-            const float v = valid ? __int_as_float(s[i]) + 0.0f : 0.f;  // -0 -> +0: zeros tie (torch.sort compares values)
-            fkl[i * 32] = v;                                            // = fkw[e * SW + sl]
-            const int b = __float_as_int(v);
+            const int b = __float_as_int(fkl[i * 32]);  // = fkw[(i L + g) SW + sl]
             const int t = b ^ ((b >> 31) & 0x7fffffff);
-            // padding slots: above +inf, every slot its own group, in slot order
-            s[i] = valid ? ((t & ~IMASK) | e) : (0x7f800000 | (e << IDXB) | e);
+            s[i] = ((t & ~IMASK) | g) + i * L;
         }
-        if (L > 1) __syncwarp();
         // ---- sort the lane's run, then merge the runs of the L lanes ----
         fsw_sort_network<R>([&](int i, int l) { FSW_PK_CMPX(s[i], s[l]); });
         fsw_static_for<LOGL>([&](auto lc) {
@@ -307,16 +364,24 @@ __global__ void __launch_bounds__(128, 5) fsw_coop_fwd_kernel(SegArgs<float> a, 
         }
 
         // ---- Fourier sums over sorted positions; ranks replace the consumed keys ----
+        // Table rows are zero beyond n, so the huge keys of padding slots (positions >= n) contribute exactly 0.
         float acc = 0.f, acc2 = 0.f;
         const int p0 = g * R;
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            if (p0 + i < n) {
-                const int idx = s[i] & IMASK;
+        for (int i4 = 0; i4 < R; i4 += 4) {
+            float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), tv = cv;
+            const bool live = p0 + i4 < n;
+            if (live) cv = __ldg(reinterpret_cast<const float4*>(tc + i4));
+            if (want_dxi && live) tv = __ldg(reinterpret_cast<const float4*>(tt + i4));
+            const float cq[4] = {cv.x, cv.y, cv.z, cv.w};
+            const float tq[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = s[i4 + j] & IMASK;
                 const float key = fks[idx * SW];
-                acc = fmaf(key, __ldg(tc + fsw_rowoff(i, ldp)), acc);
-                if (want_dxi) acc2 = fmaf(key, __ldg(tt + fsw_rowoff(i, ldp)), acc2);
-                if (SAVE_RANK) fksi[idx * SW] = p0 + i;
+                acc = fmaf(key, cq[j], acc);
+                acc2 = fmaf(key, tq[j], acc2);
+                if (SAVE_RANK) fksi[idx * SW] = p0 + i4 + j;
             }
         }
 #pragma unroll
@@ -328,14 +393,16 @@ __global__ void __launch_bounds__(128, 5) fsw_coop_fwd_kernel(SegArgs<float> a, 
             out[fsw_rowoff(cur.s, ld_out) + out_col0 + k] = A * acc + bk;
             if (want_dxi) dxi_out[fsw_rowoff(cur.s, ld_dxi) + k] = A0 * acc + (1.f + xi) * (A0p * acc - A0 * acc2);
         }
+        __syncwarp();
         if constexpr (SAVE_RANK) {
-            if (L > 1) __syncwarp();
-            unsigned short* rp = ranks + fsw_rowoff(cur.e0 + g, ldr) + k;
+            // row-wise again: lane l writes the SW ranks of elements 32 t + l with one vector store
 #pragma unroll
-            for (int i = 0; i < R; ++i)
-                if (i * L + g < n && act) rp[fsw_rowoff(i * L, ldr)] = (unsigned short)fkli[i * 32];
+            for (int t = 0; t < NC; ++t) {
+                const int e = t * 32 + lane;
+                if (e < n) fsw_store_ranks<SW>(ranks + fsw_rowoff(cur.e0 + e, ldr) + k0, reinterpret_cast<const int*>(fkw) + e * SW);
+            }
+            __syncwarp();
         }
-        if (L > 1) __syncwarp();
         // rotate the pipeline
         cur = nx1;
 #pragma unroll
@@ -345,7 +412,27 @@ __global__ void __launch_bounds__(128, 5) fsw_coop_fwd_kernel(SegArgs<float> a, 
     }
 }
 
-template <int R, int L, bool HAS_COL, bool SAVE_RANK>
+// slice-major forward tables: tab[(k (NMAX+1) + n) LD + j] = cos(pi xi_k (2j+1)/n) (and its d/dxi companion) for
+// j < n, zero for n <= j < LD.  A lane of the coop kernel reads its R consecutive positions as float4s.
+__global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* __restrict__ freqs, int K, float* __restrict__ tab_c,
+                                                                   float* __restrict__ tab_t) {
+    const int n = blockIdx.x + 1;
+    const int k = blockIdx.y;
+    const int j = threadIdx.x;
+    float c = 0.f, t = 0.f;
+    if (j < n) {
+        const double u = (double)freqs[k] / (double)n;
+        const float wn = (float)(1.0 / (double)n);
+        const float rr = Num<float>::reduce(u * (double)(2 * j + 1));
+        c = cospif(rr);
+        t = (float)M_PI * wn * (float)(2 * j + 1) * sinpif(rr);
+    }
+    const int64_t at = ((int64_t)k * (FSW_FWD_TAB_NMAX + 1) + n) * FSW_FWD_TAB_LD + j;
+    tab_c[at] = c;
+    tab_t[at] = t;
+}
+
+template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool LOCK>
 int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0, const float* bias,
                     unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
                     cudaStream_t st) {
@@ -355,13 +442,14 @@ int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t
     if (G < 1) G = 1;
     if (G > 32) G = 32;
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
-    const int64_t blocks = fsw_cdiv(warps, 4);
-    const size_t smem = (size_t)4 * R * 32 * sizeof(float);
-    auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>;
+    constexpr int WPB = LOCK ? 16 : 4;
+    const int64_t blocks = fsw_cdiv(warps, WPB);
+    const size_t smem = (size_t)WPB * R * 32 * sizeof(float);
+    auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK, LOCK>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const std::string label = std::string(SAVE_RANK ? "fwdr_coop_u" : "fwd_coop_u") + std::to_string(R * L) + "_f32";
+    static const std::string label = std::string(SAVE_RANK ? "fwdr_coop_u" : "fwd_coop_u") + std::to_string(R * L) + "_f32";  // R x L slots
     fsw_prof_begin(label.c_str(), st);
-    kern<<<(unsigned)blocks, 128, smem, st>>>(a, lo, hi, (int)G, nchunks, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t);
+    kern<<<(unsigned)blocks, WPB * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_coop_fwd_kernel");
     return FSW_OK;
@@ -372,26 +460,47 @@ int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_
                 unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
                 cudaStream_t st) {
     const bool has_col = a.col != nullptr;
+    static const bool lock = getenv("FSW_COOP_LOCK") != nullptr;
     if (ranks) {
-        return has_col ? launch_coop_fwd<R, L, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st)
-                       : launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+        if (has_col && lock) return launch_coop_fwd<R, L, true, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+        return has_col ? launch_coop_fwd<R, L, true, true, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st)
+                       : launch_coop_fwd<R, L, false, true, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
     }
-    return has_col ? launch_coop_fwd<R, L, true, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st)
-                   : launch_coop_fwd<R, L, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st);
+    return has_col ? launch_coop_fwd<R, L, true, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st)
+                   : launch_coop_fwd<R, L, false, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st);
 }
 
 }  // namespace
 
-// uniform-weight fp32 segments order[lo, hi) with n <= np, np in {64, 128, 256}; gtab_c (and gtab_t when dxi_out is
-// given) must cover n <= np (fsw_build_coef_tables layout)
+int fsw_build_fwd_tables(const float* freqs, int K, float* tab_c, float* tab_t, cudaStream_t st) {
+    static_assert(FSW_FWD_TAB_LD == 256 && FSW_FWD_TAB_NMAX <= FSW_FWD_TAB_LD, "one thread per table position");
+    fsw_prof_begin("coef_tables", st);
+    fsw_build_fwd_tables_kernel<<<dim3(FSW_FWD_TAB_NMAX, K), FSW_FWD_TAB_LD, 0, st>>>(freqs, K, tab_c, tab_t);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_build_fwd_tables_kernel");
+    return FSW_OK;
+}
+
+// uniform-weight fp32 segments order[lo, hi) with n <= np, np in {64, 128, 256}; gtab_c / gtab_t: slice-major
+// tables of fsw_build_fwd_tables ([k][n][FSW_FWD_TAB_LD], zero beyond position n-1)
 int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0,
                          const float* bias, unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c,
                          const float* gtab_t, cudaStream_t st) {
     if (gtab_c == nullptr) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: coefficient table missing");
-    switch (np) {
-        case 64: return launch_coop<32, 2>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
-        case 128: return launch_coop<32, 4>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
-        case 256: return launch_coop<32, 8>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+#define FSW_COOP_CASE(NP_, R_, L_) \
+    case NP_: return launch_coop<R_, L_>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+    static const bool r32 = getenv("FSW_COOP_R32") != nullptr;
+    if (r32) {
+        switch (np) {
+            FSW_COOP_CASE(128, 32, 4)
+            FSW_COOP_CASE(256, 32, 8)
+        }
     }
+    switch (np) {
+        FSW_COOP_CASE(64, 16, 4)
+        FSW_COOP_CASE(128, 16, 8)
+        FSW_COOP_CASE(256, 16, 16)
+    }
+#undef FSW_COOP_CASE
     return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: class %d", np);
 }
