@@ -178,8 +178,8 @@ int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float*
 int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* tab_c, float* tab_t, float* tab_A, float* tab_Ap,
                           cudaStream_t st, float2* tab_u = nullptr);
 size_t fsw_rank_tables_bytes(int64_t ldp);
-// forward coefficient tables (cos and d/dxi) for n <= FSW_FWD_TAB_NMAX, slice-major [k][n][FSW_FWD_TAB_LD], in front of
-// the forward scratch (fsw_embed_packed.cu)
+// forward coefficient tables (cos and d/dxi) for n <= FSW_FWD_TAB_NMAX, [n][FSW_FWD_TAB_LD/4][K][4], in front of the
+// forward scratch (fsw_embed_packed.cu)
 #define FSW_FWD_TAB_NMAX 256
 #define FSW_FWD_TAB_LD 256
 static inline size_t fsw_fwd_tables_bytes(int64_t K) {

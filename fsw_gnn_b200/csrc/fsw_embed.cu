@@ -721,7 +721,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
         const size_t tb = fsw_fwd_tables_bytes(a.K);
         if (bo[32 + 1] < bo[FSW_FWD_TAB_NMAX + 1] && scratch_bytes >= tb) {
             float* tc = (float*)scratch;
-            float* tt = tc + (int64_t)a.K * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD;
+            float* tt = tc + fsw_fwd_tables_bytes(a.K) / (2 * sizeof(float));
             int rc = fsw_build_fwd_tables(a.freqs, a.K, tc, tt, st);
             if (rc) return rc;
             gtab_c = tc;

@@ -114,11 +114,16 @@ __device__ __forceinline__ void fsw_store_ranks(unsigned short* dst, const int* 
     } else if constexpr (SW == 2) {
         const int2 t = *reinterpret_cast<const int2*>(src);
         *reinterpret_cast<unsigned*>(dst) = (unsigned)t.x | ((unsigned)t.y << 16);
+    } else if constexpr (SW == 4) {
+        const int4 t = *reinterpret_cast<const int4*>(src);
+        *reinterpret_cast<uint2*>(dst) = make_uint2((unsigned)t.x | ((unsigned)t.y << 16), (unsigned)t.z | ((unsigned)t.w << 16));
     } else {
 #pragma unroll
-        for (int q = 0; q < SW / 4; ++q) {
-            const int4 t = reinterpret_cast<const int4*>(src)[q];
-            reinterpret_cast<uint2*>(dst)[q] = make_uint2((unsigned)t.x | ((unsigned)t.y << 16), (unsigned)t.z | ((unsigned)t.w << 16));
+        for (int q = 0; q < SW / 8; ++q) {
+            const int4 t = reinterpret_cast<const int4*>(src)[2 * q];
+            const int4 u = reinterpret_cast<const int4*>(src)[2 * q + 1];
+            reinterpret_cast<uint4*>(dst)[q] = make_uint4((unsigned)t.x | ((unsigned)t.y << 16), (unsigned)t.z | ((unsigned)t.w << 16),
+                                                          (unsigned)u.x | ((unsigned)u.y << 16), (unsigned)u.z | ((unsigned)u.w << 16));
         }
     }
 }
@@ -140,7 +145,10 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
     static_assert((L & (L - 1)) == 0 && L >= 4 && L <= 32, "lanes per slice: power of two; 32 / L <= 8 slices tile the padded width");
     constexpr int SW = 32 / L;            // slices per warp
     constexpr int NS = R * L;             // element slots per (segment, slice)
-    constexpr int NC = NS / 32;           // elements per lane in the row-wise phases (gather, rank store)
+    constexpr int NC = NS / 32;           // column-id registers per lane (element 32 m + lane)
+    constexpr int VW = SW < 4 ? SW : 4;   // gather: floats per lane,
+    constexpr int LPR = SW / VW;          //         lanes per row,
+    constexpr int RPI = 32 / LPR;         //         rows per load instruction
     constexpr int IDXB = fsw_clog2(NS);   // low bits that carry the element index
     constexpr int IMASK = (1 << IDXB) - 1;
     constexpr int LOGL = fsw_clog2(L);
@@ -173,9 +181,10 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
     const float* xp0 = a.Xp + k0;
     const float* ep0 = a.Ep ? a.Ep + k0 : nullptr;
     const bool want_dxi = SAVE_RANK && dxi_out != nullptr;
-    // this lane's table rows: [kk][n][0 .. FSW_FWD_TAB_LD), positions g R .. g R + R - 1
-    const float* tck = gtab_c + (int64_t)kk * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD + g * R;
-    const float* ttk = gtab_t + (int64_t)kk * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD + g * R;
+    // this lane's table entries: [n][position / 4][kk][position % 4], positions g R .. g R + R - 1
+    const int tstride = a.K * 4;  // floats between consecutive position blocks
+    const float* tck = gtab_c + (int64_t)(g * (R / 4)) * tstride + kk * 4;
+    const float* ttk = gtab_t + (int64_t)(g * (R / 4)) * tstride + kk * 4;
 
     // software pipeline over segments: order two ahead, row range one ahead, column ids one ahead
     PkMeta cur, nx1;
@@ -202,30 +211,33 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
             if (q >= last) continue;
         }
         const int n = cur.n;
-        // ---- gather, row-wise: lane l takes elements e = 32 t + l and reads the SW slices of the row in one vector
-        //      load; the keys go to shared memory as [element][slice].  -0 becomes +0 (zeros tie, torch.sort compares
+        // ---- gather, row-wise: LPR adjacent lanes read the SW slices of one row (one sector-aligned vector each), 32/LPR
+        //      rows per instruction; the keys go to shared memory as [element][slice].  -0 becomes +0 (zeros tie, torch.sort compares
         //      values); slots beyond n get a huge finite key whose upper bits differ per slot (their own tie groups).
 #pragma unroll
-        for (int t = 0; t < NC; ++t) {
-            const int e = t * 32 + lane;
-            float v[SW];
+        for (int t = 0; t < NS / RPI; ++t) {
+            const int e = t * RPI + lane / LPR;
+            const int part = (lane % LPR) * VW;
+            float v[VW];
+            int row = 0;
+            if (HAS_COL) row = (LPR == 1) ? c[t] : __shfl_sync(FSW_FULL, c[(t * RPI) >> 5], ((t * RPI) & 31) + lane / LPR);
             if (e < n) {
-                const int64_t row = HAS_COL ? (int64_t)c[t] : cur.e0 + e;
-                fsw_ldg_words<SW>(xp0 + fsw_rowoff(row, ldp), v);
+                const int64_t r64 = HAS_COL ? (int64_t)row : cur.e0 + e;
+                fsw_ldg_words<VW>(xp0 + fsw_rowoff(r64, ldp) + part, v);
                 if (ep0 != nullptr) {  // edge features: per-slot additive projection (rare path)
-                    float w[SW];
-                    fsw_ldg_words<SW>(ep0 + fsw_rowoff(cur.e0 + e, ldp), w);
+                    float w[VW];
+                    fsw_ldg_words<VW>(ep0 + fsw_rowoff(cur.e0 + e, ldp) + part, w);
 #pragma unroll
-                    for (int j = 0; j < SW; ++j) v[j] += w[j];
+                    for (int j = 0; j < VW; ++j) v[j] += w[j];
                 }
 #pragma unroll
-                for (int j = 0; j < SW; ++j) v[j] += 0.0f;
+                for (int j = 0; j < VW; ++j) v[j] += 0.0f;
             } else {
                 const float pad = __int_as_float(0x7f000000 | (e << IDXB));
 #pragma unroll
-                for (int j = 0; j < SW; ++j) v[j] = pad;
+                for (int j = 0; j < VW; ++j) v[j] = pad;
             }
-            fsw_sts_words<SW>(fkw + e * SW, v);
+            fsw_sts_words<VW>(fkw + e * SW + part, v);
         }
         // prefetches for the following segments (their addresses were loaded one iteration ago)
         int cn[NC];
@@ -240,8 +252,8 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
             const float wn = (float)(1.0 / (double)n);
             fsw_amplitude<float, SAVE_RANK>(u, wn, xi, A0, A0p);
             A = (1.f + xi) * A0;
-            tc = tck + n * FSW_FWD_TAB_LD;
-            tt = ttk + n * FSW_FWD_TAB_LD;
+            tc = tck + (int64_t)n * (FSW_FWD_TAB_LD / 4) * tstride;
+            tt = ttk + (int64_t)n * (FSW_FWD_TAB_LD / 4) * tstride;
             n_prev = n;
         }
         __syncwarp();
@@ -364,15 +376,15 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
         }
 
         // ---- Fourier sums over sorted positions; ranks replace the consumed keys ----
-        // Table rows are zero beyond n, so the huge keys of padding slots (positions >= n) contribute exactly 0.
+        // Table entries are zero beyond n, so the huge keys of padding slots (positions >= n) contribute exactly 0.
         float acc = 0.f, acc2 = 0.f;
         const int p0 = g * R;
 #pragma unroll
         for (int i4 = 0; i4 < R; i4 += 4) {
             float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), tv = cv;
             const bool live = p0 + i4 < n;
-            if (live) cv = __ldg(reinterpret_cast<const float4*>(tc + i4));
-            if (want_dxi && live) tv = __ldg(reinterpret_cast<const float4*>(tt + i4));
+            if (live) cv = __ldg(reinterpret_cast<const float4*>(tc + fsw_rowoff(i4 / 4, tstride)));
+            if (want_dxi && live) tv = __ldg(reinterpret_cast<const float4*>(tt + fsw_rowoff(i4 / 4, tstride)));
             const float cq[4] = {cv.x, cv.y, cv.z, cv.w};
             const float tq[4] = {tv.x, tv.y, tv.z, tv.w};
 #pragma unroll
@@ -381,7 +393,7 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
                 const float key = fks[idx * SW];
                 acc = fmaf(key, cq[j], acc);
                 acc2 = fmaf(key, tq[j], acc2);
-                if (SAVE_RANK) fksi[idx * SW] = p0 + i4 + j;
+                if (SAVE_RANK) fksi[idx * SW] = p0 + i4 + j;  // the consumed key's slot now holds the element's rank
             }
         }
 #pragma unroll
@@ -401,7 +413,7 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
                 const int e = t * 32 + lane;
                 if (e < n) fsw_store_ranks<SW>(ranks + fsw_rowoff(cur.e0 + e, ldr) + k0, reinterpret_cast<const int*>(fkw) + e * SW);
             }
-            __syncwarp();
+            __syncwarp();  // the next segment's gather overwrites the slots
         }
         // rotate the pipeline
         cur = nx1;
@@ -412,24 +424,27 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
     }
 }
 
-// slice-major forward tables: tab[(k (NMAX+1) + n) LD + j] = cos(pi xi_k (2j+1)/n) (and its d/dxi companion) for
-// j < n, zero for n <= j < LD.  A lane of the coop kernel reads its R consecutive positions as float4s.
+// forward tables, blocked by 4 positions with the slice index inside:
+//   tab[((n (LD/4) + j/4) K + k) 4 + j%4] = cos(pi xi_k (2j+1)/n) (and its d/dxi companion) for j < n, zero for j >= n.
+// The 32/L lanes that hold the same positions of adjacent slices read adjacent float4s: one cache line per lane group.
 __global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* __restrict__ freqs, int K, float* __restrict__ tab_c,
                                                                    float* __restrict__ tab_t) {
     const int n = blockIdx.x + 1;
-    const int k = blockIdx.y;
-    const int j = threadIdx.x;
-    float c = 0.f, t = 0.f;
-    if (j < n) {
-        const double u = (double)freqs[k] / (double)n;
-        const float wn = (float)(1.0 / (double)n);
-        const float rr = Num<float>::reduce(u * (double)(2 * j + 1));
-        c = cospif(rr);
-        t = (float)M_PI * wn * (float)(2 * j + 1) * sinpif(rr);
+    const int jb = blockIdx.y;
+    for (int idx = threadIdx.x; idx < K * 4; idx += blockDim.x) {
+        const int k = idx >> 2, j = jb * 4 + (idx & 3);
+        float c = 0.f, t = 0.f;
+        if (j < n) {
+            const double u = (double)freqs[k] / (double)n;
+            const float wn = (float)(1.0 / (double)n);
+            const float rr = Num<float>::reduce(u * (double)(2 * j + 1));
+            c = cospif(rr);
+            t = (float)M_PI * wn * (float)(2 * j + 1) * sinpif(rr);
+        }
+        const int64_t at = ((int64_t)n * (FSW_FWD_TAB_LD / 4) + jb) * K * 4 + idx;
+        tab_c[at] = c;
+        tab_t[at] = t;
     }
-    const int64_t at = ((int64_t)k * (FSW_FWD_TAB_NMAX + 1) + n) * FSW_FWD_TAB_LD + j;
-    tab_c[at] = c;
-    tab_t[at] = t;
 }
 
 template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool LOCK>
@@ -473,16 +488,16 @@ int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_
 }  // namespace
 
 int fsw_build_fwd_tables(const float* freqs, int K, float* tab_c, float* tab_t, cudaStream_t st) {
-    static_assert(FSW_FWD_TAB_LD == 256 && FSW_FWD_TAB_NMAX <= FSW_FWD_TAB_LD, "one thread per table position");
+    static_assert(FSW_FWD_TAB_NMAX <= FSW_FWD_TAB_LD && FSW_FWD_TAB_LD % 4 == 0, "positions are blocked by 4");
     fsw_prof_begin("coef_tables", st);
-    fsw_build_fwd_tables_kernel<<<dim3(FSW_FWD_TAB_NMAX, K), FSW_FWD_TAB_LD, 0, st>>>(freqs, K, tab_c, tab_t);
+    fsw_build_fwd_tables_kernel<<<dim3(FSW_FWD_TAB_NMAX, FSW_FWD_TAB_LD / 4), 256, 0, st>>>(freqs, K, tab_c, tab_t);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_build_fwd_tables_kernel");
     return FSW_OK;
 }
 
-// uniform-weight fp32 segments order[lo, hi) with n <= np, np in {64, 128, 256}; gtab_c / gtab_t: slice-major
-// tables of fsw_build_fwd_tables ([k][n][FSW_FWD_TAB_LD], zero beyond position n-1)
+// uniform-weight fp32 segments order[lo, hi) with n <= np, np in {64, 128, 256}; gtab_c / gtab_t: tables of
+// fsw_build_fwd_tables
 int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0,
                          const float* bias, unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c,
                          const float* gtab_t, cudaStream_t st) {
