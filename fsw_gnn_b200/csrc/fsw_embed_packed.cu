@@ -1,24 +1,30 @@
-// K2, uniform-weight fp32 forward with the whole sort in registers: packed keys, L cooperating lanes per slice.
+// K2, uniform-weight fp32 forward for segments of 33..256 elements: the whole sort in registers, packed keys,
+// L cooperating lanes per slice.
 //
-//   fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>
-//     A (segment, slice) is sorted by L lanes of one warp holding R elements each (R * L slots; L = 1, 2, 4, 8;
-//     R = 32 when L > 1).  A warp therefore works on 32 / L consecutive slices of one segment.
+//   fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>     (R, L) = (16, 4) n <= 64, (16, 8) n <= 128, (16, 16) n <= 256
+//     A (segment, slice) is sorted by L lanes of one warp holding R elements each; a warp works on SW = 32 / L
+//     consecutive slices of one segment.
+//     * gather, row-wise: the SW slices of a source row are one aligned 16/32-byte piece, read by one or two
+//       lanes with a vector load (32 or 16 rows per instruction) and parked in shared memory as [element][slice].
 //     * packed keys: the network sorts ONE 32-bit word per element - the order-preserving integer image of the
 //       key with its low log2(R L) bits replaced by the element index.  A comparator is two integer min/max
 //       instructions instead of a compare and four selects, and no index array travels with the keys.
 //     * each lane sorts its R words with a merge-exchange network, then the lanes are merged with bitonic
-//       merges whose cross-lane steps are shuffles (static register indices) - the code stays small enough
-//       for the instruction cache and needs ~R registers, so occupancy is high (an earlier monolithic
-//       128-element network per thread stalled 70 % of its cycles on instruction fetch, profiles/r1).
-//     * the dropped low bits are restored exactly: the full keys stay in shared memory; adjacent sorted
-//       positions whose truncated keys coincide (min over XORs per block of positions, voted across the warp)
-//       are bubble-ordered by their full keys.  Equal full keys keep element order, as a stable sort would.
-//     * Fourier coefficients come from the global tables cos(pi xi (2j+1)/n) and d/dxi
-//       (fsw_build_coef_tables); the L partial sums of a slice are combined with shuffles.
-//     * SAVE_RANK: the slot of each consumed full key is overwritten by its sorted position and streamed out
-//       as uint16 rank[(e0+e), k] for the sort-free backward (fsw_embed_small.cu).
-#include <cstdlib>
-
+//       merges whose cross-lane steps are shuffles (static register indices).  The straight-line code of one
+//       segment stays below the 32 KB L1.5 instruction cache (R = 16: ~1500 instructions) - a monolithic
+//       128-element network per thread, and R = 32 variants, stalled most cycles on instruction fetch
+//       (profiles/r1/README.md).
+//     * the dropped low bits are restored exactly: adjacent sorted positions whose truncated keys coincide
+//       (min over XORs per block of 8 positions, voted across the warp) are bubble-ordered by their full keys
+//       from shared memory.  Equal full keys keep element order, as a stable sort would.  Padding slots get
+//       huge finite keys with pairwise different upper bits, so they sort last and never look like ties.
+//     * Fourier coefficients cos(pi xi (2j+1)/n) and their d/dxi companions come from global tables blocked as
+//       [n][position/4][slice][4] (fsw_build_fwd_tables): a lane reads its 16 positions as four float4s and the
+//       SW lanes of a run share cache lines.  Entries beyond n are zero, which also cancels the padding keys.
+//       The L partial sums of a slice are combined with shuffles.
+//     * SAVE_RANK: the slot of each consumed key is overwritten by its sorted position; the ranks leave row-wise,
+//       one vector store of SW uint16 per element, for the sort-free backward (fsw_embed_small.cu).
+//   Bound (ncu, profiles/r1): ALU pipe 66-74 % and L1 72-82 % busy at once; DRAM < 20 %.
 #include "fsw_sortnet.cuh"
 
 namespace {
@@ -136,8 +142,8 @@ __device__ __forceinline__ void fsw_store_ranks(unsigned short* dst, const int* 
         x = lo_;                 \
     }
 
-template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool LOCK>
-__global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)) fsw_coop_fwd_kernel(
+template <int R, int L, bool HAS_COL, bool SAVE_RANK>
+__global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
     SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks, float* __restrict__ out, int64_t ld_out, int64_t out_col0,
     const float* __restrict__ bias, unsigned short* __restrict__ ranks, int64_t ldr, float* __restrict__ dxi_out, int64_t ld_dxi,
     const float* __restrict__ gtab_c, const float* __restrict__ gtab_t) {
@@ -165,9 +171,8 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
     const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const int64_t item = wglobal / nchunks;
     const int chunk = (int)(wglobal - item * nchunks);
-    int64_t first64 = (int64_t)seg_lo + item * G;
-    if (!LOCK && first64 >= seg_hi) return;
-    if (first64 > seg_hi) first64 = seg_hi;  // LOCK: idle warps keep meeting the barriers of their group
+    const int64_t first64 = (int64_t)seg_lo + item * G;
+    if (first64 >= seg_hi) return;
     const int first = (int)first64;
     const int last = (int)((first64 + G < seg_hi) ? first64 + G : seg_hi);
     const int k0 = chunk * SW;  // the warp's slices k0 .. k0+SW-1 (inside the padded width: SW divides 8 | ldp, or ldp % SW == 0)
@@ -203,13 +208,7 @@ __global__ void __launch_bounds__(LOCK ? 512 : 128, LOCK ? 1 : (R <= 16 ? 8 : 5)
     const float* tt = ttk;
 
 #pragma unroll 1
-    for (int q = first; q < (LOCK ? first + G : last); ++q) {
-        if (LOCK) {
-            // the warps that share an SM sub-partition (warp id mod 4) walk the straight-line sort together, so one
-            // instruction fetch serves all of them
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"((int)blockDim.x / 4) : "memory");
-            if (q >= last) continue;
-        }
+    for (int q = first; q < last; ++q) {
         const int n = cur.n;
         // ---- gather, row-wise: LPR adjacent lanes read the SW slices of one row (one sector-aligned vector each), 32/LPR
         //      rows per instruction; the keys go to shared memory as [element][slice].  -0 becomes +0 (zeros tie, torch.sort compares
@@ -447,7 +446,7 @@ __global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* 
     }
 }
 
-template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool LOCK>
+template <int R, int L, bool HAS_COL, bool SAVE_RANK>
 int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0, const float* bias,
                     unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
                     cudaStream_t st) {
@@ -457,10 +456,10 @@ int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t
     if (G < 1) G = 1;
     if (G > 32) G = 32;
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
-    constexpr int WPB = LOCK ? 16 : 4;
+    constexpr int WPB = 4;
     const int64_t blocks = fsw_cdiv(warps, WPB);
     const size_t smem = (size_t)WPB * R * 32 * sizeof(float);
-    auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK, LOCK>;
+    auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const std::string label = std::string(SAVE_RANK ? "fwdr_coop_u" : "fwd_coop_u") + std::to_string(R * L) + "_f32";  // R x L slots
     fsw_prof_begin(label.c_str(), st);
@@ -475,14 +474,12 @@ int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_
                 unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
                 cudaStream_t st) {
     const bool has_col = a.col != nullptr;
-    static const bool lock = getenv("FSW_COOP_LOCK") != nullptr;
     if (ranks) {
-        if (has_col && lock) return launch_coop_fwd<R, L, true, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
-        return has_col ? launch_coop_fwd<R, L, true, true, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st)
-                       : launch_coop_fwd<R, L, false, true, false>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+        return has_col ? launch_coop_fwd<R, L, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st)
+                       : launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
     }
-    return has_col ? launch_coop_fwd<R, L, true, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st)
-                   : launch_coop_fwd<R, L, false, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st);
+    return has_col ? launch_coop_fwd<R, L, true, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st)
+                   : launch_coop_fwd<R, L, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st);
 }
 
 }  // namespace
@@ -504,13 +501,6 @@ int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float*
     if (gtab_c == nullptr) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: coefficient table missing");
 #define FSW_COOP_CASE(NP_, R_, L_) \
     case NP_: return launch_coop<R_, L_>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
-    static const bool r32 = getenv("FSW_COOP_R32") != nullptr;
-    if (r32) {
-        switch (np) {
-            FSW_COOP_CASE(128, 32, 4)
-            FSW_COOP_CASE(256, 32, 8)
-        }
-    }
     switch (np) {
         FSW_COOP_CASE(64, 16, 4)
         FSW_COOP_CASE(128, 16, 8)

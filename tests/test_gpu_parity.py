@@ -354,7 +354,7 @@ def test_plan_buckets():
 # ------------------------------------------------------------------------------------------------
 # CUDA path vs oracle on seeded random inputs (moderate sizes; all size classes incl. generic/scratch)
 # ------------------------------------------------------------------------------------------------
-def _random_graph_case(seed, N, degs, d, K, weighted, dtype, thresh=1.0):
+def _random_graph_case(seed, N, degs, d, K, weighted, dtype, thresh=1.0, X_override=None, theta_override=None, col_override=None):
     from fsw_gnn_b200 import FSW_embedding
     from fsw_gnn_b200.ops import SegmentPlan
     from oracle import fsw_oracle as O
@@ -362,12 +362,15 @@ def _random_graph_case(seed, N, degs, d, K, weighted, dtype, thresh=1.0):
     S = len(degs)
     rowptr = np.concatenate([[0], np.cumsum(degs)]).astype(np.int64)
     Etot = int(rowptr[-1])
-    col = rng.integers(0, N, Etot)
-    X = rng.standard_normal((N, d))
+    col = rng.integers(0, N, Etot) if col_override is None else col_override
+    X = rng.standard_normal((N, d)) if X_override is None else X_override
     W = (rng.random(Etot) + 0.1) if weighted else None
     torch.manual_seed(seed)
     mod = FSW_embedding(d_in=d, d_out=K, device=dev(), dtype=dtype, freqs_init="spread", learnable_slices=True, learnable_freqs=True,
                         total_mass_pad_thresh=thresh)
+    if theta_override is not None:
+        with torch.no_grad():
+            mod.projVecs.copy_(t(theta_override, dtype))
     theta = mod.projVecs.detach().cpu().numpy().astype(np.float64)
     xi = mod.freqs.detach().cpu().numpy().astype(np.float64)
     plan = SegmentPlan(S, Etot, torch.as_tensor(rowptr.astype(np.int32), device=dev()), 0,
@@ -394,6 +397,35 @@ def test_random_graph_vs_oracle(tag, weighted):
     np.testing.assert_allclose(dX, rb["dX"], **gtol(tag, rb["dX"]))
     np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), rb["dtheta"], **gtol(tag, rb["dtheta"]))
     np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], **gtol(tag, rb["dxi"]))
+
+
+@pytest.mark.parametrize("zeros", [False, True])
+def test_near_ties_exact_order(zeros):
+    """Keys that agree in all but their lowest mantissa bits, exact duplicates and signed zeros: the packed-key sort
+    (fsw_embed_packed.cu) must still deliver the exact stable order.  d = 1 and power-of-two slices make every
+    projection exact in fp32 and fp64, so the oracle's order is the only correct one; a swapped pair would move
+    dL/dX by ~1/n of its value."""
+    rng = np.random.default_rng(3)
+    N, K = 300, 37
+    degs = np.array([33, 40, 48, 49, 64, 65, 96, 100, 128, 129, 200, 255, 256, 7, 20, 300])
+    m = rng.integers(0, 48, N).astype(np.float64)
+    X = (1.0 + m * 2.0 ** -22)[:, None] * rng.choice([1.0, 2.0, 4.0], N)[:, None]   # clusters around 1, 2 and 4
+    if zeros:
+        X[rng.random(N) < 0.3] = 0.0
+        X[rng.random(N) < 0.1] = -0.0
+    theta = (rng.choice([-1.0, 1.0], K) * 2.0 ** -rng.integers(0, 4, K).astype(np.float64))[:, None]
+    out, ref, dX, rb, mod = _random_graph_case(17, N, degs, 1, K, False, torch.float32, X_override=X, theta_override=theta)
+    # sums of ~n terms of size 1..4 that cancel to ~0.1: fp32 accumulation noise, not order (a swapped near-tie
+    # would move the output by < 1e-8)
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
+    # Distinct nodes with EQUAL values may receive each other's share (the order of exact ties is unspecified in
+    # the reference too: torch.sort is not stable); the sum over a group of equal nodes is order-independent.
+    # Nodes whose values differ, however slightly, land in different groups: their order must be exact.
+    vals, group = np.unique(np.where(X[:, 0] == 0.0, 0.0, X[:, 0]), return_inverse=True)
+    got = np.zeros(len(vals)); want = np.zeros(len(vals))
+    np.add.at(got, group, dX[:, 0].astype(np.float64))
+    np.add.at(want, group, rb["dX"][:, 0])
+    np.testing.assert_allclose(got, want, **gtol("f32", want))
 
 
 def test_hub_segments_vs_oracle():
