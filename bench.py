@@ -112,9 +112,19 @@ def label_buckets(label):
         return [base + b for b in range(lo, size + 1)]
     if parts[1] == "rank" and size <= 64:
         return [base + b for b in range(0, size + 1)]
+    if parts[1] == "rankT":   # source-major rank backward: every uniform segment up to `size` elements
+        return [base + b for b in range(0, size + 1)]
     ranges = {64: (33, 64), 128: (65, 128), 256: (129, 256), 512: (257, 512), 1024: (513, 513), 2048: (514, 514), 4096: (515, 515)}
     lo, hi = ranges.get(size, (516, 516))
     return [base + b for b in range(lo, hi + 1)]
+
+
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from `ncu --set full` captures of one layer of
+# THIS workload at full size (profiles/r1/README.md names the report each number comes from); None = not captured.
+NCU_TRAFFIC_FULL_SCALE = {
+    "bwd_rankT_u512_f32": 99.0e9,   # profiles/r1/ncu_r1f_rankT_fullscale.txt: 86.2 GB for the 53.6M edges of segments <= 128,
+                                    # scaled to the 61.5M edges served since the limit went to 512 elements
+}
 
 
 def algorithmic_bytes(label, plan, K):
@@ -350,7 +360,9 @@ def main():
         bytes_per_launch = algorithmic_bytes(top, plan, K)
         ach = bytes_per_launch / (tot_ms / cnt * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                    "frac": ach / peaks["hbm_gbs"],
+                    "traffic": (NCU_TRAFFIC_FULL_SCALE.get(top) if (world == 1 and args.scale == 1.0) else None),
+                    "peak_source": peak_kind,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": tot_ms / cnt,
                     "share_of_step": (tot_ms / nprof) / ms_step}
         # the whole fused forward family (all size classes) for the north-star 70 % target

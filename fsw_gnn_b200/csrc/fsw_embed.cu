@@ -834,25 +834,30 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             if constexpr (sizeof(T) == 4) {
                 const size_t tb = fsw_rank_tables_bytes(a.ldp);
                 if (scratch_bytes < tb) return fsw_fail(FSW_ERR_WORKSPACE, "embed scratch too small for the rank tables");
-                const int lo0 = bo[base + 0], hi0 = bo[base + 128 + 1];
-                if (hi0 > lo0) {
-                    int rc;
-                    // the pre-scaled gradient GA [S, ldp] sits at the END of the scratch
-                    const size_t ga_bytes = (size_t)tr.S * a.ldp * sizeof(float);
-                    if (a.col != nullptr && tr.tptr != nullptr && dfreqs_cov == nullptr && scratch_bytes >= tb + ga_bytes + 256) {
-                        // graphs: source-major, one plain store per row of dXp (must precede every atomic kernel)
+                // the pre-scaled gradient GA [S, ldp] sits at the END of the scratch
+                const size_t ga_bytes = (size_t)tr.S * a.ldp * sizeof(float);
+                const bool source_major = a.col != nullptr && tr.tptr != nullptr && dfreqs_cov == nullptr && scratch_bytes >= tb + ga_bytes + 256;
+                if (source_major) {
+                    // graphs: every uniform segment up to FSW_RANKT_NMAX elements, one plain store per row of dXp
+                    // (must precede every kernel that adds with atomics)
+                    if (bo[base + FSW_RANKT_NMAX + 1] > bo[base + 0]) {
                         const size_t ga_off = (scratch_bytes - ga_bytes) & ~(size_t)255;  // keep 128-bit accesses aligned
                         float* ga_buf = (float*)((unsigned char*)scratch + ga_off);
                         scratch_bytes = ga_off;
-                        rc = fsw_rank_backward_T(a, tr.S, tr.nrows, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, ga_buf, st);
-                    } else
-                        rc = fsw_rank_backward_g128(a, lo0, hi0, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, scratch, st);
-                    if (rc) return rc;
+                        int rc = fsw_rank_backward_T(a, tr.S, tr.nrows, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, ga_buf, st);
+                        if (rc) return rc;
+                    }
+                } else {
+                    const int lo0 = bo[base + 0], hi0 = bo[base + 128 + 1];
+                    if (hi0 > lo0) {
+                        int rc = fsw_rank_backward_g128(a, lo0, hi0, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, scratch, st);
+                        if (rc) return rc;
+                    }
                 }
                 scratch = (unsigned char*)scratch + tb;
                 scratch_bytes -= tb;
                 struct { int lo, hi, cap; } rk[2] = {{129, 256, 256}, {257, 512, 512}};
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < 2 && !source_major; ++i) {
                     const int lo = bo[base + rk[i].lo], hi = bo[base + rk[i].hi + 1];
                     if (hi <= lo) continue;
                     int rc = fsw_rank_backward_u<T>(a, lo, hi, rk[i].cap, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, st);

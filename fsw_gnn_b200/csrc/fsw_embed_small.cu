@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float*
     const int n = blockIdx.x + 1;
     const float wn = (float)(1.0 / (double)n);
     const int64_t off = (int64_t)n * (n - 1) / 2;
-    for (int idx = threadIdx.x; idx < n * ldp; idx += blockDim.x) {
+    for (int idx = threadIdx.x; (tab_c || tab_t) && idx < n * ldp; idx += blockDim.x) {
         const int r = idx / ldp, k = idx - r * ldp;
         float c = 0.f, t = 0.f;
         if (k < K) {
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256) fsw_build_rank_tables_kernel(const float*
             c = cospif(rr);
             t = (float)M_PI * wn * (float)(2 * r + 1) * sinpif(rr);
         }
-        tab_c[(off + r) * ldp + k] = c;
+        if (tab_c) tab_c[(off + r) * ldp + k] = c;
         if (tab_t) tab_t[(off + r) * ldp + k] = t;
     }
     for (int k = threadIdx.x; k < ldp; k += blockDim.x) {
@@ -952,28 +952,30 @@ int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsign
                    : launch_rank_bwdg<false, false>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st);
 }
 
-// fp32 graphs: source-major rank backward over the transposed structure (eligible: uniform weights, n <= 128).
+// fp32 graphs: source-major rank backward over the transposed structure (eligible: uniform weights,
+// n <= FSW_RANKT_NMAX).
 // Writes EVERY row of dXp (plain stores); must run before the kernels that add with atomics.
 // `ga_buf` [S, ldp] floats is scratch for the pre-scaled upstream gradient.
 int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, const int32_t* tptr, const int32_t* tseg,
                         const int32_t* tslot, const int32_t* tn, const unsigned short* ranks, int64_t ldr, const float* g,
                         int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, void* tables, float* ga_buf, cudaStream_t st) {
     const int ldp = (int)a.ldp;
-    float* tab_c = (float*)tables;
-    float* tab_t = tab_c + FSW_GTAB_ROWS * ldp;
-    float* tab_A = tab_t + FSW_GTAB_ROWS * ldp;
-    float* tab_Ap = tab_A + (int64_t)FSW_GTAB_NMAX * ldp;
-    float2* tab_u = reinterpret_cast<float2*>(tab_Ap + (int64_t)FSW_GTAB_NMAX * ldp);
-    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_GTAB_NMAX, tab_c, nullptr, tab_A, tab_Ap, st, tab_u);
+    // only the amplitudes and xi/n are needed here, for n <= FSW_RANKT_NMAX: 4 * 512 * ldp floats, well inside
+    // fsw_rank_tables_bytes
+    static_assert(4 * FSW_RANKT_NMAX <= 2 * FSW_GTAB_ROWS, "source-major tables must fit the rank-table scratch");
+    float* tab_A = (float*)tables;
+    float* tab_Ap = tab_A + (int64_t)FSW_RANKT_NMAX * ldp;
+    float2* tab_u = reinterpret_cast<float2*>(tab_Ap + (int64_t)FSW_RANKT_NMAX * ldp);
+    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_RANKT_NMAX, nullptr, nullptr, tab_A, tab_Ap, st, tab_u);
     if (rc0) return rc0;
     fsw_prof_begin("bwd_scale_grad", st);
-    fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S * ldp, 256), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, FSW_GTAB_NMAX, ga_buf);
+    fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S * ldp, 256), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, FSW_RANKT_NMAX, ga_buf);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_scale_grad_kernel");
     const int nchunks = (a.K + 127) / 128;
     const int64_t warps = Nrows * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
-    fsw_prof_begin("bwd_rankT_u128_f32", st);
+    fsw_prof_begin("bwd_rankT_u512_f32", st);
     fsw_rank_bwdT_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_rank_bwdT_kernel");

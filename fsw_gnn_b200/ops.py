@@ -19,6 +19,9 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
+RANKT_NMAX = 512   # FSW_RANKT_NMAX (csrc/fsw_common.cuh): largest segment served by the source-major backward
+
+
 class SegmentPlan:
     """CSR description of a batch of weighted multisets + the launch plan of the fused kernels.
 
@@ -84,7 +87,7 @@ class SegmentPlan:
             tslot = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
             tn = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
             ws = _ws(lib.fsw_transpose_workspace_bytes(key), dev)
-            check(lib.fsw_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E, 128,
+            check(lib.fsw_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E, RANKT_NMAX,
                                         ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev)),
                   "fsw_csr_transpose")
             self._transpose = (key, tptr, tseg, tslot, tn)
