@@ -2,9 +2,10 @@
 
 Recipient rows of the adjacency are independent, so each rank owns a contiguous range of destination
 vertices chosen to hold an equal share of the EDGES, keeps the CSR rows / plan of that range only, and
-produces the output rows of that range.  The only exchange per layer is an all-gather of the layer's
-input features (NCCL over NVLink / NVSwitch); its adjoint in the backward pass is a reduce-scatter of the
-feature gradients; parameter gradients are all-reduced once per step.  Point-cloud batches need no
+produces the output rows of that range.  Each rank projects its own vertices onto the slices (K1), and the only
+exchange per layer is an all-gather of those PROJECTED rows (NCCL over NVLink / NVSwitch); its adjoint in the
+backward pass is a reduce-scatter of the projected gradient, after which the contractions dX, dtheta are local;
+parameter gradients are all-reduced once per step.  Point-cloud batches need no
 exchange at all (shard the batch dimension; see bench.py).
 
 One process per GPU; torch.distributed provides the communicator (backend nccl on GPUs, gloo in the
@@ -59,6 +60,40 @@ def all_gather_rows(x_local, max_rows, group=None):
     return _AllGatherRows.apply(x_local, group)
 
 
+class RowExchange:
+    """Exchange of PROJECTED rows around the fused kernels (ops.FSWEmbedFunction looks for `plan.exchange`).
+
+    Each rank projects only its own vertices (K1 scales with the number of GPUs instead of being replicated);
+    `gather` all-gathers the padded [max_rows, ldp] blocks into the [G * max_rows, ldp] matrix the re-indexed
+    sources point into, `scatter` is its adjoint: reduce-scatter (sum) of the gradient, cut back to the local rows."""
+
+    def __init__(self, max_rows, group=None):
+        self.max_rows = int(max_rows)
+        self.group = group
+
+    def gather(self, xp_local):
+        n = xp_local.shape[0]
+        G = dist.get_world_size(self.group)
+        if n < self.max_rows:
+            pad = torch.zeros((self.max_rows - n,) + tuple(xp_local.shape[1:]), dtype=xp_local.dtype, device=xp_local.device)
+            xp_local = torch.cat((xp_local, pad), dim=0)
+        out = torch.empty((G * self.max_rows,) + tuple(xp_local.shape[1:]), dtype=xp_local.dtype, device=xp_local.device)
+        dist.all_gather_into_tensor(out, xp_local.contiguous(), group=self.group)
+        return out
+
+    def scatter(self, g_all, n_local):
+        G = dist.get_world_size(self.group)
+        rows = g_all.shape[0] // G
+        g_all = g_all.contiguous()
+        if dist.get_backend(self.group) == "gloo":  # gloo has no reduce_scatter: all-reduce and keep our block
+            dist.all_reduce(g_all, group=self.group)
+            r = dist.get_rank(self.group)
+            return g_all[r * rows:r * rows + n_local].clone()
+        out = torch.empty((rows,) + tuple(g_all.shape[1:]), dtype=g_all.dtype, device=g_all.device)
+        dist.reduce_scatter_tensor(out, g_all, group=self.group)
+        return out[:n_local]
+
+
 class ShardedGraph:
     """This rank's share of a graph: destination rows [row_lo, row_hi) with all their in-edges."""
 
@@ -76,14 +111,14 @@ class ShardedGraph:
         self.num_edges = int(ei.shape[1])
         self.csr = _graph.GraphCSR(ei, self.n_local, 0, "unit", dtype)
         self.plan = self.csr.plan(thresh, dtype)
+        self.plan.exchange = RowExchange(self.max_rows, group)   # project locally, all-gather the projected rows
 
 
 def sharded_conv_forward(conv, x_local, sg):
     """One FSW_conv layer on this rank's destination rows (unit edge weights, no edge features)."""
     assert conv.edgefeat_dim == 0 and conv.edge_weighting == "unit" and not (conv.self_loop_weight > 0), \
         "the sharded path covers the default FSW_conv configuration (unit weights, no self loops / edge features)"
-    x_all = all_gather_rows(x_local, sg.max_rows, sg.group)
-    emb = conv.fsw_embed.embed_plan(x_all, sg.plan, None)
+    emb = conv.fsw_embed.embed_plan(x_local, sg.plan, None)   # the row exchange happens inside (plan.exchange)
     return conv._combine(emb, x_local)
 
 

@@ -188,6 +188,9 @@ class FSWEmbedFunction(torch.autograd.Function):
         X = X.contiguous()
         theta_x = projVecs[:, :d]
         Xp = project(X, theta_x, ldp)
+        exch = getattr(plan, "exchange", None)   # multi-GPU: X holds this rank's rows only (dist.RowExchange)
+        if exch is not None:
+            Xp = exch.gather(Xp)
         Ep = None
         if E_feat is not None:
             E_feat = E_feat.contiguous()
@@ -244,7 +247,8 @@ class FSWEmbedFunction(torch.autograd.Function):
         if need_scale and ctx.has_scale and tm_dim:
             dscale = (g[:, 0] * fT).sum()
         if (need_X or need_theta or need_xi or (need_E and ctx.has_E)) and K > 0 and plan.S > 0:
-            Nrows = X.shape[0]
+            exch = getattr(plan, "exchange", None)
+            Nrows = Xp.shape[0]   # rows the segments index (all ranks' rows when the projected rows were exchanged)
             # dXp is accumulated with atomics in graph mode -> must start from zero
             dXp = torch.zeros((Nrows, ldp), dtype=X.dtype, device=X.device) if plan.col is not None \
                 else torch.empty((Nrows, ldp), dtype=X.dtype, device=X.device)
@@ -262,6 +266,9 @@ class FSWEmbedFunction(torch.autograd.Function):
                 dxi = dxi_acc.to(X.dtype)
                 if dxi_fwd:
                     dxi = dxi + (g[:, tm_dim:tm_dim + K] * ctx.dxi_out).sum(dim=0)
+            if exch is not None:
+                dXp = exch.scatter(dXp, X.shape[0])   # sum over ranks, keep this rank's rows
+                Nrows = X.shape[0]
             if need_X:
                 dX = gemm(1, dXp, projVecs, Nrows, d, K, ldp, projVecs.stride(0))
             if need_theta:

@@ -61,6 +61,12 @@ def _worker(rank, world, port, q):
         (x_all * wgt).sum().backward()
         tot = sum(torch.arange(1, world * max_rows * d + 1, dtype=torch.float64).reshape(world * max_rows, d) * (r + 1) for r in range(world))
         assert torch.allclose(x_local.grad, tot[rank * max_rows: rank * max_rows + (hi - lo)])
+        # (3b) the non-autograd exchange used around the fused kernels (projected rows): gather layout and adjoint
+        ex = fdist.RowExchange(max_rows)
+        xp_all = ex.gather(X[lo:hi])
+        assert xp_all.shape[0] == world * max_rows and torch.equal(xp_all[col], X[ei[0]])
+        back = ex.scatter(wgt.clone(), hi - lo)
+        assert back.shape[0] == hi - lo and torch.allclose(back, tot[rank * max_rows: rank * max_rows + (hi - lo)])
         # (4) sharded embedding (oracle as the compute) == rows lo..hi of the single-process embedding
         theta = np.random.default_rng(1).standard_normal((K, d))
         theta /= np.linalg.norm(theta, axis=1, keepdims=True)
