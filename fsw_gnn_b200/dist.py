@@ -67,9 +67,10 @@ class RowExchange:
     `gather` all-gathers the padded [max_rows, ldp] blocks into the [G * max_rows, ldp] matrix the re-indexed
     sources point into, `scatter` is its adjoint: reduce-scatter (sum) of the gradient, cut back to the local rows."""
 
-    def __init__(self, max_rows, group=None):
+    def __init__(self, max_rows, group=None, chunks=4):
         self.max_rows = int(max_rows)
         self.group = group
+        self.chunks = int(chunks)   # column chunks of the slices: exchange of one runs under the kernels of another
 
     def gather(self, xp_local):
         n = xp_local.shape[0]
@@ -80,6 +81,31 @@ class RowExchange:
         out = torch.empty((G * self.max_rows,) + tuple(xp_local.shape[1:]), dtype=xp_local.dtype, device=xp_local.device)
         dist.all_gather_into_tensor(out, xp_local.contiguous(), group=self.group)
         return out
+
+    def gather_async(self, xp_local):
+        """-> (gathered [G * max_rows, ld], work): the collective runs on NCCL's stream after everything queued so far
+        on the current stream; `work.wait()` makes the current stream wait for it."""
+        n = xp_local.shape[0]
+        G = dist.get_world_size(self.group)
+        if n < self.max_rows:
+            pad = torch.zeros((self.max_rows - n,) + tuple(xp_local.shape[1:]), dtype=xp_local.dtype, device=xp_local.device)
+            xp_local = torch.cat((xp_local, pad), dim=0)
+        out = torch.empty((G * self.max_rows,) + tuple(xp_local.shape[1:]), dtype=xp_local.dtype, device=xp_local.device)
+        work = dist.all_gather_into_tensor(out, xp_local.contiguous(), group=self.group, async_op=True)
+        return out, work
+
+    def scatter_async(self, g_all, n_local):
+        """-> (summed block [max_rows, ld] (valid after work.wait(); take [:n_local]), work)"""
+        G = dist.get_world_size(self.group)
+        rows = g_all.shape[0] // G
+        g_all = g_all.contiguous()
+        if dist.get_backend(self.group) == "gloo":  # gloo has no reduce_scatter: all-reduce and keep our block
+            work = dist.all_reduce(g_all, group=self.group, async_op=True)
+            r = dist.get_rank(self.group)
+            return g_all[r * rows:(r + 1) * rows], work
+        out = torch.empty((rows,) + tuple(g_all.shape[1:]), dtype=g_all.dtype, device=g_all.device)
+        work = dist.reduce_scatter_tensor(out, g_all, group=self.group, async_op=True)
+        return out, work
 
     def scatter(self, g_all, n_local):
         G = dist.get_world_size(self.group)

@@ -184,43 +184,59 @@ class FSWEmbedFunction(torch.autograd.Function):
         K = projVecs.shape[0]
         tm_dim = 0 if tm_function is None else 1
         d_out = K + tm_dim
-        ldp = round_up(max(K, 1), 8)
         X = X.contiguous()
-        theta_x = projVecs[:, :d]
-        Xp = project(X, theta_x, ldp)
-        exch = getattr(plan, "exchange", None)   # multi-GPU: X holds this rank's rows only (dist.RowExchange)
-        if exch is not None:
-            Xp = exch.gather(Xp)
-        Ep = None
-        if E_feat is not None:
-            E_feat = E_feat.contiguous()
-            Ep = project(E_feat, projVecs[:, d:], ldp)
+        freqs = freqs.contiguous()
+        # Multi-GPU (dist.RowExchange on the plan): X holds this rank's rows only.  The slices are cut into column
+        # chunks; every chunk is projected locally, all-gathered asynchronously, and embedded as soon as its rows
+        # have arrived - the exchange of chunk c+1 runs under the kernels of chunk c.  Single GPU: one chunk.
+        exch = getattr(plan, "exchange", None)
+        nchunk = exch.chunks if (exch is not None and E_feat is None) else 1
+        bounds = column_chunks(K, nchunk)
         out = torch.empty((plan.S, d_out), dtype=X.dtype, device=X.device)
         bias_core = None
         if bias is not None:
             bias = bias.contiguous()
             bias_core = bias[tm_dim:]
-        # training: record each element's sorted position per slice (uint16) so that the backward needs no sort.
-        # 2 bytes per (element, slice); skipped when that would not fit comfortably (then the backward re-sorts).
-        ranks = None
         needs_grad = any(ctx.needs_input_grad[:6])
-        if needs_grad and SAVE_RANKS and plan.E > 0 and K > 0:
-            nbytes = plan.E * ldp * 2
-            ok = nbytes < (256 << 20)  # small buffers never need the (slow) driver query
-            if not ok:
-                free_b, _total = torch.cuda.mem_get_info(X.device)
-                # blocks cached by torch's allocator are free for us too
-                free_b += torch.cuda.memory_reserved(X.device) - torch.cuda.memory_allocated(X.device)
-                ok = nbytes < RANK_MEMORY_FRACTION * free_b
-            if ok:
-                ranks = torch.empty((plan.E, ldp), dtype=torch.int16, device=X.device)
-        # with learnable frequencies the forward also emits d out / d xi per (segment, slice)
-        dxi_out = None
-        if ranks is not None and ctx.needs_input_grad[2]:
-            dxi_out = torch.zeros((plan.S, K), dtype=X.dtype, device=X.device)
-        embed_forward(plan, Xp, ldp, Ep, freqs.contiguous(), out, d_out, tm_dim, bias_core, ranks, dxi_out)
-        ctx.ranks = ranks
-        ctx.dxi_out = dxi_out
+        Ep = None
+        if E_feat is not None:
+            E_feat = E_feat.contiguous()
+        chunks = []
+        for (k0, k1) in bounds:
+            ldc = round_up(max(k1 - k0, 1), 8)
+            xp = project(X, projVecs[k0:k1, :d], ldc)
+            work = None
+            if exch is not None:
+                xp, work = exch.gather_async(xp)
+            chunks.append([k0, k1, ldc, xp, work, None, None])
+        for ch in chunks:
+            k0, k1, ldc, xp, work = ch[:5]
+            if work is not None:
+                work.wait()   # the compute stream waits for this chunk's rows only
+                ch[4] = None
+            if E_feat is not None:
+                Ep = project(E_feat, projVecs[k0:k1, d:], ldc)
+            # training: record each element's sorted position per slice (uint16) so that the backward needs no sort.
+            # 2 bytes per (element, slice); skipped when that would not fit comfortably (then the backward re-sorts).
+            ranks = None
+            if needs_grad and SAVE_RANKS and plan.E > 0 and k1 > k0:
+                nbytes = plan.E * ldc * 2
+                ok = nbytes < (256 << 20)  # small buffers never need the (slow) driver query
+                if not ok:
+                    free_b, _total = torch.cuda.mem_get_info(X.device)
+                    # blocks cached by torch's allocator are free for us too
+                    free_b += torch.cuda.memory_reserved(X.device) - torch.cuda.memory_allocated(X.device)
+                    ok = nbytes < RANK_MEMORY_FRACTION * free_b
+                if ok:
+                    ranks = torch.empty((plan.E, ldc), dtype=torch.int16, device=X.device)
+            # with learnable frequencies the forward also emits d out / d xi per (segment, slice)
+            dxi_out = None
+            if ranks is not None and ctx.needs_input_grad[2]:
+                dxi_out = torch.zeros((plan.S, k1 - k0), dtype=X.dtype, device=X.device)
+            embed_forward(plan, xp, ldc, Ep, freqs[k0:k1], out, d_out, tm_dim + k0,
+                          None if bias_core is None else bias_core[k0:k1], ranks, dxi_out)
+            ch[5], ch[6] = ranks, dxi_out
+        ctx.chunks = [(k0, k1, ldc, xp, ranks, dxi) for (k0, k1, ldc, xp, _w, ranks, dxi) in chunks]
         fT = None
         if tm_dim:
             fT = total_mass_function(plan.mass_as(X.dtype), tm_function)
@@ -228,15 +244,16 @@ class FSWEmbedFunction(torch.autograd.Function):
             if bias is not None:
                 col0 = col0 + bias[0]
             out[:, 0] = col0
-        ctx.plan, ctx.ldp, ctx.tm_dim = plan, ldp, tm_dim
+        ctx.plan, ctx.tm_dim = plan, tm_dim
         ctx.has_E, ctx.has_bias, ctx.has_scale = E_feat is not None, bias is not None, tm_scale is not None
-        ctx.save_for_backward(X, projVecs, freqs, Xp, Ep, E_feat, fT)
+        ctx.Ep = Ep   # only with edge features (then there is a single chunk)
+        ctx.save_for_backward(X, projVecs, freqs, E_feat, fT)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        X, projVecs, freqs, Xp, Ep, E_feat, fT = ctx.saved_tensors
-        plan, ldp, tm_dim = ctx.plan, ctx.ldp, ctx.tm_dim
+        X, projVecs, freqs, E_feat, fT = ctx.saved_tensors
+        plan, tm_dim = ctx.plan, ctx.tm_dim
         need_X, need_theta, need_xi, need_bias, need_scale, need_E = ctx.needs_input_grad[:6]
         d = X.shape[1]
         K = projVecs.shape[0]
@@ -248,39 +265,56 @@ class FSWEmbedFunction(torch.autograd.Function):
             dscale = (g[:, 0] * fT).sum()
         if (need_X or need_theta or need_xi or (need_E and ctx.has_E)) and K > 0 and plan.S > 0:
             exch = getattr(plan, "exchange", None)
-            Nrows = Xp.shape[0]   # rows the segments index (all ranks' rows when the projected rows were exchanged)
-            # dXp is accumulated with atomics in graph mode -> must start from zero
-            dXp = torch.zeros((Nrows, ldp), dtype=X.dtype, device=X.device) if plan.col is not None \
-                else torch.empty((Nrows, ldp), dtype=X.dtype, device=X.device)
-            if plan.col is None and ldp != K:
-                dXp.zero_()
-            dEp = torch.zeros((plan.E, ldp), dtype=X.dtype, device=X.device) if ctx.has_E else None
-            dxi_acc = torch.zeros(K, dtype=torch.float64, device=X.device) if need_xi else None
-            dxi_fwd = ctx.dxi_out is not None
-            transpose = None
-            if ctx.ranks is not None and X.dtype == torch.float32 and plan.col is not None and (dxi_fwd or not need_xi):
-                transpose = plan.transpose(Nrows)
-            embed_backward(plan, Xp, ldp, Ep, freqs.contiguous(), g, g.shape[1], tm_dim, dXp, dEp, dxi_acc, ctx.ranks,
-                           dxi_from_forward=(dxi_fwd or not need_xi), transpose=transpose, nrows=Nrows)
+            n_local = X.shape[0]
             if need_xi:
-                dxi = dxi_acc.to(X.dtype)
-                if dxi_fwd:
-                    dxi = dxi + (g[:, tm_dim:tm_dim + K] * ctx.dxi_out).sum(dim=0)
-            if exch is not None:
-                dXp = exch.scatter(dXp, X.shape[0])   # sum over ranks, keep this rank's rows
-                Nrows = X.shape[0]
-            if need_X:
-                dX = gemm(1, dXp, projVecs, Nrows, d, K, ldp, projVecs.stride(0))
+                dxi = torch.empty(K, dtype=X.dtype, device=X.device)
+            done = []
+            for (k0, k1, ldc, Xp, ranks, dxi_out) in ctx.chunks:
+                Nrows = Xp.shape[0]   # rows the segments index (all ranks' rows when the projected rows were exchanged)
+                # dXp is accumulated with atomics in graph mode -> must start from zero
+                dXp = torch.zeros((Nrows, ldc), dtype=X.dtype, device=X.device) if plan.col is not None \
+                    else torch.empty((Nrows, ldc), dtype=X.dtype, device=X.device)
+                if plan.col is None and ldc != k1 - k0:
+                    dXp.zero_()
+                dEp = torch.zeros((plan.E, ldc), dtype=X.dtype, device=X.device) if ctx.has_E else None
+                dxi_acc = torch.zeros(k1 - k0, dtype=torch.float64, device=X.device) if need_xi else None
+                dxi_fwd = dxi_out is not None
+                transpose = None
+                if ranks is not None and X.dtype == torch.float32 and plan.col is not None and (dxi_fwd or not need_xi):
+                    transpose = plan.transpose(Nrows)
+                embed_backward(plan, Xp, ldc, ctx.Ep, freqs[k0:k1], g, g.shape[1], tm_dim + k0, dXp, dEp, dxi_acc, ranks,
+                               dxi_from_forward=(dxi_fwd or not need_xi), transpose=transpose, nrows=Nrows)
+                if need_xi:
+                    dxi_c = dxi_acc.to(X.dtype)
+                    if dxi_fwd:
+                        dxi_c = dxi_c + (g[:, tm_dim + k0:tm_dim + k1] * dxi_out).sum(dim=0)
+                    dxi[k0:k1] = dxi_c
+                work = None
+                if exch is not None:
+                    # sum over ranks, keep this rank's rows: runs under the next chunk's kernels
+                    dXp, work = exch.scatter_async(dXp, n_local)
+                done.append((k0, k1, ldc, dXp, dEp, work))
             if need_theta:
                 dtheta = torch.zeros_like(projVecs)
-                gemm(2, dXp, X, K, d, Nrows, ldp, X.stride(0), out=dtheta, ldc=dtheta.stride(0), accumulate=True)
-            if ctx.has_E:
-                de = E_feat.shape[1]
-                if need_E:
-                    dE = gemm(1, dEp, projVecs[:, d:], plan.E, de, K, ldp, projVecs.stride(0))
+            for i, (k0, k1, ldc, dXp, dEp, work) in enumerate(done):
+                if work is not None:
+                    work.wait()
+                    dXp = dXp[:n_local]
+                kc = k1 - k0
+                if need_X:
+                    if i == 0:
+                        dX = gemm(1, dXp, projVecs[k0:k1], n_local, d, kc, ldc, projVecs.stride(0))
+                    else:
+                        gemm(1, dXp, projVecs[k0:k1], n_local, d, kc, ldc, projVecs.stride(0), out=dX, ldc=dX.stride(0), accumulate=True)
                 if need_theta:
-                    gemm(2, dEp, E_feat, K, de, plan.E, ldp, E_feat.stride(0), out=dtheta[:, d:], ldc=dtheta.stride(0),
-                         accumulate=True)
+                    gemm(2, dXp, X, kc, d, n_local, ldc, X.stride(0), out=dtheta[k0:k1], ldc=dtheta.stride(0), accumulate=True)
+                if ctx.has_E:
+                    de = E_feat.shape[1]
+                    if need_E:
+                        dE = gemm(1, dEp, projVecs[k0:k1, d:], plan.E, de, kc, ldc, projVecs.stride(0))
+                    if need_theta:
+                        gemm(2, dEp, E_feat, kc, de, plan.E, ldc, E_feat.stride(0), out=dtheta[k0:k1, d:], ldc=dtheta.stride(0),
+                             accumulate=True)
         else:
             if need_X:
                 dX = torch.zeros_like(X)
@@ -289,6 +323,18 @@ class FSWEmbedFunction(torch.autograd.Function):
             if need_xi:
                 dxi = torch.zeros_like(freqs)
         return dX, dtheta, dxi, dbias, dscale, dE, None, None
+
+
+def column_chunks(K, n):
+    """[k0, k1) column ranges: n chunks of equal width rounded up to 8 columns (fewer when K is small)."""
+    n = max(1, min(int(n), (K + 7) // 8 if K > 0 else 1))
+    w = round_up(-(-K // n), 8) if K > 0 else 0
+    out = []
+    k0 = 0
+    while k0 < K:
+        out.append((k0, min(k0 + w, K)))
+        k0 += w
+    return out or [(0, 0)]
 
 
 def fsw_embed(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function):
