@@ -67,10 +67,13 @@ class RowExchange:
     `gather` all-gathers the padded [max_rows, ldp] blocks into the [G * max_rows, ldp] matrix the re-indexed
     sources point into, `scatter` is its adjoint: reduce-scatter (sum) of the gradient, cut back to the local rows."""
 
-    def __init__(self, max_rows, group=None, chunks=4):
+    def __init__(self, max_rows, group=None, chunks=1):
         self.max_rows = int(max_rows)
         self.group = group
-        self.chunks = int(chunks)   # column chunks of the slices: exchange of one runs under the kernels of another
+        # column chunks of the slices: with > 1 the exchange of one chunk runs under the kernels of another.  Measured
+        # on 8 B200s (profiles/r1/README.md): 84 ms/step with 1 chunk, 92 with 2, 122 with 4 - the concurrent NCCL
+        # kernels slow the sort kernels down by more than the overlap hides, and narrow chunks waste lanes.
+        self.chunks = int(chunks)
 
     def gather(self, xp_local):
         n = xp_local.shape[0]

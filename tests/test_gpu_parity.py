@@ -428,6 +428,53 @@ def test_near_ties_exact_order(zeros):
     np.testing.assert_allclose(got, want, **gtol("f32", want))
 
 
+class _LocalExchange:
+    """Stand-in for dist.RowExchange on one GPU: same chunked call sequence, no communication."""
+    def __init__(self, chunks):
+        self.chunks = chunks
+
+    def gather_async(self, xp):
+        return xp, None
+
+    def scatter_async(self, g, n_local):
+        return g, None
+
+
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_column_chunked_calls_equal_single_call(chunks):
+    """The multi-GPU path cuts the slices into column chunks (one embed call per chunk, exchange overlapped):
+    values and gradients must not depend on the cut."""
+    from fsw_gnn_b200 import FSW_conv
+    from fsw_gnn_b200.graph import cached_graph
+    torch.manual_seed(2)
+    N, d = 3000, 24
+    rng = np.random.default_rng(4)
+    deg = np.clip(np.round(np.exp(2.0 + rng.standard_normal(N))), 1, 700).astype(np.int64)
+    dst = np.repeat(np.arange(N), deg)
+    src = rng.integers(0, N, dst.size)
+    ei = torch.as_tensor(np.stack([src, dst]), device=dev())
+    conv = FSW_conv(d, d, device=dev())
+    X = torch.randn(N, d, device=dev())
+    res = []
+    for c in (1, chunks):
+        plan = cached_graph(ei, N, 0, "unit", 1.0, torch.float32)[1]
+        if c > 1:
+            plan.exchange = _LocalExchange(c)
+        x = X.clone().requires_grad_(True)
+        for p in conv.parameters():
+            p.grad = None
+        out = conv(x, ei)
+        out.square().sum().backward()
+        res.append((out.detach().clone(), x.grad.clone(), [p.grad.clone() for p in conv.parameters() if p.grad is not None]))
+        if c > 1:
+            del plan.exchange
+    (o1, g1, p1), (o2, g2, p2) = res
+    torch.testing.assert_close(o2, o1, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(g2, g1, rtol=1e-5, atol=1e-5 * float(g1.abs().max()))
+    for a, b in zip(p2, p1):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()) + 1e-7)
+
+
 def test_hub_segments_vs_oracle():
     """very large segments (global-scratch merge path; > 32768 elements switches the payload to int32)"""
     degs = np.array([3, 5000, 40000, 17, 700])
