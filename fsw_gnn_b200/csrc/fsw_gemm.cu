@@ -4,7 +4,8 @@
 //   op 2 (TN)  dtheta += dXp^T . X         autograd of :911 w.r.t. projVecs (split over the long N axis)
 //
 // The reference runs these as cuBLAS SGEMM with TF32 off, so the contraction must be true fp32:
-// this is a register-tiled SIMT kernel (128x64x16 CTA tile, 8x4 per thread, k-major shared tiles).
+// register-tiled SIMT kernels: a full-width strip kernel for the shapes of the path (small dimension <= 200, fp32)
+// and a generic 128x64x16 kernel for everything else (fp64, odd strides).
 // A tcgen05 3xTF32 variant for large d_in is future work.
 #include "fsw_common.cuh"
 
@@ -101,6 +102,229 @@ __global__ void __launch_bounds__(256) fsw_gemm_kernel(int64_t M, int64_t N, int
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 strip kernel: the CTA tile spans the WHOLE small dimension N (N <= 8 CG, CG = 13 or 25 column groups), so the
+// long operand is read from HBM exactly once and nothing is wasted on padding N to a power of two (N = 199 slices or
+// 100 features would lose 22 % in 128-wide tiles).  RG x CG threads own 8 x 8 outputs each (columns split 4 + 4 so that
+// the 128-bit shared loads of a quarter warp touch 32 distinct banks), k-major shared tiles, register-prefetch double
+// buffering: the loads of step i+1 are in flight while step i is multiplied.
+//   AMODE / BMODE 0: element (r, k) at r * ld + k (rows of length Kd; read as float4 along k, transposed on the way in)
+//                 1: element (r, k) at k * ld + r (float4 along r)
+// Requirements (checked by the dispatcher): ld % 4 == 0, 16-byte aligned bases (split boundaries are multiples of 16).
+// ---------------------------------------------------------------------------------------------------
+constexpr int SBK = 16;
+
+template <int RG, int CG>
+struct StripCfg {
+    static constexpr int BMs = 8 * RG, BNs = 8 * CG;
+    static constexpr int NTHR = ((RG * CG + 31) / 32) * 32;
+    static constexpr int LDA = BMs + 4, LDB = BNs + 4;
+    static constexpr int UA = BMs * SBK / 4, UB = BNs * SBK / 4;  // float4 units per k-step
+    static constexpr int PA = (UA + NTHR - 1) / NTHR, PB = (UB + NTHR - 1) / NTHR;
+};
+
+// one float4 unit of a [ROWS x SBK] tile: mode 0 -> (r, 4 consecutive k), mode 1 -> (4 consecutive r, k)
+template <int MODE, int ROWS>
+__device__ __forceinline__ float4 fsw_strip_load(const float* __restrict__ P, int64_t ld, int64_t r0, int64_t R, int64_t k0,
+                                                 int64_t kend, int u) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 0) {
+        const int r = u % ROWS, kq = u / ROWS;
+        const int64_t gr = r0 + r, gk = k0 + kq * 4;
+        if (gr < R && gk < kend) {
+            const float* p = P + gr * ld + gk;
+            if (gk + 3 < kend) {
+                v = __ldg(reinterpret_cast<const float4*>(p));
+            } else {  // tail of a row whose length is not a multiple of 4
+                v.x = __ldg(p);
+                if (gk + 1 < kend) v.y = __ldg(p + 1);
+                if (gk + 2 < kend) v.z = __ldg(p + 2);
+            }
+        }
+    } else {
+        const int rq = u % (ROWS / 4), k = u / (ROWS / 4);
+        const int64_t gr = r0 + rq * 4, gk = k0 + k;
+        if (gk < kend && gr < R) {
+            const float* p = P + gk * ld + gr;
+            if (gr + 3 < R) {
+                v = __ldg(reinterpret_cast<const float4*>(p));
+            } else {
+                v.x = __ldg(p);
+                if (gr + 1 < R) v.y = __ldg(p + 1);
+                if (gr + 2 < R) v.z = __ldg(p + 2);
+            }
+        }
+    }
+    return v;
+}
+
+template <int MODE, int ROWS, int LD>
+__device__ __forceinline__ void fsw_strip_store(float* __restrict__ S, int u, float4 v) {
+    if (MODE == 0) {
+        const int r = u % ROWS, kq = u / ROWS;
+        S[(kq * 4 + 0) * LD + r] = v.x;
+        S[(kq * 4 + 1) * LD + r] = v.y;
+        S[(kq * 4 + 2) * LD + r] = v.z;
+        S[(kq * 4 + 3) * LD + r] = v.w;
+    } else {
+        const int rq = u % (ROWS / 4), k = u / (ROWS / 4);
+        *reinterpret_cast<float4*>(S + k * LD + rq * 4) = v;
+    }
+}
+
+template <int RG, int CG, int AMODE, int BMODE>
+__global__ void __launch_bounds__(StripCfg<RG, CG>::NTHR, StripCfg<RG, CG>::NTHR <= 256 ? 2 : 1) fsw_gemm_strip_kernel(int64_t M, int64_t N, int64_t Kd, const float* __restrict__ A,
+                                                                                int64_t lda, const float* __restrict__ B, int64_t ldb,
+                                                                                float* __restrict__ C, int64_t ldc, int accumulate,
+                                                                                int64_t k_per_split, int use_atomics) {
+    using Cfg = StripCfg<RG, CG>;
+    constexpr int BMs = Cfg::BMs, BNs = Cfg::BNs, NTHR = Cfg::NTHR, LDA = Cfg::LDA, LDB = Cfg::LDB;
+    __shared__ __align__(16) float As[2][SBK * LDA];
+    __shared__ __align__(16) float Bs[2][SBK * LDB];
+    const int tid = threadIdx.x;
+    const bool worker = tid < RG * CG;
+    const int rg = worker ? tid / CG : 0, cg = worker ? tid % CG : 0;
+    const int64_t m0 = (int64_t)blockIdx.x * BMs;
+    const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
+    const int64_t kend = (kbeg + k_per_split < Kd) ? kbeg + k_per_split : Kd;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 pa[Cfg::PA], pb[Cfg::PB];
+    auto load_tiles = [&](int64_t k0) {
+#pragma unroll
+        for (int p = 0; p < Cfg::PA; ++p) {
+            const int u = tid + p * NTHR;
+            pa[p] = (u < Cfg::UA) ? fsw_strip_load<AMODE, BMs>(A, lda, m0, M, k0, kend, u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int p = 0; p < Cfg::PB; ++p) {
+            const int u = tid + p * NTHR;
+            pb[p] = (u < Cfg::UB) ? fsw_strip_load<BMODE, BNs>(B, ldb, 0, N, k0, kend, u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int p = 0; p < Cfg::PA; ++p) {
+            const int u = tid + p * NTHR;
+            if (u < Cfg::UA) fsw_strip_store<AMODE, BMs, LDA>(As[buf], u, pa[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < Cfg::PB; ++p) {
+            const int u = tid + p * NTHR;
+            if (u < Cfg::UB) fsw_strip_store<BMODE, BNs, LDB>(Bs[buf], u, pb[p]);
+        }
+    };
+
+    load_tiles(kbeg);
+    store_tiles(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t k0 = kbeg; k0 < kend; k0 += SBK) {
+        const bool more = k0 + SBK < kend;
+        if (more) load_tiles(k0 + SBK);  // in flight during the multiply below
+        if (worker) {
+            const float* as = As[buf] + rg * 8;
+            const float* bs = Bs[buf] + cg * 4;
+#pragma unroll
+            for (int k = 0; k < SBK; ++k) {
+                const float4 a0 = *reinterpret_cast<const float4*>(as + k * LDA);
+                const float4 a1 = *reinterpret_cast<const float4*>(as + k * LDA + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(bs + k * LDB);
+                const float4 b1 = *reinterpret_cast<const float4*>(bs + k * LDB + BNs / 2);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        }
+        if (more) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    if (!worker) return;
+    // thread's columns: cg*4 .. +3 and BNs/2 + cg*4 .. +3
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t gm = m0 + rg * 8 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t gn = (int64_t)h * (BNs / 2) + cg * 4;
+            float* c = C + gm * ldc + gn;
+            const float v[4] = {acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]};
+            if (!use_atomics && !accumulate && gn + 3 < N && ((ldc & 3) == 0)) {
+                *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (gn + j >= N) continue;
+                    if (use_atomics)
+                        atomicAdd(c + j, v[j]);
+                    else if (accumulate)
+                        c[j] += v[j];
+                    else
+                        c[j] = v[j];
+                }
+            }
+        }
+    }
+}
+
+template <int RG, int CG, int AMODE, int BMODE>
+int launch_strip(int op, int64_t M, int64_t N, int64_t Kd, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                 int64_t ldc, int accumulate, cudaStream_t st) {
+    using Cfg = StripCfg<RG, CG>;
+    const int64_t mt = fsw_cdiv(M, Cfg::BMs);
+    int64_t splits = 1;
+    if (op == 2) {  // split the long reduction axis so that the grid fills the machine
+        splits = (148 * 2 + mt - 1) / mt;
+        const int64_t max_splits = fsw_cdiv(Kd, 8 * SBK);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    int64_t k_per_split = fsw_cdiv(fsw_cdiv(Kd, splits), SBK) * SBK;
+    splits = fsw_cdiv(Kd, k_per_split);
+    dim3 grid((unsigned)mt, 1, (unsigned)splits);
+    static const char* labels[3] = {"gemm_nt", "gemm_nn", "gemm_tn"};
+    fsw_prof_begin(labels[op], st);
+    fsw_gemm_strip_kernel<RG, CG, AMODE, BMODE><<<grid, Cfg::NTHR, 0, st>>>(M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, k_per_split,
+                                                                         op == 2 ? 1 : 0);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_gemm_strip_kernel");
+    return FSW_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// returns -1 when the shape / alignment is not covered (the generic kernel takes over)
+int gemm_strip_f32(int op, int64_t M, int64_t N, int64_t Kd, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                   int64_t ldc, int accumulate, cudaStream_t st) {
+    if (N > 200 || Kd < 16 || !aligned16(A) || !aligned16(B) || !aligned16(C) || (lda & 3) || (ldb & 3)) return -1;
+    const bool wide = N > 104;
+    switch (op) {
+        case 0:
+            return wide ? launch_strip<10, 25, 0, 0>(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st)
+                        : launch_strip<16, 13, 0, 0>(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 1:
+            return wide ? launch_strip<10, 25, 0, 1>(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st)
+                        : launch_strip<16, 13, 0, 1>(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 2:
+            if (M > 200 || wide) return -1;
+            return launch_strip<25, 13, 1, 1>(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+    }
+    return -1;
+}
+
 // Small-d projection (d_in <= 8, e.g. 3-d point clouds): memory bound on the Xp write.  One thread
 // produces 4 consecutive slices of one row; theta is read through the read-only cache.
 template <typename T, int D>
@@ -157,6 +381,10 @@ int gemm_t(int op, int64_t M, int64_t N, int64_t Kd, const T* A, int64_t lda, co
         fsw_prof_end(st);
         FSW_CHECK_LAUNCH("fsw_project_small_kernel");
         return FSW_OK;
+    }
+    if constexpr (sizeof(T) == 4) {
+        const int rc = gemm_strip_f32(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        if (rc >= 0) return rc;
     }
     int64_t splits = 1;
     if (op == 2) {

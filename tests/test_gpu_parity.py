@@ -428,6 +428,36 @@ def test_near_ties_exact_order(zeros):
     np.testing.assert_allclose(got, want, **gtol("f32", want))
 
 
+@pytest.mark.parametrize("shape", [(1000, 199, 100), (777, 100, 200), (130, 37, 16), (4097, 104, 48), (300, 200, 64), (515, 61, 52)])
+def test_gemm_strip_kernels_vs_fp64(shape):
+    """K1 full-width strip kernels (fp32, small dimension <= 200): X.theta^T, dXp.theta and dXp^T.X against fp64
+    matmul of the same fp32 inputs.  Tolerance 2e-6 relative to the largest output (fp32 FMA accumulation)."""
+    from fsw_gnn_b200 import ops
+    M, N, Kd = shape
+    g = torch.Generator(device=dev()); g.manual_seed(M + N)
+    A = torch.randn(M, Kd, device=dev(), generator=g)
+    B = torch.randn(N, Kd, device=dev(), generator=g)
+    ldc = (N + 7) // 8 * 8
+    C = torch.full((M, ldc), 7.0, device=dev())
+    ops.gemm(0, A, B, M, N, Kd, Kd, Kd, out=C, ldc=ldc)
+    ref = A.double() @ B.double().T
+    assert float((C[:, :N].double() - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    assert bool((C[:, N:] == 7.0).all())                       # padding columns untouched
+    # NN: [M, N] x [N, Kd'] with the padded leading dimension, then accumulate a second time
+    Bn = torch.randn(N, Kd, device=dev(), generator=g)         # [Kd_nn = N, N_nn = Kd]
+    Cp = torch.zeros(M, ldc, device=dev()); Cp[:, :N] = C[:, :N]
+    D = ops.gemm(1, Cp, Bn, M, Kd, N, ldc, Kd)
+    ref2 = Cp[:, :N].double() @ Bn.double()
+    assert float((D.double() - ref2).abs().max()) <= 2e-6 * float(ref2.abs().max())
+    ops.gemm(1, Cp, Bn, M, Kd, N, ldc, Kd, out=D, ldc=Kd, accumulate=True)
+    assert float((D.double() - 2 * ref2).abs().max()) <= 4e-6 * float(ref2.abs().max())
+    # TN: dtheta [N, Kd] += Cp^T . A  (reduction over the M rows, split over CTAs with atomics)
+    T = torch.zeros(N, Kd, device=dev())
+    ops.gemm(2, Cp, A, N, Kd, M, ldc, Kd, out=T, ldc=Kd, accumulate=True)
+    ref3 = Cp[:, :N].double().T @ A.double()
+    assert float((T.double() - ref3).abs().max()) <= 4e-6 * float(ref3.abs().max())
+
+
 class _LocalExchange:
     """Stand-in for dist.RowExchange on one GPU: same chunked call sequence, no communication."""
     def __init__(self, chunks):
