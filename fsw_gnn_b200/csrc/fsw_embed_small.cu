@@ -121,38 +121,96 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
             n_prev = n;
         }
 
-        if constexpr (SAVE_RANK) {
-            int idx[NP];
+        T acc = (T)0, acc2 = (T)0;
+        if constexpr (SAVE_RANK && sizeof(T) == 4) {
+            // fp32 training path: PACKED keys (see fsw_embed_packed.cu) - the network sorts one 32-bit word per element,
+            // the order-preserving integer image of the key with its low 5 (6) bits replaced by the element index: two
+            // integer min/max per comparator instead of a compare and four selects.  The full keys wait in shared
+            // memory (the rank scratch); adjacent positions with equal truncated keys are bubble-ordered on them, so
+            // the order is exact and ties keep element order.
+            constexpr int IB = (NP > 32) ? 6 : 5, IM = (1 << IB) - 1;
+            static_assert(NP <= (1 << IB), "element index must fit the packed low bits");
+            float* fk = reinterpret_cast<float*>(srank) + lane;
+            int p[NP];
 #pragma unroll
-            for (int j = 0; j < NP; ++j) idx[j] = j;
+            for (int j = 0; j < NP; ++j) {
+                const float v = (j < n) ? key[j] + 0.0f : __int_as_float(0x7f000000 | (j << IB));  // -0 -> +0; padding: own groups
+                fk[j * 32] = v;
+                const int b = __float_as_int(v);
+                const int t = b ^ ((b >> 31) & 0x7fffffff);
+                p[j] = (t & ~IM) | j;
+            }
             fsw_sort_network<NP>([&](int i, int l) {
-                const T x = key[i], y = key[l];
-                const int px = idx[i], py = idx[l];
-                const bool sw = x > y;
-                key[i] = sw ? y : x;
-                key[l] = sw ? x : y;
-                idx[i] = sw ? py : px;
-                idx[l] = sw ? px : py;
+                const int x = p[i], y = p[l];
+                p[i] = min(x, y);
+                p[l] = max(x, y);
             });
+            if constexpr (NP > 1) {
+                unsigned mn = 0xffffffffu;
 #pragma unroll
-            for (int j = 0; j < NP; ++j) srank[idx[j] * 32 + lane] = j;
+                for (int j = 0; j + 1 < NP; ++j) mn = min(mn, (unsigned)(p[j] ^ p[j + 1]));
+                if (__any_sync(FSW_FULL, mn <= (unsigned)IM)) {
+                    bool again = true;
+                    while (again) {
+                        bool swapped = false;
+#pragma unroll
+                        for (int j = 0; j + 1 < NP; ++j) {
+                            const int x = p[j], y = p[j + 1];
+                            if ((unsigned)(x ^ y) <= (unsigned)IM) {
+                                if (fk[(x & IM) * 32] > fk[(y & IM) * 32]) {
+                                    p[j] = y;
+                                    p[j + 1] = x;
+                                    swapped = true;
+                                }
+                            }
+                        }
+                        again = __any_sync(FSW_FULL, swapped);
+                    }
+                }
+            }
+            const bool want_dxi = dxi_out != nullptr;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const int ix = (p[j] & IM) * 32;
+                const float kv = fk[ix];
+                acc = fmaf(kv, tab[j * 32 + lane], acc);               // table rows >= n are zero: padding keys cancel
+                if (want_dxi) acc2 = fmaf(kv, tabt[j * 32 + lane], acc2);
+                reinterpret_cast<int*>(fk)[ix] = j;                    // the consumed key's slot now holds the element's rank
+            }
+            if (act) out[fsw_rowoff(cur.s, ld_out) + out_col0 + k] = A * acc + bk;
+            if (want_dxi && act) dxi_out[fsw_rowoff(cur.s, ld_dxi) + k] = A0 * acc + ((T)1 + xi) * (A0p * acc - A0 * acc2);
         } else {
-            fsw_sort_network<NP>([&](int i, int l) {
-                const T x = key[i], y = key[l];
-                key[i] = fmin(x, y);
-                key[l] = fmax(x, y);
-            });
-        }
-        T acc = (T)0;
+            if constexpr (SAVE_RANK) {
+                int idx[NP];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) acc = fma(key[j], tab[j * 32 + lane], acc);
-        if (act) out[fsw_rowoff(cur.s, ld_out) + out_col0 + k] = A * acc + bk;
-        if constexpr (SAVE_RANK) {
-            if (dxi_out != nullptr) {  // d out / d xi of this (segment, slice), summed against g in the backward
-                T acc2 = (T)0;
+                for (int j = 0; j < NP; ++j) idx[j] = j;
+                fsw_sort_network<NP>([&](int i, int l) {
+                    const T x = key[i], y = key[l];
+                    const int px = idx[i], py = idx[l];
+                    const bool sw = x > y;
+                    key[i] = sw ? y : x;
+                    key[l] = sw ? x : y;
+                    idx[i] = sw ? py : px;
+                    idx[l] = sw ? px : py;
+                });
 #pragma unroll
-                for (int j = 0; j < NP; ++j) acc2 = fma(key[j], tabt[j * 32 + lane], acc2);
-                if (act) dxi_out[fsw_rowoff(cur.s, ld_dxi) + k] = A0 * acc + ((T)1 + xi) * (A0p * acc - A0 * acc2);
+                for (int j = 0; j < NP; ++j) srank[idx[j] * 32 + lane] = j;
+            } else {
+                fsw_sort_network<NP>([&](int i, int l) {
+                    const T x = key[i], y = key[l];
+                    key[i] = fmin(x, y);
+                    key[l] = fmax(x, y);
+                });
+            }
+#pragma unroll
+            for (int j = 0; j < NP; ++j) acc = fma(key[j], tab[j * 32 + lane], acc);
+            if (act) out[fsw_rowoff(cur.s, ld_out) + out_col0 + k] = A * acc + bk;
+            if constexpr (SAVE_RANK) {
+                if (dxi_out != nullptr) {  // d out / d xi of this (segment, slice), summed against g in the backward
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) acc2 = fma(key[j], tabt[j * 32 + lane], acc2);
+                    if (act) dxi_out[fsw_rowoff(cur.s, ld_dxi) + k] = A0 * acc + ((T)1 + xi) * (A0p * acc - A0 * acc2);
+                }
             }
         }
         if constexpr (SAVE_RANK) {
@@ -689,19 +747,21 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
 __global__ void __launch_bounds__(256) fsw_scale_grad_kernel(SegArgs<float> a, int64_t S, const float* __restrict__ g, int64_t ld_g,
                                                              int64_t g_col0, const float* __restrict__ tab_A, int nmax,
                                                              float* __restrict__ GA) {
+    // one warp per segment row: n and the eligibility are read once, the row is streamed in coalesced pieces
     const int ldp = (int)a.ldp;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= S * ldp) return;
-    const int64_t s = idx / ldp;
-    const int k = (int)(idx - s * ldp);
-    float v = 0.f;
-    if (k < a.K) {
-        const int n = __ldg(a.rowptr + s + 1) - __ldg(a.rowptr + s);
-        const int w = __ldg(a.info + s);
-        if ((w & FSW_INFO_UNIFORM) && n >= 1 && n <= nmax)
-            v = __ldg(g + s * ld_g + g_col0 + k) * (1.f + __ldg(a.freqs + k)) * __ldg(tab_A + (int64_t)(n - 1) * ldp + k);
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= S) return;
+    const int n = __ldg(a.rowptr + s + 1) - __ldg(a.rowptr + s);
+    const bool ok = (__ldg(a.info + s) & FSW_INFO_UNIFORM) && n >= 1 && n <= nmax;
+    const float* gr = g + fsw_rowoff(s, ld_g) + g_col0;
+    const float* ar = tab_A + fsw_rowoff(n - 1, ldp);
+    float* out = GA + fsw_rowoff(s, ldp);
+    for (int k = lane; k < ldp; k += 32) {
+        float v = 0.f;
+        if (ok && k < a.K) v = __ldg(gr + k) * (1.f + __ldg(a.freqs + k)) * __ldg(ar + k);
+        out[k] = v;
     }
-    GA[idx] = v;
 }
 
 struct __align__(16) FswPair4 {
@@ -969,7 +1029,7 @@ int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, const
     int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_RANKT_NMAX, nullptr, nullptr, tab_A, tab_Ap, st, tab_u);
     if (rc0) return rc0;
     fsw_prof_begin("bwd_scale_grad", st);
-    fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S * ldp, 256), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, FSW_RANKT_NMAX, ga_buf);
+    fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S, 8), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, FSW_RANKT_NMAX, ga_buf);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_scale_grad_kernel");
     const int nchunks = (a.K + 127) / 128;
