@@ -827,6 +827,15 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
     const int msn = max_small_np<T>();
     const bool have_ranks = ranks != nullptr;
     double* dfreqs_cov = (have_ranks && dxi_fwd) ? nullptr : dfreqs;  // for classes covered by the forward d/dxi
+    if constexpr (sizeof(T) == 4) {
+        // dense batch of unit-weight multisets (every segment uniform, n elements, ranks recorded for all of them):
+        // one streaming kernel does the whole backward
+        if (have_ranks && dfreqs_cov == nullptr && a.rowptr == nullptr && a.col == nullptr && a.W == nullptr && a.n_fixed >= 1 &&
+            a.n_fixed <= 32768 && (double)a.n_fixed >= a.thresh && bo[FSW_PLAN_BUCKETS_PER_KIND] == bo[2 * FSW_PLAN_BUCKETS_PER_KIND]) {
+            const int64_t S = bo[2 * FSW_PLAN_BUCKETS_PER_KIND];
+            return fsw_rank_backward_dense(a, S, (int)a.n_fixed, ranks, ldr, g, ld_g, g_col0, dXp, dEp, st);
+        }
+    }
     for (int kind = 0; kind < 2; ++kind) {
         const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
         if (kind == 0 && have_ranks) {

@@ -733,6 +733,64 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdg_kernel(SegArgs<float> a,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Dense batches (no rowptr, no column ids, unit weights): every element row belongs to ONE segment of n elements and
+// receives exactly one value per slice, so the rank backward is a pure streaming kernel - 2 B of rank in, 4 B of
+// gradient out per (element, slice), coalesced, no tables: xi/n (double-float) and g (1+xi) A0(n) live in registers.
+// Block = 64 column groups (4 slices each) x 4 rows; blockIdx.x = (segment, chunk of 64 rows), blockIdx.y = 256-slice chunk.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fsw_rank_bwd_dense_kernel(SegArgs<float> a, int n, int chunks_per_seg,
+                                                                 const unsigned short* __restrict__ ranks, int64_t ldr,
+                                                                 const float* __restrict__ g, int64_t ld_g, int64_t g_col0,
+                                                                 float* __restrict__ dXp, float* __restrict__ dEp) {
+    constexpr int V = 4;
+    const int cg = blockIdx.y * 64 + (threadIdx.x & 63);
+    const int rsub = threadIdx.x >> 6;
+    const int k0 = cg * V;
+    const int ldp = (int)a.ldp;
+    if (k0 >= ldp) return;
+    const int64_t s = blockIdx.x / chunks_per_seg;
+    const int chunk = (int)(blockIdx.x - s * chunks_per_seg);
+    float uh[V], ul[V], ga[V];
+    const float wn = (float)(1.0 / (double)n);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        const int k = k0 + q;
+        uh[q] = ul[q] = ga[q] = 0.f;
+        if (k < a.K) {
+            const float xi = __ldg(a.freqs + k);
+            const double u = (double)xi / (double)n;
+            uh[q] = (float)u;
+            ul[q] = (float)(u - (double)uh[q]);
+            float A0, A0p;
+            fsw_amplitude<float, false>(u, wn, xi, A0, A0p);
+            ga[q] = __ldg(g + fsw_rowoff(s, ld_g) + g_col0 + k) * (1.f + xi) * A0;
+        }
+    }
+    const int64_t e0 = s * n;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+        const int r = chunk * 64 + it * 4 + rsub;
+        if (r >= n) break;
+        const int64_t e = e0 + r;
+        int rk[V];
+        fsw_unpack_ranks<V>(ranks + fsw_rowoff(e, ldr) + k0, rk);
+        float v[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            const float m = __uint_as_float(0x4B000000u | (unsigned)(2 * rk[q] + 1)) - 8388608.0f;  // exact below 2^23
+            const float ph = m * uh[q];
+            const float pe = fmaf(m, uh[q], -ph);
+            const float pl = fmaf(m, ul[q], pe);
+            const float hq = (0.5f * ph + 12582912.0f) - 12582912.0f;
+            const float red = fmaf(hq, -2.0f, ph);
+            v[q] = ga[q] * fsw_cospi_unit(red + pl);
+        }
+        fsw_store_vec<V>(dXp + fsw_rowoff(e, ldp) + k0, v);
+        if (dEp) fsw_store_vec<V>(dEp + fsw_rowoff(e, ldp) + k0, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // SOURCE-major rank backward (graphs): warp = (point row j, 128-slice chunk).  It walks the transposed
 // structure (all (segment, slot) pairs that reference row j), accumulates GA[seg] * cos(...) in registers
 // and writes dXp[j] ONCE with a plain 128-bit store: no atomics, no read-modify-write of dXp.
@@ -1010,6 +1068,19 @@ int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsign
                        : launch_rank_bwdg<false, true>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st);
     return has_col ? launch_rank_bwdg<true, false>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st)
                    : launch_rank_bwdg<false, false>(a, lo, hi, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs, tb, st);
+}
+
+// fp32 dense batches with unit weights: S segments of n elements each, ranks recorded by the forward for all of them
+int fsw_rank_backward_dense(const SegArgs<float>& a, int64_t S, int n, const unsigned short* ranks, int64_t ldr, const float* g,
+                            int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, cudaStream_t st) {
+    const int chunks = (n + 63) / 64;
+    if (S * chunks > 0x7fffffff) return fsw_fail(FSW_ERR_INVALID, "fsw_rank_backward_dense: batch too large for one launch");
+    dim3 grid((unsigned)(S * chunks), (unsigned)fsw_cdiv(a.ldp / 4, 64));
+    fsw_prof_begin("bwd_rank_dense_f32", st);
+    fsw_rank_bwd_dense_kernel<<<grid, 256, 0, st>>>(a, n, chunks, ranks, ldr, g, ld_g, g_col0, dXp, dEp);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_rank_bwd_dense_kernel");
+    return FSW_OK;
 }
 
 // fp32 graphs: source-major rank backward over the transposed structure (eligible: uniform weights,
