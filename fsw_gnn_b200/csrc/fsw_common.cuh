@@ -173,7 +173,7 @@ int fsw_rank_backward_u(const SegArgs<T>& a, int lo, int hi, int cap, const unsi
 // packed-key register sort (fsw_embed_packed.cu): uniform-weight fp32 segments with n <= np, np in {96, 128}
 int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0,
                          const float* bias, unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c,
-                         const float* gtab_t, cudaStream_t st);
+                         const float* gtab_t, int tab_n0, int tab_ld4, cudaStream_t st);
 
 int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* tab_c, float* tab_t, float* tab_A, float* tab_Ap,
                           cudaStream_t st, float2* tab_u = nullptr);
@@ -185,7 +185,7 @@ size_t fsw_rank_tables_bytes(int64_t ldp);
 static inline size_t fsw_fwd_tables_bytes(int64_t K) {
     return (size_t)(2 * K * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD) * sizeof(float);
 }
-int fsw_build_fwd_tables(const float* freqs, int K, float* tab_c, float* tab_t, cudaStream_t st);
+int fsw_build_fwd_tables(const float* freqs, int K, int n_lo, int n_hi, int ld4, float* tab_c, float* tab_t, cudaStream_t st);
 int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g,
                            int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, double* dfreqs, void* tables, cudaStream_t st);
 

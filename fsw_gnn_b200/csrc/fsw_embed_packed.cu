@@ -1,7 +1,8 @@
 // K2, uniform-weight fp32 forward for segments of 33..256 elements: the whole sort in registers, packed keys,
 // L cooperating lanes per slice.
 //
-//   fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>     (R, L) = (16, 4) n <= 64, (16, 8) n <= 128, (16, 16) n <= 256
+//   fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>     (R, L) = (16, 4) n <= 64, (16, 8) n <= 128, (16, 16) n <= 256;
+//                                                      dense batches also (16, 32) n <= 512 and (32, 32) n <= 1024
 //     A (segment, slice) is sorted by L lanes of one warp holding R elements each; a warp works on SW = 32 / L
 //     consecutive slices of one segment.
 //     * gather, row-wise: the SW slices of a source row are one aligned 16/32-byte piece, read by one or two
@@ -146,7 +147,7 @@ template <int R, int L, bool HAS_COL, bool SAVE_RANK>
 __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
     SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks, float* __restrict__ out, int64_t ld_out, int64_t out_col0,
     const float* __restrict__ bias, unsigned short* __restrict__ ranks, int64_t ldr, float* __restrict__ dxi_out, int64_t ld_dxi,
-    const float* __restrict__ gtab_c, const float* __restrict__ gtab_t) {
+    const float* __restrict__ gtab_c, const float* __restrict__ gtab_t, int tab_n0, int tab_ld4) {
     static_assert((R & (R - 1)) == 0 && R >= 4, "bitonic cross-lane merges and float4 table reads need R = 4, 8, 16, 32");
     static_assert((L & (L - 1)) == 0 && L >= 4 && L <= 32, "lanes per slice: power of two; 32 / L <= 8 slices tile the padded width");
     constexpr int SW = 32 / L;            // slices per warp
@@ -251,8 +252,8 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
             const float wn = (float)(1.0 / (double)n);
             fsw_amplitude<float, SAVE_RANK>(u, wn, xi, A0, A0p);
             A = (1.f + xi) * A0;
-            tc = tck + (int64_t)n * (FSW_FWD_TAB_LD / 4) * tstride;
-            tt = ttk + (int64_t)n * (FSW_FWD_TAB_LD / 4) * tstride;
+            tc = tck + (int64_t)(n - tab_n0) * tab_ld4 * tstride;
+            tt = ttk + (int64_t)(n - tab_n0) * tab_ld4 * tstride;
             n_prev = n;
         }
         __syncwarp();
@@ -267,39 +268,76 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
         }
         // ---- sort the lane's run, then merge the runs of the L lanes ----
         fsw_sort_network<R>([&](int i, int l) { FSW_PK_CMPX(s[i], s[l]); });
-        fsw_static_for<LOGL>([&](auto lc) {
-            constexpr int lv = decltype(lc)::value + 1;  // merge groups of 2^(lv-1) lanes into groups of 2^lv
-            {
-                // lane g meets lane g ^ (2^lv - 1), position i against R-1-i of the partner
-                const bool upper = (g >> (lv - 1)) & 1;
-                constexpr int xm = ((1 << lv) - 1) * SW;
-                fsw_static_for<R / 2>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    const int ya = __shfl_xor_sync(FSW_FULL, s[R - 1 - i], xm);
-                    const int yb = __shfl_xor_sync(FSW_FULL, s[i], xm);
-                    s[i] = upper ? max(s[i], ya) : min(s[i], ya);
-                    s[R - 1 - i] = upper ? max(s[R - 1 - i], yb) : min(s[R - 1 - i], yb);
+        if constexpr (L <= 16) {
+            fsw_static_for<LOGL>([&](auto lc) {
+                constexpr int lv = decltype(lc)::value + 1;  // merge groups of 2^(lv-1) lanes into groups of 2^lv
+                {
+                    // lane g meets lane g ^ (2^lv - 1), position i against R-1-i of the partner
+                    const bool upper = (g >> (lv - 1)) & 1;
+                    constexpr int xm = ((1 << lv) - 1) * SW;
+                    fsw_static_for<R / 2>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        const int ya = __shfl_xor_sync(FSW_FULL, s[R - 1 - i], xm);
+                        const int yb = __shfl_xor_sync(FSW_FULL, s[i], xm);
+                        s[i] = upper ? max(s[i], ya) : min(s[i], ya);
+                        s[R - 1 - i] = upper ? max(s[R - 1 - i], yb) : min(s[R - 1 - i], yb);
+                    });
+                }
+                fsw_static_for<lv - 1>([&](auto dc) {
+                    constexpr int d = 1 << (lv - 2 - decltype(dc)::value);  // lane distance 2^(lv-2) .. 1, same position
+                    const bool upper = (g & d) != 0;
+    #pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int y = __shfl_xor_sync(FSW_FULL, s[i], d * SW);
+                        s[i] = upper ? max(s[i], y) : min(s[i], y);
+                    }
+                });
+                // the lane now holds a bitonic run: half-cleaners at distance R/2 .. 1
+                fsw_static_for<fsw_clog2(R)>([&](auto hc) {
+                    constexpr int h = R >> (decltype(hc)::value + 1);
+                    fsw_static_for<R / 2>([&](auto ic) {
+                        constexpr int t = decltype(ic)::value;
+                        constexpr int i = (t / h) * 2 * h + (t % h);
+                        FSW_PK_CMPX(s[i], s[i + h]);
+                    });
+                });
+            });
+        } else {
+            // many lanes per slice: the same steps as loops over the merge level and the lane distance (runtime
+            // shuffle masks), so that the code stays inside the instruction cache
+#pragma unroll 1
+            for (int lv = 1; lv <= LOGL; ++lv) {
+                {
+                    const bool upper = (g >> (lv - 1)) & 1;
+                    const int xm = ((1 << lv) - 1) * SW;
+                    fsw_static_for<R / 2>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        const int ya = __shfl_xor_sync(FSW_FULL, s[R - 1 - i], xm);
+                        const int yb = __shfl_xor_sync(FSW_FULL, s[i], xm);
+                        s[i] = upper ? max(s[i], ya) : min(s[i], ya);
+                        s[R - 1 - i] = upper ? max(s[R - 1 - i], yb) : min(s[R - 1 - i], yb);
+                    });
+                }
+#pragma unroll 1
+                for (int d = (lv >= 2) ? (1 << (lv - 2)) : 0; d >= 1; d >>= 1) {
+                    const bool upper = (g & d) != 0;
+                    const int xm = d * SW;
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int y = __shfl_xor_sync(FSW_FULL, s[i], xm);
+                        s[i] = upper ? max(s[i], y) : min(s[i], y);
+                    }
+                }
+                fsw_static_for<fsw_clog2(R)>([&](auto hc) {
+                    constexpr int h = R >> (decltype(hc)::value + 1);
+                    fsw_static_for<R / 2>([&](auto ic) {
+                        constexpr int t = decltype(ic)::value;
+                        constexpr int i = (t / h) * 2 * h + (t % h);
+                        FSW_PK_CMPX(s[i], s[i + h]);
+                    });
                 });
             }
-            fsw_static_for<lv - 1>([&](auto dc) {
-                constexpr int d = 1 << (lv - 2 - decltype(dc)::value);  // lane distance 2^(lv-2) .. 1, same position
-                const bool upper = (g & d) != 0;
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    const int y = __shfl_xor_sync(FSW_FULL, s[i], d * SW);
-                    s[i] = upper ? max(s[i], y) : min(s[i], y);
-                }
-            });
-            // the lane now holds a bitonic run: half-cleaners at distance R/2 .. 1
-            fsw_static_for<fsw_clog2(R)>([&](auto hc) {
-                constexpr int h = R >> (decltype(hc)::value + 1);
-                fsw_static_for<R / 2>([&](auto ic) {
-                    constexpr int t = decltype(ic)::value;
-                    constexpr int i = (t / h) * 2 * h + (t % h);
-                    FSW_PK_CMPX(s[i], s[i + h]);
-                });
-            });
-        });
+        }
         // sorted position of s[i] in lane g: p = g R + i
 
         // ---- exact order inside groups of equal truncated keys ----
@@ -426,10 +464,11 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
 // forward tables, blocked by 4 positions with the slice index inside:
 //   tab[((n (LD/4) + j/4) K + k) 4 + j%4] = cos(pi xi_k (2j+1)/n) (and its d/dxi companion) for j < n, zero for j >= n.
 // The 32/L lanes that hold the same positions of adjacent slices read adjacent float4s: one cache line per lane group.
-__global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* __restrict__ freqs, int K, float* __restrict__ tab_c,
-                                                                   float* __restrict__ tab_t) {
-    const int n = blockIdx.x + 1;
+__global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* __restrict__ freqs, int K, int n0, int ld4,
+                                                                   float* __restrict__ tab_c, float* __restrict__ tab_t) {
+    const int n = n0 + blockIdx.x;
     const int jb = blockIdx.y;
+    if (n < 1) return;
     for (int idx = threadIdx.x; idx < K * 4; idx += blockDim.x) {
         const int k = idx >> 2, j = jb * 4 + (idx & 3);
         float c = 0.f, t = 0.f;
@@ -440,7 +479,7 @@ __global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* 
             c = cospif(rr);
             t = (float)M_PI * wn * (float)(2 * j + 1) * sinpif(rr);
         }
-        const int64_t at = ((int64_t)n * (FSW_FWD_TAB_LD / 4) + jb) * K * 4 + idx;
+        const int64_t at = ((int64_t)(n - n0) * ld4 + jb) * K * 4 + idx;
         tab_c[at] = c;
         tab_t[at] = t;
     }
@@ -449,7 +488,7 @@ __global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* 
 template <int R, int L, bool HAS_COL, bool SAVE_RANK>
 int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0, const float* bias,
                     unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
-                    cudaStream_t st) {
+                    int tab_n0, int tab_ld4, cudaStream_t st) {
     constexpr int SW = 32 / L;
     const int nchunks = (a.K + SW - 1) / SW;
     int64_t G = (int64_t)(hi - lo) * nchunks / (148 * 64);
@@ -463,7 +502,7 @@ int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const std::string label = std::string(SAVE_RANK ? "fwdr_coop_u" : "fwd_coop_u") + std::to_string(R * L) + "_f32";  // R x L slots
     fsw_prof_begin(label.c_str(), st);
-    kern<<<(unsigned)blocks, WPB * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t);
+    kern<<<(unsigned)blocks, WPB * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_coop_fwd_kernel");
     return FSW_OK;
@@ -472,39 +511,47 @@ int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t
 template <int R, int L>
 int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0, const float* bias,
                 unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
-                cudaStream_t st) {
+                int tab_n0, int tab_ld4, cudaStream_t st) {
     const bool has_col = a.col != nullptr;
-    if (ranks) {
-        return has_col ? launch_coop_fwd<R, L, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st)
-                       : launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+    if constexpr (R * L > 256) {
+        // more than 256 slots: dense batches only (a column-id register per 32 slots would not fit)
+        if (has_col) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: %d slots need a dense batch", R * L);
+        return ranks ? launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
+                     : launch_coop_fwd<R, L, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+    } else {
+        if (ranks) {
+            return has_col ? launch_coop_fwd<R, L, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
+                           : launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+        }
+        return has_col ? launch_coop_fwd<R, L, true, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st)
+                       : launch_coop_fwd<R, L, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st);
     }
-    return has_col ? launch_coop_fwd<R, L, true, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st)
-                   : launch_coop_fwd<R, L, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, st);
 }
 
 }  // namespace
 
-int fsw_build_fwd_tables(const float* freqs, int K, float* tab_c, float* tab_t, cudaStream_t st) {
-    static_assert(FSW_FWD_TAB_NMAX <= FSW_FWD_TAB_LD && FSW_FWD_TAB_LD % 4 == 0, "positions are blocked by 4");
+int fsw_build_fwd_tables(const float* freqs, int K, int n_lo, int n_hi, int ld4, float* tab_c, float* tab_t, cudaStream_t st) {
     fsw_prof_begin("coef_tables", st);
-    fsw_build_fwd_tables_kernel<<<dim3(FSW_FWD_TAB_NMAX, FSW_FWD_TAB_LD / 4), 256, 0, st>>>(freqs, K, tab_c, tab_t);
+    fsw_build_fwd_tables_kernel<<<dim3(n_hi - n_lo + 1, ld4), 256, 0, st>>>(freqs, K, n_lo, ld4, tab_c, tab_t);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_build_fwd_tables_kernel");
     return FSW_OK;
 }
 
-// uniform-weight fp32 segments order[lo, hi) with n <= np, np in {64, 128, 256}; gtab_c / gtab_t: tables of
-// fsw_build_fwd_tables
+// uniform-weight fp32 segments order[lo, hi) with n <= np, np in {64, 128, 256} (graphs and dense batches) or {512, 1024}
+// (dense batches); gtab_c / gtab_t: tables of fsw_build_fwd_tables covering n >= tab_n0 with tab_ld4 position blocks per n
 int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0,
                          const float* bias, unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c,
-                         const float* gtab_t, cudaStream_t st) {
+                         const float* gtab_t, int tab_n0, int tab_ld4, cudaStream_t st) {
     if (gtab_c == nullptr) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: coefficient table missing");
 #define FSW_COOP_CASE(NP_, R_, L_) \
-    case NP_: return launch_coop<R_, L_>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st);
+    case NP_: return launch_coop<R_, L_>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
     switch (np) {
         FSW_COOP_CASE(64, 16, 4)
         FSW_COOP_CASE(128, 16, 8)
         FSW_COOP_CASE(256, 16, 16)
+        FSW_COOP_CASE(512, 16, 32)
+        FSW_COOP_CASE(1024, 32, 32)
     }
 #undef FSW_COOP_CASE
     return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: class %d", np);

@@ -458,6 +458,46 @@ def test_gemm_strip_kernels_vs_fp64(shape):
     assert float((T.double() - ref3).abs().max()) <= 4e-6 * float(ref3.abs().max())
 
 
+@pytest.mark.parametrize("n", [300, 512, 777, 1024])
+def test_dense_batch_large_multisets_vs_oracle(n):
+    """dense batches of 257..1024 points: packed-key forward with 32 cooperating lanes + streaming rank backward.
+    d = 1 with power-of-two slices makes every projection exact in fp32 and fp64, so the sorted order is unambiguous
+    (with random 3-d slices about one pair per 1000-point batch lies within an fp32 ulp and legitimately swaps)."""
+    from fsw_gnn_b200 import FSW_embedding
+    from oracle import fsw_oracle as O
+    rng = np.random.default_rng(n)
+    B, d, K = 5, 1, 21
+    X = rng.standard_normal((B, n, d))
+    X[1, : n // 3] = X[1, n // 3: 2 * (n // 3)]          # exact duplicates inside one multiset
+    torch.manual_seed(n)
+    mod = FSW_embedding(d_in=d, d_out=K, device=dev(), dtype=torch.float32, freqs_init="spread", learnable_slices=True,
+                        learnable_freqs=True)
+    with torch.no_grad():
+        mod.projVecs.copy_(t((rng.choice([-1.0, 1.0], K) * 2.0 ** -rng.integers(0, 4, K).astype(np.float64))[:, None], torch.float32))
+    Xt = t(X, torch.float32).requires_grad_(True)
+    out = mod(Xt)
+    gout = rng.standard_normal((B, K))
+    (out * t(gout, torch.float32)).sum().backward()
+    Xq = Xt.detach().cpu().numpy().astype(np.float64).reshape(B * n, d)
+    theta = mod.projVecs.detach().cpu().numpy().astype(np.float64)
+    xi = mod.freqs.detach().cpu().numpy().astype(np.float64)
+    rowptr = np.arange(B + 1, dtype=np.int64) * n
+    col = np.arange(B * n)
+    ref = O.fsw_embed_csr(Xq, rowptr, col, None, theta, xi) + mod.bias.detach().cpu().numpy().astype(np.float64)
+    rb = O.fsw_embed_csr_backward(Xq, rowptr, col, None, theta, xi, gout)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, **tol("f32", ref))
+    # duplicated points may swap their shares (tie order): compare the sum over each pair of duplicates
+    dX = Xt.grad.cpu().numpy().reshape(B * n, d).astype(np.float64)
+    want = rb["dX"].copy()
+    m = n // 3
+    for arr in (dX, want):
+        pair = arr[n: n + m] + arr[n + m: n + 2 * m]
+        arr[n: n + m] = pair
+        arr[n + m: n + 2 * m] = pair
+    np.testing.assert_allclose(dX, want, **gtol("f32", want))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], **gtol("f32", rb["dxi"]))
+
+
 class _LocalExchange:
     """Stand-in for dist.RowExchange on one GPU: same chunked call sequence, no communication."""
     def __init__(self, chunks):
