@@ -826,22 +826,24 @@ struct __align__(16) FswPair4 {
     int seg, slot, n, pad;
 };
 
-// One batch of U (segment, slot) pairs of a source row: packed ranks and pre-scaled gradients of 4 slices per lane.
-template <int U>
+// One batch of U (segment, slot) pairs of a source row: packed ranks and pre-scaled gradients of V = 4 P slices per lane.
+template <int U, int P>
 struct FswPairBatch {
-    uint2 rk[U];
-    float4 ga[U];
+    uint2 rk[U][P];
+    float4 ga[U][P];
     int nn[U];
     int slot[U];
 };
 
+// V slices per lane: 4 (rows of up to 128 slices per warp) or 8 (up to 256: one warp per row for K = 199)
+template <int V, int U>
 __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
                                                             const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
                                                             const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
                                                             const unsigned short* __restrict__ ranks, int64_t ldr,
                                                             const float* __restrict__ GA, float* __restrict__ dXp,
                                                             float* __restrict__ dEp, const float2* __restrict__ tab_u) {
-    constexpr int V = 4, U = 4;
+    constexpr int P = V / 4;
     const int lane = threadIdx.x & 31;
     const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t j = wglobal / nchunks;
@@ -850,7 +852,9 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
     const int k0 = (chunk * 32 + lane) * V;
     if (k0 >= a.ldp) return;
     const int ldp = (int)a.ldp, ldri = (int)ldr;
-    float acc[V] = {0.f, 0.f, 0.f, 0.f};
+    float acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = 0.f;
     const int t_beg = __ldg(tptr + j), t_end = __ldg(tptr + j + 1);
     const unsigned lanemask = __activemask();  // lanes beyond the padded row width have left
     const int nlanes = __popc(lanemask);       // active lanes are a prefix 0..nlanes-1
@@ -861,7 +865,7 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
     int my_seg = 0, my_slot = 0, my_n = 0, cnt = 0;
 
     // ranks and gradients of the batch starting at triple t0 (loads only: issued one batch ahead of their use)
-    auto load_batch = [&](int t0, FswPairBatch<U>& B) {
+    auto load_batch = [&](int t0, FswPairBatch<U, P>& B) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int src = min(t0 + u, cnt - 1);
@@ -869,40 +873,52 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
             B.slot[u] = __shfl_sync(lanemask, my_slot, src);
             const int n = __shfl_sync(lanemask, my_n, src);
             B.nn[u] = t0 + u < cnt ? n : 0;
-            B.rk[u] = __ldg(reinterpret_cast<const uint2*>(rbase + fsw_rowoff(B.slot[u], ldri)));
-            B.ga[u] = __ldg(reinterpret_cast<const float4*>(gbase + fsw_rowoff(seg, ldp)));
+            const uint2* rp = reinterpret_cast<const uint2*>(rbase + fsw_rowoff(B.slot[u], ldri));
+            const float4* gp = reinterpret_cast<const float4*>(gbase + fsw_rowoff(seg, ldp));
+#pragma unroll
+            for (int h = 0; h < P; ++h) {
+                B.rk[u][h] = __ldg(rp + h);
+                B.ga[u][h] = __ldg(gp + h);
+            }
         }
     };
     // coefficients cos(pi (2r+1) xi / n) evaluated directly: a table lookup would scatter the 32 lanes of a warp over
     // 32 cache lines (each lane has its own rank) and bind the kernel on L1 wavefronts.  The phase is formed in fp32
     // from the double-float xi/n = hi + lo: (2r+1) hi is split exactly with an FMA.  Padding columns carry GA = 0
     // and xi/n = 0, so whatever their (never written) ranks hold contributes exactly 0.
-    auto consume = [&](const FswPairBatch<U>& B) {
+    auto consume = [&](const FswPairBatch<U, P>& B) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (B.nn[u] > 0) {
-                const float2* up = ubase + fsw_rowoff(B.nn[u] - 1, ldp);
-                const float4 u01 = __ldg(reinterpret_cast<const float4*>(up));
-                const float4 u23 = __ldg(reinterpret_cast<const float4*>(up + 2));
-                const float uh[V] = {u01.x, u01.z, u23.x, u23.z};
-                const float ul[V] = {u01.y, u01.w, u23.y, u23.w};
-                const unsigned m2[V] = {(B.rk[u].x & 0xffffu) * 2u + 1u, (B.rk[u].x >> 16) * 2u + 1u, (B.rk[u].y & 0xffffu) * 2u + 1u,
-                                        (B.rk[u].y >> 16) * 2u + 1u};
-                const float gq[V] = {B.ga[u].x, B.ga[u].y, B.ga[u].z, B.ga[u].w};
+                const float4* up = reinterpret_cast<const float4*>(ubase + fsw_rowoff(B.nn[u] - 1, ldp));
                 float v[V];
 #pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    // 2r+1 -> float without an I2F: exact below 2^23 through the mantissa trick
-                    const float m = __uint_as_float(0x4B000000u | m2[q]) - 8388608.0f;
-                    const float ph = m * uh[q];
-                    const float pe = fmaf(m, uh[q], -ph);  // exact rounding error of the product
-                    const float pl = fmaf(m, ul[q], pe);
-                    const float hq = (0.5f * ph + 12582912.0f) - 12582912.0f;  // rint(ph / 2) without an FRND
-                    const float red = fmaf(hq, -2.0f, ph);                      // exact: ph reduced to [-1, 1]
-                    v[q] = gq[q] * fsw_cospi_unit(red + pl);
-                    acc[q] += v[q];
+                for (int h = 0; h < P; ++h) {
+                    const float4 u01 = __ldg(up + 2 * h);
+                    const float4 u23 = __ldg(up + 2 * h + 1);
+                    const float uh[4] = {u01.x, u01.z, u23.x, u23.z};
+                    const float ul[4] = {u01.y, u01.w, u23.y, u23.w};
+                    const uint2 rk = B.rk[u][h];
+                    const unsigned m2[4] = {(rk.x & 0xffffu) * 2u + 1u, (rk.x >> 16) * 2u + 1u, (rk.y & 0xffffu) * 2u + 1u, (rk.y >> 16) * 2u + 1u};
+                    const float gq[4] = {B.ga[u][h].x, B.ga[u][h].y, B.ga[u][h].z, B.ga[u][h].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // 2r+1 -> float without an I2F: exact below 2^23 through the mantissa trick
+                        const float m = __uint_as_float(0x4B000000u | m2[q]) - 8388608.0f;
+                        const float ph = m * uh[q];
+                        const float pe = fmaf(m, uh[q], -ph);  // exact rounding error of the product
+                        const float pl = fmaf(m, ul[q], pe);
+                        const float hq = (0.5f * ph + 12582912.0f) - 12582912.0f;  // rint(ph / 2) without an FRND
+                        const float red = fmaf(hq, -2.0f, ph);                      // exact: ph reduced to [-1, 1]
+                        v[4 * h + q] = gq[q] * fsw_cospi_unit(red + pl);
+                        acc[4 * h + q] += v[4 * h + q];
+                    }
                 }
-                if (dEp) fsw_store_vec<V>(dEp + fsw_rowoff(B.slot[u], ldp) + k0, v);
+                if (dEp) {
+                    float* ep = dEp + fsw_rowoff(B.slot[u], ldp) + k0;
+#pragma unroll
+                    for (int h = 0; h < P; ++h) reinterpret_cast<float4*>(ep)[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+                }
             }
         }
     };
@@ -915,7 +931,7 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
             my_slot = __ldg(tslot + tb + lane);
             my_n = __ldg(tn + tb + lane);
         }
-        FswPairBatch<U> A, B;
+        FswPairBatch<U, P> A, B;
         load_batch(0, A);
         for (int t0 = 0; t0 < cnt; t0 += 2 * U) {
             const bool more = t0 + U < cnt;
@@ -927,7 +943,9 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
             }
         }
     }
-    fsw_store_vec<V>(dXp + fsw_rowoff(j, ldp) + k0, acc);
+    float* op = dXp + fsw_rowoff(j, ldp) + k0;
+#pragma unroll
+    for (int h = 0; h < P; ++h) reinterpret_cast<float4*>(op)[h] = make_float4(acc[4 * h], acc[4 * h + 1], acc[4 * h + 2], acc[4 * h + 3]);
 }
 
 template <bool HAS_COL, bool NEED_DXI>
@@ -1103,11 +1121,17 @@ int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, const
     fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S, 8), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, FSW_RANKT_NMAX, ga_buf);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_scale_grad_kernel");
-    const int nchunks = (a.K + 127) / 128;
+    // more than 128 slices: 8 per lane, so that a row of up to 256 slices is one warp (K = 199: 25 lanes of one warp
+    // instead of 32 + 18 lanes of two, and half the per-row / per-pair bookkeeping)
+    const bool wide = a.K > 128;
+    const int nchunks = wide ? (a.K + 255) / 256 : (a.K + 127) / 128;
     const int64_t warps = Nrows * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
     fsw_prof_begin("bwd_rankT_u512_f32", st);
-    fsw_rank_bwdT_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
+    if (wide)
+        fsw_rank_bwdT_kernel<8, 2><<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
+    else
+        fsw_rank_bwdT_kernel<4, 4><<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_rank_bwdT_kernel");
     return FSW_OK;
