@@ -603,6 +603,65 @@ def test_conv_config2_properties():
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
 
 
+def test_conv_config4_properties():
+    """configs[4]: power-law graph, 1M vertices, one hub of 100 000 in-edges, d_in=256 -> d_out=512 (skewed segment
+    sizes from 1 to 1e5 through every forward path incl. the L2-scratch merge with int32 payload; generic K1 kernel).
+    Edge-order invariance, positive homogeneity, degree channel, finite gradients, oracle on a row subsample."""
+    from fsw_gnn_b200 import FSW_conv
+    from fsw_gnn_b200.graph import cached_graph
+    from oracle import fsw_oracle as O
+    torch.manual_seed(4)
+    N, d_in, d_out = 1_000_000, 256, 512
+    g = torch.Generator(device=dev()); g.manual_seed(11)
+    u = torch.rand(N, device=dev(), generator=g).clamp_min(1e-9)
+    deg = torch.clamp((u ** (-1.0 / 1.6)).floor(), 1, 100000).to(torch.int64)     # Pareto tail, mean ~ 2.6
+    deg[12345] = 100000                                                          # the hub the config names
+    deg[777] = 40000
+    dst = torch.repeat_interleave(torch.arange(N, device=dev()), deg)
+    E = int(dst.numel())
+    src = torch.randint(0, N, (E,), device=dev(), generator=g)
+    ei = torch.stack((src, dst)).contiguous()
+    conv = FSW_conv(d_in, d_out, device=dev())
+    emb_mod = conv.fsw_embed
+    x = torch.randn(N, d_in, device=dev(), generator=g)
+    csr, plan = cached_graph(ei, N, 0, "unit", 1.0, torch.float32)
+    e1 = emb_mod.embed_plan(x, plan)
+    assert bool(torch.isfinite(e1).all())
+    assert torch.equal(e1[:, 0], deg.to(torch.float32))                           # total-mass channel = in-degree
+    perm = torch.randperm(E, device=dev(), generator=g)
+    eip = ei[:, perm].contiguous()
+    _, plan_p = cached_graph(eip, N, 0, "unit", 1.0, torch.float32)
+    e1p = emb_mod.embed_plan(x, plan_p)
+    assert torch.allclose(e1p, e1, rtol=1e-5, atol=2e-6)                          # multisets do not depend on edge order
+    del e1p, plan_p, eip, perm
+    e4 = emb_mod.embed_plan(4.0 * x, plan)                                        # power of two: exact in fp32
+    assert torch.allclose(e4[:, 1:], 4.0 * e1[:, 1:], rtol=1e-5, atol=1e-5)
+    del e4
+    # oracle on rows of every size class (fp32-rounded inputs, fp64 arithmetic)
+    rows = np.array([3, 12345 % 7 + 10] + [int(i) for i in torch.nonzero((deg > 60) & (deg < 3000))[:6, 0].cpu()] + [777])
+    rowptr = csr.rowptr.cpu().numpy().astype(np.int64)
+    col = csr.col.cpu().numpy()
+    used = np.unique(np.concatenate([col[rowptr[r]:rowptr[r + 1]] for r in rows]))
+    remap = {int(v): i for i, v in enumerate(used)}
+    sub_ptr = np.concatenate([[0], np.cumsum(np.diff(rowptr)[rows])])
+    sub_col = np.array([remap[int(c)] for r in rows for c in col[rowptr[r]:rowptr[r + 1]]])
+    Xs = x[torch.as_tensor(used, device=dev())].cpu().numpy().astype(np.float64)
+    ref = O.fsw_embed_csr(Xs, sub_ptr, sub_col, None, emb_mod.projVecs.detach().cpu().numpy().astype(np.float64),
+                          emb_mod.freqs.detach().cpu().numpy().astype(np.float64))
+    got = e1[torch.as_tensor(rows, device=dev()), 1:].detach().cpu().numpy()
+    # d_in = 256: the fp32 projections have magnitude ~16 and carry ~1e-6 of absolute rounding (the reference's fp32
+    # tensordot has the same); the oracle projects in fp64, hence abs 1e-5 here instead of 2e-6
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+    # one training step: gradients exist and are finite for inputs and all parameters
+    xr = x.clone().requires_grad_(True)
+    conv(xr, ei).square().mean().backward()
+    assert bool(torch.isfinite(xr.grad).all()) and float(xr.grad.abs().max()) > 0
+    assert emb_mod.projVecs.grad is not None and emb_mod.freqs.grad is not None
+    for p in conv.parameters():
+        if p.grad is not None:
+            assert bool(torch.isfinite(p.grad).all())
+
+
 def test_pointcloud_config3_properties():
     """256 x 1024 x 3 -> 256 (ModelNet-shaped): point-order invariance, homogeneity, batch independence,
     oracle on two multisets."""
