@@ -498,6 +498,42 @@ def test_dense_batch_large_multisets_vs_oracle(n):
     np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], **gtol("f32", rb["dxi"]))
 
 
+@pytest.mark.parametrize("n", [100, 1024, 65536])
+def test_single_multiset_config1(n):
+    """configs[0] / SURVEY 8(d) C1: one point cloud X [n, 3], FSW_embedding(3, 64), unit weights - value and the
+    gradients w.r.t. points, slices and frequencies against the oracle (n = 65 536 runs the L2-scratch path with
+    int32 payload and the re-sorting backward)."""
+    from fsw_gnn_b200 import FSW_embedding
+    from oracle import fsw_oracle as O
+    rng = np.random.default_rng(n)
+    d, K = 3, 64
+    torch.manual_seed(1)
+    mod = FSW_embedding(d_in=d, d_out=K, device=dev(), dtype=torch.float32, learnable_slices=True, learnable_freqs=True)
+    Xt = t(rng.standard_normal((n, d)), torch.float32).requires_grad_(True)
+    out = mod(Xt)
+    assert tuple(out.shape) == (K,)
+    gout = rng.standard_normal(K)
+    (out * t(gout, torch.float32)).sum().backward()
+    Xq = Xt.detach().cpu().numpy().astype(np.float64)
+    theta = mod.projVecs.detach().cpu().numpy().astype(np.float64)
+    xi = mod.freqs.detach().cpu().numpy().astype(np.float64)
+    Kc = theta.shape[0]
+    rowptr = np.array([0, n], dtype=np.int64)
+    col = np.arange(n)
+    core = O.fsw_embed_csr(Xq, rowptr, col, None, theta, xi)[0]
+    got = out.detach().cpu().numpy().astype(np.float64)
+    if mod.bias is not None and mod.enable_bias:
+        got = got - mod.bias.detach().cpu().numpy().astype(np.float64).reshape(-1)
+    np.testing.assert_allclose(got[K - Kc:], core, rtol=1e-5, atol=2e-6)
+    rb = O.fsw_embed_csr_backward(Xq, rowptr, col, None, theta, xi, gout[None, K - Kc:])
+    # with n = 65 536 points a few projections per slice agree to the last fp32 bit and may swap their shares
+    dX = Xt.grad.cpu().numpy().astype(np.float64)
+    err = np.abs(dX - rb["dX"])
+    lim = 1e-6 + 1e-5 * np.abs(rb["dX"]) + 1e-5 * np.abs(rb["dX"]).max()
+    assert (err > lim).mean() <= (2e-3 if n > 10000 else 0.0), "%.4f%% of dX off" % (100 * (err > lim).mean())
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], rtol=2e-4, atol=1e-5 * float(np.abs(rb["dxi"]).max()))
+
+
 class _LocalExchange:
     """Stand-in for dist.RowExchange on one GPU: same chunked call sequence, no communication."""
     def __init__(self, chunks):
