@@ -104,6 +104,8 @@ def label_buckets(label):
     """buckets of the segment plan covered by a profiled kernel label, e.g. fwdr_small_u24_f32 -> uniform 17..24,
     bwd_rank_u64_f32 -> uniform 0..64, fwd_medium_u128_f32 -> uniform 65..128."""
     parts = label.split("_")
+    if len(parts) < 3 or parts[2][:1] not in ("u", "g") or not parts[2][1:].isdigit():
+        return []
     kind = 0 if parts[2][0] == "u" else 1
     size = int(parts[2][1:])
     base = kind * 517
@@ -112,8 +114,8 @@ def label_buckets(label):
         return [base + b for b in range(lo, size + 1)]
     if parts[1] == "rank" and size <= 64:
         return [base + b for b in range(0, size + 1)]
-    if parts[1] == "rankT":   # source-major rank backward: every uniform segment up to `size` elements
-        return [base + b for b in range(0, size + 1)]
+    if parts[1] == "rankT":   # source-major rank backward: every uniform segment (up to 32768 elements)
+        return [b for b in range(0, 517)]
     ranges = {64: (33, 64), 128: (65, 128), 256: (129, 256), 512: (257, 512), 1024: (513, 513), 2048: (514, 514), 4096: (515, 515)}
     lo, hi = ranges.get(size, (516, 516))
     return [base + b for b in range(lo, hi + 1)]
@@ -122,7 +124,7 @@ def label_buckets(label):
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from `ncu --set full` captures of one layer of
 # THIS workload at full size (profiles/r1/README.md names the report each number comes from); None = not captured.
 NCU_TRAFFIC_FULL_SCALE = {
-    "bwd_rankT_u512_f32": 99.0e9,   # profiles/r1/ncu_r1f_rankT_fullscale.txt: 86.2 GB for the 53.6M edges of segments <= 128,
+    "bwd_rankT_u32768_f32": 99.0e9,   # profiles/r1/ncu_r1f_rankT_fullscale.txt: 86.2 GB for the 53.6M edges of segments <= 128,
                                     # scaled to the 61.5M edges served since the limit went to 512 elements
 }
 

@@ -191,7 +191,8 @@ int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsign
 
 int fsw_rank_backward_dense(const SegArgs<float>& a, int64_t S, int n, const unsigned short* ranks, int64_t ldr, const float* g,
                             int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, cudaStream_t st);
-int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, const int32_t* tptr, const int32_t* tseg,
+#define FSW_RANKT_TAB 512   // xi/n and A0(n) come from tables up to this n, are computed on the fly beyond
+int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, int nmax, const int32_t* tptr, const int32_t* tseg,
                         const int32_t* tslot, const int32_t* tn, const unsigned short* ranks, int64_t ldr, const float* g,
                         int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, void* tables, float* ga_buf, cudaStream_t st);
 

@@ -849,6 +849,8 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             return fsw_rank_backward_dense(a, S, (int)a.n_fixed, ranks, ldr, g, ld_g, g_col0, dXp, dEp, st);
         }
     }
+    bool source_major = false;   // uniform segments of up to tnmax elements done by the source-major rank backward
+    const int tnmax = FSW_RANKT_ELIGIBLE(max_n_eff);
     for (int kind = 0; kind < 2; ++kind) {
         const int base = kind * FSW_PLAN_BUCKETS_PER_KIND;
         if (kind == 0 && have_ranks) {
@@ -858,15 +860,15 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
                 if (scratch_bytes < tb) return fsw_fail(FSW_ERR_WORKSPACE, "embed scratch too small for the rank tables");
                 // the pre-scaled gradient GA [S, ldp] sits at the END of the scratch
                 const size_t ga_bytes = (size_t)tr.S * a.ldp * sizeof(float);
-                const bool source_major = a.col != nullptr && tr.tptr != nullptr && dfreqs_cov == nullptr && scratch_bytes >= tb + ga_bytes + 256;
+                source_major = a.col != nullptr && tr.tptr != nullptr && dfreqs_cov == nullptr && scratch_bytes >= tb + ga_bytes + 256;
                 if (source_major) {
-                    // graphs: every uniform segment up to FSW_RANKT_NMAX elements, one plain store per row of dXp
+                    // graphs: every uniform segment up to tnmax elements, one plain store per row of dXp
                     // (must precede every kernel that adds with atomics)
-                    if (bo[base + FSW_RANKT_NMAX + 1] > bo[base + 0]) {
+                    if (bo[base + FSW_PLAN_BUCKETS_PER_KIND] > bo[base + 0]) {
                         const size_t ga_off = (scratch_bytes - ga_bytes) & ~(size_t)255;  // keep 128-bit accesses aligned
                         float* ga_buf = (float*)((unsigned char*)scratch + ga_off);
                         scratch_bytes = ga_off;
-                        int rc = fsw_rank_backward_T(a, tr.S, tr.nrows, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, ga_buf, st);
+                        int rc = fsw_rank_backward_T(a, tr.S, tr.nrows, tnmax, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, ga_buf, st);
                         if (rc) return rc;
                     }
                 } else {
@@ -914,7 +916,8 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             const int cap = rr[ri].cap;
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
-                if (kind == 0 && cap >= 128 && cap <= 512 && have_ranks) continue;  // done by the rank kernel
+                if (kind == 0 && cap >= 128 && cap <= 512 && have_ranks) continue;  // done by the rank kernels
+                if (kind == 0 && source_major && (cap <= 4096 || tnmax == FSW_RANKT_NMAX)) continue;  // source-major rank backward
                 if (kind == 0 && cap >= 128) {
                     // re-sorting backward; the forward produced d/dxi for these when it recorded ranks (cap <= 32768)
                     double* df = (have_ranks && cap <= 32768) ? dfreqs_cov : dfreqs;

@@ -813,12 +813,25 @@ __global__ void __launch_bounds__(256) fsw_scale_grad_kernel(SegArgs<float> a, i
     const int n = __ldg(a.rowptr + s + 1) - __ldg(a.rowptr + s);
     const bool ok = (__ldg(a.info + s) & FSW_INFO_UNIFORM) && n >= 1 && n <= nmax;
     const float* gr = g + fsw_rowoff(s, ld_g) + g_col0;
-    const float* ar = tab_A + fsw_rowoff(n - 1, ldp);
     float* out = GA + fsw_rowoff(s, ldp);
-    for (int k = lane; k < ldp; k += 32) {
-        float v = 0.f;
-        if (ok && k < a.K) v = __ldg(gr + k) * (1.f + __ldg(a.freqs + k)) * __ldg(ar + k);
-        out[k] = v;
+    if (!ok || n <= FSW_RANKT_TAB) {
+        const float* ar = tab_A + fsw_rowoff(max(n, 1) - 1, ldp);
+        for (int k = lane; k < ldp; k += 32) {
+            float v = 0.f;
+            if (ok && k < a.K) v = __ldg(gr + k) * (1.f + __ldg(a.freqs + k)) * __ldg(ar + k);
+            out[k] = v;
+        }
+    } else {  // the few segments beyond the amplitude table
+        for (int k = lane; k < ldp; k += 32) {
+            float v = 0.f;
+            if (k < a.K) {
+                const float xi = __ldg(a.freqs + k);
+                float A0, A0p;
+                fsw_amplitude<float, false>((double)xi / (double)n, (float)(1.0 / (double)n), xi, A0, A0p);
+                v = __ldg(gr + k) * (1.f + xi) * A0;
+            }
+            out[k] = v;
+        }
     }
 }
 
@@ -837,7 +850,7 @@ struct FswPairBatch {
 
 // V slices per lane: 4 (rows of up to 128 slices per warp) or 8 (up to 256: one warp per row for K = 199)
 template <int V, int U>
-__global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
+__global__ void __launch_bounds__(128, 5) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
                                                             const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
                                                             const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
                                                             const unsigned short* __restrict__ ranks, int64_t ldr,
@@ -890,14 +903,29 @@ __global__ void __launch_bounds__(128) fsw_rank_bwdT_kernel(SegArgs<float> a, in
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (B.nn[u] > 0) {
-                const float4* up = reinterpret_cast<const float4*>(ubase + fsw_rowoff(B.nn[u] - 1, ldp));
+                const bool tabled = B.nn[u] <= FSW_RANKT_TAB;   // warp-uniform
+                const float4* up = reinterpret_cast<const float4*>(ubase + fsw_rowoff(min(B.nn[u], FSW_RANKT_TAB) - 1, ldp));
                 float v[V];
 #pragma unroll
                 for (int h = 0; h < P; ++h) {
-                    const float4 u01 = __ldg(up + 2 * h);
-                    const float4 u23 = __ldg(up + 2 * h + 1);
-                    const float uh[4] = {u01.x, u01.z, u23.x, u23.z};
-                    const float ul[4] = {u01.y, u01.w, u23.y, u23.w};
+                    float uh[4], ul[4];
+                    if (tabled) {
+                        const float4 u01 = __ldg(up + 2 * h);
+                        const float4 u23 = __ldg(up + 2 * h + 1);
+                        uh[0] = u01.x, uh[1] = u01.z, uh[2] = u23.x, uh[3] = u23.z;
+                        ul[0] = u01.y, ul[1] = u01.w, ul[2] = u23.y, ul[3] = u23.w;
+                    } else {  // the few large segments: xi / n as a double-float pair on the fly, in fp32 arithmetic only
+                        const float nf = (float)B.nn[u];                  // exact: n <= 32768
+                        const float ih = __frcp_rn(nf);
+                        const float il = fmaf(-nf, ih, 1.0f) * ih;        // 1/n = ih + il (Newton residual)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int k = k0 + 4 * h + q;
+                            const float xq = (k < a.K) ? __ldg(a.freqs + k) : 0.f;
+                            uh[q] = xq * ih;
+                            ul[q] = fmaf(xq, il, fmaf(xq, ih, -uh[q]));
+                        }
+                    }
                     const uint2 rk = B.rk[u][h];
                     const unsigned m2[4] = {(rk.x & 0xffffu) * 2u + 1u, (rk.x >> 16) * 2u + 1u, (rk.y & 0xffffu) * 2u + 1u, (rk.y >> 16) * 2u + 1u};
                     const float gq[4] = {B.ga[u][h].x, B.ga[u][h].y, B.ga[u][h].z, B.ga[u][h].w};
@@ -1101,24 +1129,24 @@ int fsw_rank_backward_dense(const SegArgs<float>& a, int64_t S, int n, const uns
     return FSW_OK;
 }
 
-// fp32 graphs: source-major rank backward over the transposed structure (eligible: uniform weights,
-// n <= FSW_RANKT_NMAX).
+// fp32 graphs: source-major rank backward over the transposed structure (eligible: uniform weights, n <= nmax =
+// FSW_RANKT_ELIGIBLE(max n_eff)).
 // Writes EVERY row of dXp (plain stores); must run before the kernels that add with atomics.
 // `ga_buf` [S, ldp] floats is scratch for the pre-scaled upstream gradient.
-int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, const int32_t* tptr, const int32_t* tseg,
+int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, int nmax, const int32_t* tptr, const int32_t* tseg,
                         const int32_t* tslot, const int32_t* tn, const unsigned short* ranks, int64_t ldr, const float* g,
                         int64_t ld_g, int64_t g_col0, float* dXp, float* dEp, void* tables, float* ga_buf, cudaStream_t st) {
     const int ldp = (int)a.ldp;
-    // only the amplitudes and xi/n are needed here, for n <= FSW_RANKT_NMAX: 4 * 512 * ldp floats, well inside
-    // fsw_rank_tables_bytes
-    static_assert(4 * FSW_RANKT_NMAX <= 2 * FSW_GTAB_ROWS, "source-major tables must fit the rank-table scratch");
+    // only the amplitudes and xi/n are needed here, tabulated for n <= FSW_RANKT_TAB: 4 * 512 * ldp floats, well
+    // inside fsw_rank_tables_bytes; larger segments (up to `nmax`) compute them on the fly
+    static_assert(4 * FSW_RANKT_TAB <= 2 * FSW_GTAB_ROWS, "source-major tables must fit the rank-table scratch");
     float* tab_A = (float*)tables;
-    float* tab_Ap = tab_A + (int64_t)FSW_RANKT_NMAX * ldp;
-    float2* tab_u = reinterpret_cast<float2*>(tab_Ap + (int64_t)FSW_RANKT_NMAX * ldp);
-    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_RANKT_NMAX, nullptr, nullptr, tab_A, tab_Ap, st, tab_u);
+    float* tab_Ap = tab_A + (int64_t)FSW_RANKT_TAB * ldp;
+    float2* tab_u = reinterpret_cast<float2*>(tab_Ap + (int64_t)FSW_RANKT_TAB * ldp);
+    int rc0 = fsw_build_coef_tables(a.freqs, a.K, ldp, FSW_RANKT_TAB, nullptr, nullptr, tab_A, tab_Ap, st, tab_u);
     if (rc0) return rc0;
     fsw_prof_begin("bwd_scale_grad", st);
-    fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S, 8), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, FSW_RANKT_NMAX, ga_buf);
+    fsw_scale_grad_kernel<<<(unsigned)fsw_cdiv(S, 8), 256, 0, st>>>(a, S, g, ld_g, g_col0, tab_A, nmax, ga_buf);
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_scale_grad_kernel");
     // more than 128 slices: 8 per lane, so that a row of up to 256 slices is one warp (K = 199: 25 lanes of one warp
@@ -1127,7 +1155,7 @@ int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, const
     const int nchunks = wide ? (a.K + 255) / 256 : (a.K + 127) / 128;
     const int64_t warps = Nrows * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
-    fsw_prof_begin("bwd_rankT_u512_f32", st);
+    fsw_prof_begin("bwd_rankT_u32768_f32", st);
     if (wide)
         fsw_rank_bwdT_kernel<8, 2><<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
     else

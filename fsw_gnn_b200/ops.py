@@ -19,7 +19,7 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
-RANKT_NMAX = 512   # FSW_RANKT_NMAX (csrc/fsw_common.cuh): largest segment served by the source-major backward
+RANKT_NMAX = 32768   # FSW_RANKT_NMAX (include/fsw_embedding.h): largest segment served by the source-major backward
 
 
 class SegmentPlan:
@@ -87,7 +87,8 @@ class SegmentPlan:
             tslot = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
             tn = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
             ws = _ws(lib.fsw_transpose_workspace_bytes(key), dev)
-            check(lib.fsw_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E, RANKT_NMAX,
+            check(lib.fsw_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E,
+                                        RANKT_NMAX if self.max_n_eff <= RANKT_NMAX else 4096,   # FSW_RANKT_ELIGIBLE
                                         ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev)),
                   "fsw_csr_transpose")
             self._transpose = (key, tptr, tseg, tslot, tn)
