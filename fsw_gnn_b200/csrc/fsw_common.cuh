@@ -180,10 +180,21 @@ int fsw_build_coef_tables(const float* freqs, int K, int ldp, int nmax, float* t
 size_t fsw_rank_tables_bytes(int64_t ldp);
 // forward coefficient tables (cos and d/dxi) for n <= FSW_FWD_TAB_NMAX, [n][FSW_FWD_TAB_LD/4][K][4], in front of the
 // forward scratch (fsw_embed_packed.cu)
-#define FSW_FWD_TAB_NMAX 256
-#define FSW_FWD_TAB_LD 256
-static inline size_t fsw_fwd_tables_bytes(int64_t K) {
-    return (size_t)(2 * K * (FSW_FWD_TAB_NMAX + 1) * FSW_FWD_TAB_LD) * sizeof(float);
+#define FSW_FWD_TAB_NMAX 512
+// extent of the tables for a plan: the largest uniform segment size in 33..FSW_FWD_TAB_NMAX that occurs (0: none)
+static inline int fsw_fwd_tables_nmax(const int32_t* bo) {
+    for (int n = FSW_FWD_TAB_NMAX; n > 32; --n)
+        if (bo[n] < bo[n + 1]) return n;
+    return 0;
+}
+// both tables (cos, d/dxi): (nmax + 1) size classes x ceil(nmax / 4) position blocks x K slices x 4 positions
+static inline size_t fsw_fwd_tables_bytes(int64_t K, int nmax) {
+    const int64_t ld4 = (nmax + 3) / 4;
+    return (size_t)(2 * (int64_t)(nmax + 1) * ld4 * K * 4) * sizeof(float);
+}
+// a dense batch of FSW_FWD_TAB_NMAX+1 .. 1024 points per multiset: one size class
+static inline size_t fsw_fwd_tables_bytes_single(int64_t K, int64_t n) {
+    return (size_t)(2 * ((n + 3) / 4) * K * 4) * sizeof(float);
 }
 int fsw_build_fwd_tables(const float* freqs, int K, int n_lo, int n_hi, int ld4, float* tab_c, float* tab_t, cudaStream_t st);
 int fsw_rank_backward_g128(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g,

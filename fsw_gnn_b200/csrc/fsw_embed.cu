@@ -717,21 +717,23 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
     // served by the packed-key kernels is present
     const float* gtab_c = nullptr;
     const float* gtab_t = nullptr;
-    int tab_n0 = 0, tab_ld4 = FSW_FWD_TAB_LD / 4, tab_nmax = 0;   // n covered by the tables: tab_n0 .. tab_nmax
+    int tab_n0 = 0, tab_ld4 = 0, tab_nmax = 0;   // n covered by the tables: tab_n0 .. tab_nmax
     if constexpr (sizeof(T) == 4) {
-        const size_t tb = fsw_fwd_tables_bytes(a.K);
         const bool dense_single = a.rowptr == nullptr && a.n_fixed > FSW_FWD_TAB_NMAX && a.n_fixed <= 1024 && bo[0] < bo[FSW_PLAN_BUCKETS_PER_KIND];
-        if (scratch_bytes >= tb && (dense_single || bo[32 + 1] < bo[FSW_FWD_TAB_NMAX + 1])) {
+        const int nmax_present = fsw_fwd_tables_nmax(bo);
+        const size_t tb = dense_single ? fsw_fwd_tables_bytes_single(a.K, a.n_fixed) : fsw_fwd_tables_bytes(a.K, nmax_present);
+        if (scratch_bytes >= tb && (dense_single || nmax_present > 0)) {
             float* tc = (float*)scratch;
-            float* tt = tc + fsw_fwd_tables_bytes(a.K) / (2 * sizeof(float));
+            float* tt = tc + tb / (2 * sizeof(float));
             int rc;
             if (dense_single) {  // a dense batch has one segment size: a table for that n alone (a.K * n * 4 floats)
                 tab_n0 = tab_nmax = (int)a.n_fixed;
                 tab_ld4 = (int)((a.n_fixed + 3) / 4);
                 rc = fsw_build_fwd_tables(a.freqs, a.K, tab_n0, tab_n0, tab_ld4, tc, tt, st);
             } else {
-                tab_nmax = FSW_FWD_TAB_NMAX;
-                rc = fsw_build_fwd_tables(a.freqs, a.K, 1, FSW_FWD_TAB_NMAX, tab_ld4, tc + (int64_t)tab_ld4 * a.K * 4,
+                tab_nmax = nmax_present;
+                tab_ld4 = (nmax_present + 3) / 4;
+                rc = fsw_build_fwd_tables(a.freqs, a.K, 1, nmax_present, tab_ld4, tc + (int64_t)tab_ld4 * a.K * 4,
                                           tt + (int64_t)tab_ld4 * a.K * 4, st);
             }
             if (rc) return rc;
@@ -749,7 +751,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
                 if (hi <= lo) continue;
                 if constexpr (sizeof(T) == 4) {
-                    if (gtab_c != nullptr && c.np > 32 && tab_nmax >= 64 && tab_n0 <= 1) {  // 33..64: packed keys, 4 cooperating lanes
+                    if (gtab_c != nullptr && c.np > 32 && tab_n0 == 0) {  // 33..64: packed keys, 4 cooperating lanes
                         const int np = c.np == 48 ? 64 : c.np;
                         int rc = fsw_packed_forward_u(a, np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
                         if (rc) return rc;
@@ -775,9 +777,10 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
             const int cap = rr[ri].cap;
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
-                // 65..256 elements (and dense batches of up to 1024): packed keys, cooperating lanes
-                if (kind == 0 && gtab_c != nullptr && cap <= 1024 && cap <= (tab_n0 <= 1 ? 256 : 1024) && tab_nmax >= (tab_n0 <= 1 ? cap : 1) &&
-                    (tab_n0 <= 1 || (a.n_fixed > cap / 2 && a.n_fixed <= cap))) {
+                // 65..512 elements (and dense batches of up to 1024): packed keys, cooperating lanes.  The graph tables
+                // (tab_n0 == 0) reach the largest size <= 512 that occurs; a dense single-size table serves its own class.
+                if (kind == 0 && gtab_c != nullptr && cap <= 1024 &&
+                    (tab_n0 == 0 ? cap <= FSW_FWD_TAB_NMAX : (a.n_fixed > cap / 2 && a.n_fixed <= cap))) {
                     int rc = fsw_packed_forward_u(a, cap, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
                     if (rc) return rc;
                     continue;
@@ -993,7 +996,15 @@ extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t 
             if (grid * tb > need) need = grid * tb;
         }
     }
-    if (dtype == FSW_F32) need += backward ? fsw_rank_tables_bytes((K + 7) / 8 * 8) : fsw_fwd_tables_bytes(K);
+    if (dtype == FSW_F32) {
+        size_t tabs = fsw_rank_tables_bytes((K + 7) / 8 * 8);
+        if (!backward) {
+            tabs = fsw_fwd_tables_bytes(K, fsw_fwd_tables_nmax(bo));
+            if (max_n_eff > FSW_FWD_TAB_NMAX && max_n_eff <= 1024 && fsw_fwd_tables_bytes_single(K, max_n_eff) > tabs)
+                tabs = fsw_fwd_tables_bytes_single(K, max_n_eff);
+        }
+        need += tabs;
+    }
     return need;
 }
 

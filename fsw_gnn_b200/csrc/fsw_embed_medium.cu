@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
 
         // ---- 3. last pass: the merged stream is consumed, not stored ----
         const bool want_dxi = (MODE == 1) && (dxi_out != nullptr);
-        const bool use_gtab = (MODE == 1) && (gtab_c != nullptr) && (n <= FSW_FWD_TAB_NMAX);
+        const bool use_gtab = (MODE == 1) && (gtab_c != nullptr) && (n <= 256);  // (legacy row-major tables; callers pass NULL)
         const T* gtc = use_gtab ? gtab_c + ((int64_t)n * (n - 1) / 2) * a.ldp + kk : nullptr;
         const T* gtt = use_gtab ? gtab_t + ((int64_t)n * (n - 1) / 2) * a.ldp + kk : nullptr;
         (void)want_dxi;

@@ -2,7 +2,7 @@
 // L cooperating lanes per slice.
 //
 //   fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>     (R, L) = (16, 4) n <= 64, (16, 8) n <= 128, (16, 16) n <= 256;
-//                                                      dense batches also (16, 32) n <= 512 and (32, 32) n <= 1024
+//                                                      (32, 16) n <= 512; dense batches also (32, 32) n <= 1024
 //     A (segment, slice) is sorted by L lanes of one warp holding R elements each; a warp works on SW = 32 / L
 //     consecutive slices of one segment.
 //     * gather, row-wise: the SW slices of a source row are one aligned 16/32-byte piece, read by one or two
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
     constexpr int SW = 32 / L;            // slices per warp
     constexpr int NS = R * L;             // element slots per (segment, slice)
     constexpr int NC = NS / 32;           // column-id registers per lane (element 32 m + lane)
+    constexpr bool PREFETCH_COLS = NC <= 8;
     constexpr int VW = SW < 4 ? SW : 4;   // gather: floats per lane,
     constexpr int LPR = SW / VW;          //         lanes per row,
     constexpr int RPI = 32 / LPR;         //         rows per load instruction
@@ -239,9 +240,10 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
             }
             fsw_sts_words<VW>(fkw + e * SW + part, v);
         }
-        // prefetches for the following segments (their addresses were loaded one iteration ago)
-        int cn[NC];
-        fsw_pk_cols<NC, HAS_COL>(a.col, nx1.e0, nx1.n, lane, cn);
+        // prefetches for the following segments (their addresses were loaded one iteration ago); with more than 8
+        // column-id registers the ids are fetched at the end of the iteration instead (long segments hide it)
+        int cn[PREFETCH_COLS ? NC : 1];
+        if constexpr (PREFETCH_COLS) fsw_pk_cols<NC, HAS_COL>(a.col, nx1.e0, nx1.n, lane, cn);
         PkMeta nx2;
         nx2.s = s2;
         fsw_pk_range(a, s2, nx2.e0, nx2.n);
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
         }
         // ---- sort the lane's run, then merge the runs of the L lanes ----
         fsw_sort_network<R>([&](int i, int l) { FSW_PK_CMPX(s[i], s[l]); });
-        if constexpr (L <= 16) {
+        if constexpr (L <= 16 && R <= 16) {
             fsw_static_for<LOGL>([&](auto lc) {
                 constexpr int lv = decltype(lc)::value + 1;  // merge groups of 2^(lv-1) lanes into groups of 2^lv
                 {
@@ -303,8 +305,8 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
                 });
             });
         } else {
-            // many lanes per slice: the same steps as loops over the merge level and the lane distance (runtime
-            // shuffle masks), so that the code stays inside the instruction cache
+            // many lanes per slice or long runs: the same steps as loops over the merge level and the lane distance
+            // (runtime shuffle masks), so that the code stays inside the instruction cache
 #pragma unroll 1
             for (int lv = 1; lv <= LOGL; ++lv) {
                 {
@@ -454,8 +456,12 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
         }
         // rotate the pipeline
         cur = nx1;
+        if constexpr (PREFETCH_COLS) {
 #pragma unroll
-        for (int m = 0; m < NC; ++m) c[m] = cn[m];
+            for (int m = 0; m < NC; ++m) c[m] = cn[m];
+        } else {
+            fsw_pk_cols<NC, HAS_COL>(a.col, cur.e0, cur.n, lane, c);
+        }
         nx1 = nx2;
         s2 = s3;
     }
@@ -513,8 +519,8 @@ int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_
                 unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
                 int tab_n0, int tab_ld4, cudaStream_t st) {
     const bool has_col = a.col != nullptr;
-    if constexpr (R * L > 256) {
-        // more than 256 slots: dense batches only (a column-id register per 32 slots would not fit)
+    if constexpr (R * L > 512) {
+        // more than 512 slots: dense batches only (a column-id register per 32 slots would not fit)
         if (has_col) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: %d slots need a dense batch", R * L);
         return ranks ? launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
                      : launch_coop_fwd<R, L, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st);
@@ -550,7 +556,7 @@ int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float*
         FSW_COOP_CASE(64, 16, 4)
         FSW_COOP_CASE(128, 16, 8)
         FSW_COOP_CASE(256, 16, 16)
-        FSW_COOP_CASE(512, 16, 32)
+        FSW_COOP_CASE(512, 32, 16)
         FSW_COOP_CASE(1024, 32, 32)
     }
 #undef FSW_COOP_CASE
