@@ -581,6 +581,71 @@ def test_column_chunked_calls_equal_single_call(chunks):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()) + 1e-7)
 
 
+def test_edge_features_all_size_classes_vs_oracle():
+    """per-edge feature vectors (d_edge = 3) through every forward path (small, coop 64..512, merge path) and the
+    matching backward: value, dX, dE, dtheta, dxi against the oracle"""
+    from fsw_gnn_b200 import FSW_embedding
+    from fsw_gnn_b200.ops import SegmentPlan
+    from oracle import fsw_oracle as O
+    rng = np.random.default_rng(23)
+    N, d, de, K = 500, 5, 3, 29
+    degs = np.array([0, 1, 3, 7, 12, 20, 31, 40, 64, 70, 128, 130, 255, 300, 512, 600, 1100])
+    S = len(degs)
+    rowptr = np.concatenate([[0], np.cumsum(degs)]).astype(np.int64)
+    E = int(rowptr[-1])
+    col = rng.integers(0, N, E)
+    X = rng.standard_normal((N, d))
+    Ef = rng.standard_normal((E, de))
+    torch.manual_seed(23)
+    mod = FSW_embedding(d_in=d, d_out=K, d_edge=de, device=dev(), dtype=torch.float32, freqs_init="spread", learnable_slices=True,
+                        learnable_freqs=True)
+    theta = mod.projVecs.detach().cpu().numpy().astype(np.float64)
+    xi = mod.freqs.detach().cpu().numpy().astype(np.float64)
+    assert theta.shape[1] == d + de
+    plan = SegmentPlan(S, E, torch.as_tensor(rowptr.astype(np.int32), device=dev()), 0, torch.as_tensor(col.astype(np.int32), device=dev()),
+                       None, 1.0, torch.float32, dev())
+    Xt = t(X, torch.float32).requires_grad_(True)
+    Et = t(Ef, torch.float32).requires_grad_(True)
+    out = mod.embed_plan(Xt, plan, Et)
+    gout = rng.standard_normal((S, K))
+    (out * t(gout, torch.float32)).sum().backward()
+    Xq = Xt.detach().cpu().numpy().astype(np.float64)
+    Eq = Et.detach().cpu().numpy().astype(np.float64)
+    ref = O.fsw_embed_csr(Xq, rowptr, col, None, theta, xi, E_feat=Eq) + mod.bias.detach().cpu().numpy().astype(np.float64)
+    rb = O.fsw_embed_csr_backward(Xq, rowptr, col, None, theta, xi, gout, E_feat=Eq)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, **tol("f32", ref))
+    np.testing.assert_allclose(Xt.grad.cpu().numpy(), rb["dX"], **gtol("f32", rb["dX"]))
+    np.testing.assert_allclose(Et.grad.cpu().numpy(), rb["dE"], **gtol("f32", rb["dE"]))
+    np.testing.assert_allclose(mod.projVecs.grad.cpu().numpy(), rb["dtheta"], **gtol("f32", rb["dtheta"]))
+    np.testing.assert_allclose(mod.freqs.grad.cpu().numpy(), rb["dxi"], **gtol("f32", rb["dxi"]))
+
+
+def test_inference_path_equals_training_forward():
+    """torch.no_grad() runs the kernels without rank recording (other template instances, no d/dxi): same values"""
+    from fsw_gnn_b200 import FSW_embedding
+    from fsw_gnn_b200.ops import SegmentPlan
+    rng = np.random.default_rng(5)
+    N, d, K = 700, 6, 37
+    degs = np.array([0, 2, 9, 17, 33, 48, 65, 100, 129, 200, 257, 400, 513, 900, 2300])
+    rowptr = np.concatenate([[0], np.cumsum(degs)]).astype(np.int64)
+    E = int(rowptr[-1])
+    plan = SegmentPlan(len(degs), E, torch.as_tensor(rowptr.astype(np.int32), device=dev()), 0,
+                       torch.as_tensor(rng.integers(0, N, E).astype(np.int32), device=dev()), None, 1.0, torch.float32, dev())
+    torch.manual_seed(5)
+    mod = FSW_embedding(d_in=d, d_out=K, device=dev(), dtype=torch.float32, learnable_slices=True, learnable_freqs=True)
+    X = t(rng.standard_normal((N, d)), torch.float32)
+    out_train = mod.embed_plan(X.clone().requires_grad_(True), plan).detach()
+    with torch.no_grad():
+        out_inf = mod.embed_plan(X, plan)
+    assert not out_inf.requires_grad
+    torch.testing.assert_close(out_inf, out_train, rtol=1e-6, atol=1e-6)
+    # dense batch, both paths
+    Xd = t(rng.standard_normal((4, 300, d)), torch.float32)
+    with torch.no_grad():
+        od = mod(Xd)
+    torch.testing.assert_close(od, mod(Xd.clone().requires_grad_(True)).detach(), rtol=1e-6, atol=1e-6)
+
+
 def test_hub_segments_vs_oracle():
     """very large segments (global-scratch merge path; > 32768 elements switches the payload to int32)"""
     degs = np.array([3, 5000, 40000, 17, 700])
