@@ -1,15 +1,22 @@
-// K2 / K3: fused FSW embedding forward and backward over CSR segments.
+// K2 / K3: fused FSW embedding forward and backward over CSR segments - entry points and dispatch, plus the kernels
+// for general (non-uniform) weights and fp64.
 //
 // Replaces FSW_embedding.forward_helper (fsw_embedding.py:894-1112) and the autograd functions it
-// drives (class ag, :1232-2258; helpers sp, :2266-2775).  One launch family per size class:
+// drives (class ag, :1232-2258; helpers sp, :2266-2775).  The segment plan sorts the segments into size buckets;
+// every bucket range is served by one launch of the kernel family that fits it:
 //
-//   small  (n_eff <= 64 fp32 / 32 fp64): one THREAD owns one (segment, slice).  Lanes of a warp are 32
+//   uniform weights, fp32 (the case of FSW_conv's default adjacency and of unit-weight point clouds)
+//     n <= 32        fsw_small_fwd_kernel        (fsw_embed_small.cu)   thread per (segment, slice), register network
+//     33 .. 512      fsw_coop_fwd_kernel         (fsw_embed_packed.cu)  L lanes per slice, packed keys; dense <= 1024
+//     larger         fsw_medium_kernel           (fsw_embed_medium.cu)  CTA tile, register runs + merge path
+//     backward       fsw_rank_bwdT_kernel / fsw_rank_bwd_dense_kernel (fsw_embed_small.cu): no sort, the forward
+//                    recorded every element's sorted position; re-sorting kernels only beyond 32768 elements
+//   general weights / fp64 (this file)
+//     small  (n_eff <= 64 fp32 / 32 fp64): one THREAD owns one (segment, slice).  Lanes of a warp are 32
 //          consecutive slices, so the gather Xp[col[e], k0..k0+31] is one coalesced 128-byte line per
-//          element.  Keys live in registers and are sorted with a data-oblivious Batcher odd-even
-//          merge network (no shuffles, no divergence).  Segments are visited in plan order (sorted by
-//          size) so that, with uniform weights, the per-(n, slice) Fourier coefficient table
-//          cos(pi xi (2j+1)/n) is built once and reused for a run of segments.
-//   generic (anything larger): one CTA owns a tile [n_pad][32 slices] in shared memory (or in an
+//          element.  Keys (and raw weights) live in registers and are sorted with a data-oblivious merge-exchange
+//          network (no shuffles, no divergence).
+//     generic (anything larger): one CTA owns a tile [n_pad][32 slices] in shared memory (or in an
 //          L2-resident global scratch when it does not fit) and runs a block-wide bitonic network
 //          with rows as elements and lanes as slices (bank = lane, conflict free).
 //

@@ -1,4 +1,5 @@
-// K2 / K3 medium path: segments of 65 .. 512 elements with uniform weights (fp32).
+// K2 / K3 medium / large path: uniform-weight fp32 segments beyond the register-sort kernels (more than 512 elements;
+// 65 .. 512 only when the coefficient tables of the packed-key kernels do not fit the scratch).
 //
 // One CTA owns a tile [n][32 slices] of one (segment, slice-chunk); lanes are slices, so every shared
 // memory access of a warp hits 32 different banks whatever the rows are (bank = lane).

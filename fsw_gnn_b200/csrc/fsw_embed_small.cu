@@ -1,5 +1,5 @@
-// K2 / K3, uniform-weight fast path for small segments (n <= 64 fp32, <= 32 fp64) and the rank-based
-// backward used for every uniform-weight segment.
+// K2 / K3, uniform-weight fast path for small segments (n <= 32; up to 64 when the packed-key kernels are not
+// available, <= 32 fp64) and the rank-based backward used for every uniform-weight segment.
 //
 //   fsw_small_fwd_kernel<T, NP, HAS_COL, SAVE_RANK>
 //     one THREAD per (segment, slice), lanes = 32 consecutive slices, keys in registers, merge-exchange
