@@ -758,8 +758,8 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
                 if (hi <= lo) continue;
                 if constexpr (sizeof(T) == 4) {
-                    if (gtab_c != nullptr && c.np > 32 && tab_n0 == 0) {  // 33..64: packed keys, 4 cooperating lanes
-                        const int np = c.np == 48 ? 64 : c.np;
+                    if (gtab_c != nullptr && c.np > 32 && tab_n0 == 0) {  // 33..48, 49..64: packed keys, 4 cooperating lanes
+                        const int np = c.np;
                         int rc = fsw_packed_forward_u(a, np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
                         if (rc) return rc;
                         continue;
@@ -788,7 +788,15 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 // (tab_n0 == 0) reach the largest size <= 512 that occurs; a dense single-size table serves its own class.
                 if (kind == 0 && gtab_c != nullptr && cap <= 1024 &&
                     (tab_n0 == 0 ? cap <= FSW_FWD_TAB_NMAX : (a.n_fixed > cap / 2 && a.n_fixed <= cap))) {
-                    int rc = fsw_packed_forward_u(a, cap, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+                    int rc = FSW_OK;
+                    if (tab_n0 == 0 && cap <= FSW_FWD_TAB_NMAX) {
+                        // two classes per power of two: 3/4 cap slots for the lower part of the range (less padding)
+                        const int mid = bo[base + 3 * cap / 4 + 1];
+                        if (mid > lo) rc = fsw_packed_forward_u(a, 3 * cap / 4, lo, mid, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+                        if (rc == FSW_OK && hi > mid) rc = fsw_packed_forward_u(a, cap, mid, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+                    } else {
+                        rc = fsw_packed_forward_u(a, cap, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+                    }
                     if (rc) return rc;
                     continue;
                 }
