@@ -1,0 +1,57 @@
+"""Host-side logic that needs no GPU: column chunking of the multi-GPU exchange, the benchmark's mapping from
+profiled kernel labels to plan buckets (the roofline accounting), constants shared between the header and Python."""
+import importlib.util
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_column_chunks_cover_all_slices_in_multiples_of_8():
+    from fsw_gnn_b200.ops import column_chunks
+    for K in (0, 1, 7, 8, 9, 63, 64, 199, 200, 255, 1023):
+        for n in (1, 2, 3, 4, 8, 100):
+            ch = column_chunks(K, n)
+            if K == 0:
+                assert ch == [(0, 0)]
+                continue
+            assert ch[0][0] == 0 and ch[-1][1] == K
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+            assert all(k0 % 8 == 0 and k1 > k0 for k0, k1 in ch)
+            assert len(ch) <= max(1, min(n, (K + 7) // 8))
+
+
+def test_bench_label_buckets_partition_the_uniform_buckets():
+    b = _bench()
+    # every forward class label of the C4 run maps to a disjoint bucket range; together they cover 0..516
+    labels = (["fwdr_small_u%d_f32" % n for n in (4, 8, 12, 16, 24, 32)] +
+              ["fwdr_coop_u%d_f32" % n for n in (48, 64, 96, 128, 192, 256, 384, 512)] +
+              ["fwdr_medium_u%d_f32" % n for n in (1024, 2048, 4096, 8192)])
+    seen = []
+    for lab in labels:
+        bs = b.label_buckets(lab)
+        assert bs, lab
+        seen += bs
+    assert sorted(seen) == list(range(0, 517)), "forward labels must tile the uniform-weight buckets exactly once"
+    assert b.label_buckets("bwd_rankT_u32768_f32") == list(range(0, 517))
+    assert b.label_buckets("bwd_rank_dense_f32") == [] and b.label_buckets("coef_tables") == []
+    # general-weight labels live in the second kind
+    assert b.label_buckets("fwd_small_g16_f32") == [517 + n for n in range(9, 17)]
+
+
+def test_python_constants_match_the_header():
+    from fsw_gnn_b200 import _lib, ops
+    hdr = open(os.path.join(ROOT, "include", "fsw_embedding.h")).read()
+    per_kind = int(re.search(r"#define FSW_PLAN_BUCKETS_PER_KIND (\d+)", hdr).group(1))
+    assert _lib.PLAN_BUCKETS_PER_KIND == per_kind == 517
+    assert ops.RANKT_NMAX == int(re.search(r"#define FSW_RANKT_NMAX (\d+)", hdr).group(1))
+    assert "FSW_RANKT_ELIGIBLE" in hdr
