@@ -325,6 +325,132 @@ int gemm_strip_f32(int op, int64_t M, int64_t N, int64_t Kd, const float* A, int
     return -1;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Backward contractions for small d_in (N <= 8, e.g. 3-d point clouds), fp32: both are ONE streaming pass over the
+// [rows, K] gradient of the projections (memory bound), where a tiled GEMM would waste > 90 % of its 64-wide tile.
+//   nn_small: C[M, N] (+)= A[M, Kd] . B[Kd, N]      dX = dXp . theta     warp per row, lanes over Kd, shuffle reduction
+//   tn_small: C[M, N] += A[Kd, M]^T . B[Kd, N]      dtheta = dXp^T . X   lanes over M, register accumulators over a
+//                                                                        run of rows, one atomic per warp and output
+// KJ = ceil(width / 32) values per lane (width = Kd resp. M <= 32 KJ).
+// ---------------------------------------------------------------------------------------------------
+template <int N, int KJ>
+__global__ void __launch_bounds__(256) fsw_gemm_nn_small_kernel(int64_t M, int Kd, const float* __restrict__ A, int64_t lda,
+                                                                const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
+                                                                int64_t ldc, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float b[KJ][N];
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+        const int k = lane + 32 * j;
+#pragma unroll
+        for (int n = 0; n < N; ++n) b[j][n] = (k < Kd) ? __ldg(B + (int64_t)k * ldb + n) : 0.f;
+    }
+    for (int64_t r = warp0; r < M; r += nwarps) {
+        const float* ar = A + r * lda;
+        float v[KJ];
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) v[j] = (lane + 32 * j < Kd) ? __ldg(ar + lane + 32 * j) : 0.f;
+        float s[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) t = fmaf(v[j], b[j][n], t);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            s[n] = t;
+        }
+        if (lane < N) {
+            float out = s[0];
+#pragma unroll
+            for (int n = 1; n < N; ++n) out = (lane == n) ? s[n] : out;
+            float* c = C + r * ldc + lane;
+            *c = accumulate ? *c + out : out;
+        }
+    }
+}
+
+template <int N, int KJ>
+__global__ void __launch_bounds__(256) fsw_gemm_tn_small_kernel(int64_t Kd, int M, const float* __restrict__ A, int64_t lda,
+                                                                const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
+                                                                int64_t ldc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float acc[KJ][N];
+#pragma unroll
+    for (int j = 0; j < KJ; ++j)
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[j][n] = 0.f;
+    for (int64_t r = warp0; r < Kd; r += nwarps) {
+        const float* ar = A + r * lda;
+        float x[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) x[n] = __ldg(B + r * ldb + n);   // same address in every lane: one broadcast load
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) {
+            const float v = (lane + 32 * j < M) ? __ldg(ar + lane + 32 * j) : 0.f;
+#pragma unroll
+            for (int n = 0; n < N; ++n) acc[j][n] = fmaf(v, x[n], acc[j][n]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+        const int m = lane + 32 * j;
+        if (m < M) {
+#pragma unroll
+            for (int n = 0; n < N; ++n) atomicAdd(C + (int64_t)m * ldc + n, acc[j][n]);
+        }
+    }
+}
+
+template <int N>
+int launch_small_n(int op, int64_t M, int64_t Kd, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int accumulate, cudaStream_t st) {
+    const int64_t width = (op == 1) ? Kd : M;      // the axis spread over the lanes
+    const int KJ = (int)((width + 31) / 32);
+    if (KJ > 8) return -1;
+    const int64_t rows = (op == 1) ? M : Kd;
+    int64_t blocks = fsw_cdiv(rows, 8 * 16);        // 8 warps per block, >= 16 rows per warp
+    const int64_t cap = (op == 1) ? 148 * 8 : 148 * 2;   // op 2 ends with one atomic per warp and output: fewer, longer warps
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    fsw_prof_begin(op == 1 ? "gemm_nn" : "gemm_tn", st);
+#define FSW_SMALLN(KJ_)                                                                                                              \
+    case KJ_:                                                                                                                        \
+        if (op == 1)                                                                                                                 \
+            fsw_gemm_nn_small_kernel<N, KJ_><<<(unsigned)blocks, 256, 0, st>>>(M, (int)Kd, A, lda, B, ldb, C, ldc, accumulate);      \
+        else                                                                                                                         \
+            fsw_gemm_tn_small_kernel<N, KJ_><<<(unsigned)blocks, 256, 0, st>>>(Kd, (int)M, A, lda, B, ldb, C, ldc);                  \
+        break;
+    switch (KJ) {
+        FSW_SMALLN(1) FSW_SMALLN(2) FSW_SMALLN(3) FSW_SMALLN(4) FSW_SMALLN(5) FSW_SMALLN(6) FSW_SMALLN(7) FSW_SMALLN(8)
+    }
+#undef FSW_SMALLN
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_gemm_small_n_kernel");
+    return FSW_OK;
+}
+
+// ops 1 and 2 with N <= 8 columns and the lane axis <= 256 wide; returns -1 when not covered
+int gemm_small_n_f32(int op, int64_t M, int64_t N, int64_t Kd, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                     int64_t ldc, int accumulate, cudaStream_t st) {
+    if ((op != 1 && op != 2) || N < 1 || N > 8) return -1;
+    switch ((int)N) {
+        case 1: return launch_small_n<1>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 2: return launch_small_n<2>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 3: return launch_small_n<3>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 4: return launch_small_n<4>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 5: return launch_small_n<5>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 6: return launch_small_n<6>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 7: return launch_small_n<7>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        case 8: return launch_small_n<8>(op, M, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+    }
+    return -1;
+}
+
 // Small-d projection (d_in <= 8, e.g. 3-d point clouds): memory bound on the Xp write.  One thread
 // produces 4 consecutive slices of one row; theta is read through the read-only cache.
 template <typename T, int D>
@@ -383,7 +509,9 @@ int gemm_t(int op, int64_t M, int64_t N, int64_t Kd, const T* A, int64_t lda, co
         return FSW_OK;
     }
     if constexpr (sizeof(T) == 4) {
-        const int rc = gemm_strip_f32(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        int rc = gemm_small_n_f32(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
+        if (rc >= 0) return rc;
+        rc = gemm_strip_f32(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
         if (rc >= 0) return rc;
     }
     int64_t splits = 1;

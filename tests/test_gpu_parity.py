@@ -428,10 +428,12 @@ def test_near_ties_exact_order(zeros):
     np.testing.assert_allclose(got, want, **gtol("f32", want))
 
 
-@pytest.mark.parametrize("shape", [(1000, 199, 100), (777, 100, 200), (130, 37, 16), (4097, 104, 48), (300, 200, 64), (515, 61, 52)])
+@pytest.mark.parametrize("shape", [(1000, 199, 100), (777, 100, 200), (130, 37, 16), (4097, 104, 48), (300, 200, 64), (515, 61, 52),
+                                   (1000, 199, 3), (3000, 255, 8), (700, 64, 1), (20000, 256, 3)])
 def test_gemm_strip_kernels_vs_fp64(shape):
     """K1 full-width strip kernels (fp32, small dimension <= 200): X.theta^T, dXp.theta and dXp^T.X against fp64
-    matmul of the same fp32 inputs.  Tolerance 2e-6 relative to the largest output (fp32 FMA accumulation)."""
+    matmul of the same fp32 inputs.  Tolerance 1e-6 of the largest sum of absolute terms (fp32 FMA accumulation); also the
+    streaming small-N kernels (d_in <= 8) of the backward contractions."""
     from fsw_gnn_b200 import ops
     M, N, Kd = shape
     g = torch.Generator(device=dev()); g.manual_seed(M + N)
@@ -448,14 +450,16 @@ def test_gemm_strip_kernels_vs_fp64(shape):
     Cp = torch.zeros(M, ldc, device=dev()); Cp[:, :N] = C[:, :N]
     D = ops.gemm(1, Cp, Bn, M, Kd, N, ldc, Kd)
     ref2 = Cp[:, :N].double() @ Bn.double()
-    assert float((D.double() - ref2).abs().max()) <= 2e-6 * float(ref2.abs().max())
+    scale2 = float((Cp[:, :N].double().abs() @ Bn.double().abs()).max())   # size of the summed terms (results may cancel)
+    assert float((D.double() - ref2).abs().max()) <= 1e-6 * scale2
     ops.gemm(1, Cp, Bn, M, Kd, N, ldc, Kd, out=D, ldc=Kd, accumulate=True)
-    assert float((D.double() - 2 * ref2).abs().max()) <= 4e-6 * float(ref2.abs().max())
+    assert float((D.double() - 2 * ref2).abs().max()) <= 2e-6 * scale2
     # TN: dtheta [N, Kd] += Cp^T . A  (reduction over the M rows, split over CTAs with atomics)
     T = torch.zeros(N, Kd, device=dev())
     ops.gemm(2, Cp, A, N, Kd, M, ldc, Kd, out=T, ldc=Kd, accumulate=True)
     ref3 = Cp[:, :N].double().T @ A.double()
-    assert float((T.double() - ref3).abs().max()) <= 4e-6 * float(ref3.abs().max())
+    scale3 = float((Cp[:, :N].double().abs().T @ A.double().abs()).max())
+    assert float((T.double() - ref3).abs().max()) <= 1e-6 * scale3
 
 
 @pytest.mark.parametrize("n", [300, 512, 777, 1024])
