@@ -459,7 +459,7 @@ def test_gemm_strip_kernels_vs_fp64(shape):
     ops.gemm(2, Cp, A, N, Kd, M, ldc, Kd, out=T, ldc=Kd, accumulate=True)
     ref3 = Cp[:, :N].double().T @ A.double()
     scale3 = float((Cp[:, :N].double().abs().T @ A.double().abs()).max())
-    assert float((T.double() - ref3).abs().max()) <= 1e-6 * scale3
+    assert float((T.double() - ref3).abs().max()) <= 4e-6 * scale3   # reduction over M rows, split over warps + atomics
 
 
 @pytest.mark.parametrize("n", [300, 512, 777, 1024])
