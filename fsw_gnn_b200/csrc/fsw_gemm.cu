@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(256) fsw_gemm_nn_small_kernel(int64_t M, int K
 #pragma unroll
         for (int n = 0; n < N; ++n) b[j][n] = (k < Kd) ? __ldg(B + (int64_t)k * ldb + n) : 0.f;
     }
+#pragma unroll 2
     for (int64_t r = warp0; r < M; r += nwarps) {
         const float* ar = A + r * lda;
         float v[KJ];
@@ -384,7 +385,8 @@ __global__ void __launch_bounds__(256) fsw_gemm_tn_small_kernel(int64_t Kd, int 
     for (int j = 0; j < KJ; ++j)
 #pragma unroll
         for (int n = 0; n < N; ++n) acc[j][n] = 0.f;
-    for (int64_t r = warp0; r < Kd; r += nwarps) {
+#pragma unroll 4
+    for (int64_t r = warp0; r < Kd; r += nwarps) {   // several rows in flight per warp
         const float* ar = A + r * lda;
         float x[N];
 #pragma unroll
