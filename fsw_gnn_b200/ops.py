@@ -258,7 +258,8 @@ class FSWEmbedFunction(torch.autograd.Function):
         need_X, need_theta, need_xi, need_bias, need_scale, need_E = ctx.needs_input_grad[:6]
         d = X.shape[1]
         K = projVecs.shape[0]
-        g = g.contiguous()
+        if not (g.dim() == 2 and g.stride(1) == 1 and g.stride(0) >= g.shape[1]):
+            g = g.contiguous()   # row-strided views (e.g. a column slice handed back by torch.cat) are read in place
         dX = dtheta = dxi = dbias = dscale = dE = None
         if need_bias and ctx.has_bias:
             dbias = g.sum(dim=0)
@@ -283,7 +284,7 @@ class FSWEmbedFunction(torch.autograd.Function):
                 transpose = None
                 if ranks is not None and X.dtype == torch.float32 and plan.col is not None and (dxi_fwd or not need_xi):
                     transpose = plan.transpose(Nrows)
-                embed_backward(plan, Xp, ldc, ctx.Ep, freqs[k0:k1], g, g.shape[1], tm_dim + k0, dXp, dEp, dxi_acc, ranks,
+                embed_backward(plan, Xp, ldc, ctx.Ep, freqs[k0:k1], g, g.stride(0), tm_dim + k0, dXp, dEp, dxi_acc, ranks,
                                dxi_from_forward=(dxi_fwd or not need_xi), transpose=transpose, nrows=Nrows)
                 if need_xi:
                     dxi_c = dxi_acc.to(X.dtype)
