@@ -835,10 +835,6 @@ __global__ void __launch_bounds__(256) fsw_scale_grad_kernel(SegArgs<float> a, i
     }
 }
 
-struct __align__(16) FswPair4 {
-    int seg, slot, n, pad;
-};
-
 // One batch of U (segment, slot) pairs of a source row: packed ranks and pre-scaled gradients of V = 4 P slices per lane.
 template <int U, int P>
 struct FswPairBatch {
