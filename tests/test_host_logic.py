@@ -55,3 +55,22 @@ def test_python_constants_match_the_header():
     assert _lib.PLAN_BUCKETS_PER_KIND == per_kind == 517
     assert ops.RANKT_NMAX == int(re.search(r"#define FSW_RANKT_NMAX (\d+)", hdr).group(1))
     assert "FSW_RANKT_ELIGIBLE" in hdr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference's algorithm on the host cores) needs no GPU:
+    one JSON line with the contract's keys, its own cpu_baseline and a zero-copy e2e."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
