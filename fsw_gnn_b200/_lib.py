@@ -55,6 +55,10 @@ _SIGNATURES = {
     "fsw_embed_backward": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,
                                    c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp, c_i64,
                                    c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "fsw_embed_weight_grad_scratch_bytes": (c_sz, [c_i32, c_i64]),
+    "fsw_embed_backward_weights": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_dbl, c_i32,
+                                           c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "fsw_embed_weight_grad_finish": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_dbl, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "fsw_transpose_workspace_bytes": (c_sz, [c_i64]),
     "fsw_csr_transpose": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
@@ -107,6 +111,16 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def call(device, name, *args):
+    """Run library entry point `name` with `device` as the current CUDA device and raise on a non-zero status.
+    The C ABI takes raw pointers and a stream; launches, memsets and function-attribute calls act on the calling
+    thread's CURRENT device, so every entry into the library runs in the device context of the tensors it is given
+    (a module on cuda:1 works whatever the current device is, like the torch reference)."""
+    fn = getattr(load(), name)
+    with torch.cuda.device(device):
+        check(fn(*args), name)
 
 
 def require_cuda(t, name):

@@ -298,41 +298,8 @@ __global__ void __launch_bounds__(128) fsw_bwd_small_kernel(SegArgs<T> a, int se
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Generic path: block-wide bitonic network, rows = elements, lanes = slices.
+// Generic path: block-wide bitonic network (fsw_block_bitonic, fsw_sortnet.cuh), rows = elements, lanes = slices.
 // ---------------------------------------------------------------------------------------------------
-template <typename KT, typename PT, bool HAS_PAY>
-__device__ __forceinline__ void fsw_block_bitonic(KT* keys, PT* pay, int n_pad) {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nw = blockDim.x >> 5;
-    for (int k = 2; k <= n_pad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = warp; t < (n_pad >> 1); t += nw) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i | j;
-                const bool asc = ((i & k) == 0);
-                KT x = keys[i * 32 + lane], y = keys[l * 32 + lane];
-                if ((x > y) == asc) {
-                    keys[i * 32 + lane] = y;
-                    keys[l * 32 + lane] = x;
-                    if (HAS_PAY) {
-                        PT px = pay[i * 32 + lane], py = pay[l * 32 + lane];
-                        pay[i * 32 + lane] = py;
-                        pay[l * 32 + lane] = px;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-__device__ __forceinline__ int fsw_next_pow2(int n) {
-    int p = 2;
-    while (p < n) p <<= 1;
-    return p;
-}
-
 // forward.  MODE 0: uniform weights (keys only).  MODE 1: general (payload = raw weight, -1 = pad point)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) fsw_fwd_generic_kernel(SegArgs<T> a, int seg_lo, int nchunks, int64_t ntiles,
@@ -1061,7 +1028,7 @@ extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const 
                                   const int32_t* tn, int64_t nrows, void* stream) {
     if (S == 0 || K == 0) return FSW_OK;
     if (dW != nullptr)
-        return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_embed_backward: gradient w.r.t. the weights W is not implemented");
+        return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: dW must be NULL (use fsw_embed_backward_weights)");
     if (!Xp || !mass || !info || !bucket_offsets_host || !freqs || !g || !dXp)
         return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: null argument");
     if (!rowptr && n_fixed <= 0) return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: rowptr == NULL needs n_fixed > 0");

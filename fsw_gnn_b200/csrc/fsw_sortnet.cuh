@@ -167,3 +167,40 @@ __device__ __forceinline__ void fsw_gather_lean(const char* __restrict__ xp_byte
 #pragma unroll
     for (int j = 0; j < NP; ++j) key[j] = (j < cnt) ? key[j] : Num<T>::big();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Block-wide bitonic network over a tile [n_pad rows][32 lanes] (shared or global memory): rows = elements, lanes = slices.
+// ---------------------------------------------------------------------------------------------------
+template <typename KT, typename PT, bool HAS_PAY>
+__device__ __forceinline__ void fsw_block_bitonic(KT* keys, PT* pay, int n_pad) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = warp; t < (n_pad >> 1); t += nw) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool asc = ((i & k) == 0);
+                KT x = keys[i * 32 + lane], y = keys[l * 32 + lane];
+                if ((x > y) == asc) {
+                    keys[i * 32 + lane] = y;
+                    keys[l * 32 + lane] = x;
+                    if (HAS_PAY) {
+                        PT px = pay[i * 32 + lane], py = pay[l * 32 + lane];
+                        pay[i * 32 + lane] = py;
+                        pay[l * 32 + lane] = px;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int fsw_next_pow2(int n) {
+    int p = 2;
+    while (p < n) p <<= 1;
+    return p;
+}
+

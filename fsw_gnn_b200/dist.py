@@ -138,7 +138,7 @@ class ShardedGraph:
         col = remap_sources(src, self.row_ranges, self.max_rows)
         ei = torch.stack((col, dst - self.row_lo), dim=0).contiguous()
         self.num_edges = int(ei.shape[1])
-        self.csr = _graph.GraphCSR(ei, self.n_local, 0, "unit", dtype)
+        self.csr = _graph.GraphCSR(ei, self.n_local, 0, "unit", dtype, num_sources=len(self.row_ranges) * self.max_rows)
         self.plan = self.csr.plan(thresh, dtype)
         self.plan.exchange = RowExchange(self.max_rows, group)   # project locally, all-gather the projected rows
 
@@ -152,14 +152,19 @@ def sharded_conv_forward(conv, x_local, sg):
 
 
 def all_reduce_gradients(modules, group=None):
-    """Sum the parameter gradients over the ranks (one flat all-reduce)."""
-    grads = [p.grad for m in modules for p in m.parameters() if p.grad is not None]
-    if not grads:
+    """Sum the parameter gradients over the ranks (one flat all-reduce).  Every trainable parameter takes part on every
+    rank - a rank whose shard produced no gradient for one (e.g. an empty shard) contributes zeros - so that the flat
+    buffers have the same layout everywhere."""
+    params = [p for m in modules for p in m.parameters() if p.requires_grad]
+    if not params:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
     dist.all_reduce(flat, group=group)
     off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+    for p in params:
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p))
         off += n

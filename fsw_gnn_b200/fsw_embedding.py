@@ -332,8 +332,6 @@ class FSW_embedding(nn.Module):
             if checks:
                 assert torch.isfinite(W_vals).all(), "All entries of W must be finite (no NaNs / infs)"
                 assert (W_vals >= 0).all(), "All entries of W must be nonnegative"
-            if W.requires_grad:
-                raise NotImplementedError("fsw_gnn_b200: gradients with respect to the weights W are not implemented")
         X_edge_sparse = False
         if X_edge is not None:
             assert torch.is_tensor(W), "When X_edge is provided, W must be provided explicitly"
@@ -392,12 +390,16 @@ class FSW_embedding(nn.Module):
         thresh = self.total_mass_pad_thresh
         Xf = X.reshape(-1, self.d_in)
         E_feat = None
+        W_values = None   # the plan's weights as a differentiable tensor, when W requires grad
+        want_dW = torch.is_tensor(W) and W.requires_grad and torch.is_grad_enabled()
         if not graph_mode and not W_sparse:
             B = int(np.prod(batch_dims, dtype=np.int64)) if batch_dims else 1
             if torch.is_tensor(W):
                 Wf = W.reshape(-1).contiguous()
                 plan = self._cached_plan(("dense", Wf.data_ptr(), W._version, B, n, thresh, dtype), W,
-                                         lambda: _graph.plan_dense(B, n, Wf, thresh, dtype, device))
+                                         lambda: _graph.plan_dense(B, n, Wf.detach(), thresh, dtype, device))
+                if want_dW:
+                    W_values = Wf
             elif W == "unit":
                 plan = self._cached_plan(("unit", B, n, thresh, dtype), None,
                                          lambda: _graph.plan_dense(B, n, None, thresh, dtype, device))
@@ -417,11 +419,13 @@ class FSW_embedding(nn.Module):
                     # dense adjacency: zero weights contribute nothing and are dropped
                     idx = torch.nonzero(W).t().contiguous()
                     vals = W[tuple(idx)]
-                plan_ = _graph.plan_from_coo(idx, vals, wshape, graph_mode, thresh, dtype)
+                plan_ = _graph.plan_from_coo(idx, vals.detach(), wshape, graph_mode, thresh, dtype)
                 plan_.coo_indices = idx
                 return plan_
 
             plan = self._cached_plan(("coo", key_ptr, W._version, wshape, W_sparse, graph_mode, thresh, dtype), W, build_coo)
+            if want_dW:
+                W_values = (W.values() if W_sparse else W[tuple(plan.coo_indices)]).contiguous()
             if X_edge is not None:
                 if X_edge_sparse:
                     E_feat = X_edge.values()
@@ -430,13 +434,15 @@ class FSW_embedding(nn.Module):
                 else:
                     xe = X_edge if X_edge.dim() == W.dim() + 1 else X_edge.unsqueeze(-1)
                     E_feat = xe[tuple(plan.coo_indices)]
-        out = self.embed_plan(Xf, plan, E_feat)
+        out = self.embed_plan(Xf, plan, E_feat, W_values=W_values)
         return out.reshape(out_shape)
 
     # ------------------------------------------------------------------------------------------
-    def embed_plan(self, Xf, plan, E_feat=None):
+    def embed_plan(self, Xf, plan, E_feat=None, W_values=None):
         """[S, d_out] embedding of the segments of `plan` over the point matrix Xf [Nrows, d_in].
-        This is the entry FSW_conv uses directly with its cached graph plan."""
+        This is the entry FSW_conv uses directly with its cached graph plan.
+        W_values: the plan's element weights (same values and order as plan.W) as a tensor that requires grad, when the
+        gradient with respect to the weights is wanted; None otherwise."""
         theta, xi = self.projVecs, self.freqs
         if self.cartesian_mode:
             # every (slice, frequency) pair becomes one fused (slice, frequency) column: k * nFreqs + f
@@ -446,13 +452,16 @@ class FSW_embedding(nn.Module):
         if bias is not None and bias.dim() == 2:
             bias = bias.reshape(-1)
         scale = self.total_mass_encoding_scale if self.encode_total_mass else None
+        if W_values is not None and not (W_values.requires_grad and torch.is_grad_enabled()):
+            W_values = None
         if not self.encode_total_mass:
-            return _ops.fsw_embed(Xf, theta, xi, bias, None, E_feat, plan, None)
+            return _ops.fsw_embed(Xf, theta, xi, bias, None, E_feat, plan, None, W_values)
         if self.total_mass_encoding_method == "plain":
-            return _ops.fsw_embed(Xf, theta, xi, bias, scale, E_feat, plan, self.total_mass_encoding_function)
+            return _ops.fsw_embed(Xf, theta, xi, bias, scale, E_feat, plan, self.total_mass_encoding_function, W_values)
         # homogeneous variants (fsw_embedding.py:876-884): composed in torch on the [S, K] core
-        core = _ops.fsw_embed(Xf, theta, xi, None, None, E_feat, plan, None)
-        tm = _ops.total_mass_function(plan.mass_as(core.dtype), self.total_mass_encoding_function).unsqueeze(-1) * scale
+        core = _ops.fsw_embed(Xf, theta, xi, None, None, E_feat, plan, None, W_values)
+        mass = plan.mass_as(core.dtype) if W_values is None else plan.differentiable_mass(W_values)
+        tm = _ops.total_mass_function(mass, self.total_mass_encoding_function).unsqueeze(-1) * scale
         nrm = torch.mean(core.abs(), dim=-1, keepdim=True)
         if self.total_mass_encoding_method == "homog":
             out = torch.cat((tm * nrm, core), dim=-1)

@@ -7,7 +7,7 @@
 import torch
 
 from . import _lib
-from ._lib import check, dtype_code, ptr, stream_ptr
+from ._lib import dtype_code, ptr, stream_ptr
 from .ops import SegmentPlan, _ws
 
 
@@ -20,8 +20,7 @@ def rowptr_from_sorted_rows(rows, S):
     lib = _lib.load()
     rows = rows.contiguous()
     rowptr = torch.empty(S + 1, dtype=torch.int32, device=rows.device)
-    check(lib.fsw_rowptr_from_sorted_rows(ptr(rows), rows.numel(), S, ptr(rowptr), stream_ptr(rows.device)),
-          "fsw_rowptr_from_sorted_rows")
+    _lib.call(rows.device, "fsw_rowptr_from_sorted_rows", ptr(rows), rows.numel(), S, ptr(rowptr), stream_ptr(rows.device))
     return rowptr
 
 
@@ -55,20 +54,43 @@ def plan_from_coo(indices, values, shape, graph_mode, thresh, dtype):
     return SegmentPlan(nseg, W.numel(), rowptr, 0, col, W, thresh, dtype, device)
 
 
+def validate_edge_index(edge_index, num_vertices, num_sources=None):
+    """Every id must address an existing row: destinations in [0, num_vertices), sources in [0, num_sources).
+    The reference raises here as well (sparse_coo_tensor / coalesce check the indices against the size,
+    fsw_conv.py:397-398); the CSR kernels themselves do not bounds-check.  One pass over the edge list and one small
+    D2H read, on the cache-miss path only (a new graph is followed by the plan's own D2H read anyway)."""
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must have shape [2, E], got %s" % (tuple(edge_index.shape),))
+    E = int(edge_index.shape[1])
+    if E >= 2 ** 31 - int(num_vertices):
+        raise RuntimeError("more than 2^31 edges are not supported (int32 CSR)")
+    if E == 0:
+        return
+    num_sources = int(num_vertices) if num_sources is None else int(num_sources)
+    lo, hi = torch.aminmax(edge_index, dim=1)
+    src_lo, dst_lo, src_hi, dst_hi = [int(v) for v in torch.stack((lo, hi)).reshape(-1).tolist()]
+    if src_lo < 0 or dst_lo < 0 or src_hi >= num_sources or dst_hi >= int(num_vertices):
+        raise RuntimeError("edge_index out of range: sources in [%d, %d] (need [0, %d)), destinations in [%d, %d] (need [0, %d))"
+                           % (src_lo, src_hi, num_sources, dst_lo, dst_hi, int(num_vertices)))
+
+
 class GraphCSR:
     """Destination-major CSR of a graph given as edge_index (fsw_conv.py:384-409)."""
 
-    def __init__(self, edge_index, num_vertices, self_loop_weight, edge_weighting, dtype, coalesce=False):
+    def __init__(self, edge_index, num_vertices, self_loop_weight, edge_weighting, dtype, coalesce=False, num_sources=None):
         """coalesce=False: duplicate (dst, src) pairs stay separate elements (exact for the embedding and
         its gradients, see include/fsw_embedding.h section 3).  coalesce=True merges them like the
         reference's `coalesce()` (fsw_conv.py:397-398, :438-439) - needed with edge features, where
-        the merged element carries the SUM of the duplicates' feature vectors."""
+        the merged element carries the SUM of the duplicates' feature vectors.
+        num_sources: rows of the point matrix the sources index (default num_vertices; the sharded path re-indexes its
+        sources into the gathered layout of G * max_rows rows)."""
         self.coalesced = bool(coalesce)
+        _lib.require_cuda(edge_index, "edge_index")
+        validate_edge_index(edge_index, num_vertices, num_sources)
         if coalesce:
             self._init_coalesced(edge_index, num_vertices, self_loop_weight, edge_weighting, dtype)
             return
         lib = _lib.load()
-        _lib.require_cuda(edge_index, "edge_index")
         assert edge_weighting in {"unit", "gcn"}, "invalid value passed in argument <edge_weighting>"
         device = edge_index.device
         ei = edge_index.contiguous()
@@ -83,14 +105,13 @@ class GraphCSR:
         self.col = torch.empty(max(Etot, 1), dtype=torch.int32, device=device)[:Etot]
         self.eid = torch.empty(max(Etot, 1), dtype=torch.int32, device=device)[:Etot]
         ws = _ws(lib.fsw_csr_workspace_bytes(N), device)
-        check(lib.fsw_csr_from_edge_index(ptr(ei), E, N, self_loops, ptr(self.rowptr), ptr(self.col), ptr(self.eid),
-                                          ptr(ws), ws.numel(), stream_ptr(device)), "fsw_csr_from_edge_index")
+        _lib.call(device, "fsw_csr_from_edge_index", ptr(ei), E, N, self_loops, ptr(self.rowptr), ptr(self.col), ptr(self.eid),
+                  ptr(ws), ws.numel(), stream_ptr(device))
         gcn = 1 if edge_weighting == "gcn" else 0
         self.in_degrees = torch.empty(N, dtype=dtype, device=device)
         self.W = torch.empty(Etot, dtype=dtype, device=device) if (gcn or self_loops) else None
-        check(lib.fsw_edge_weights(dtype_code(dtype), ptr(self.rowptr), ptr(self.col), ptr(self.eid), N, E, self_loops,
-                                   float(self_loop_weight), gcn, ptr(self.in_degrees), ptr(self.W), stream_ptr(device)),
-              "fsw_edge_weights")
+        _lib.call(device, "fsw_edge_weights", dtype_code(dtype), ptr(self.rowptr), ptr(self.col), ptr(self.eid), N, E, self_loops,
+                  float(self_loop_weight), gcn, ptr(self.in_degrees), ptr(self.W), stream_ptr(device))
 
     def _init_coalesced(self, edge_index, num_vertices, self_loop_weight, edge_weighting, dtype):
         _lib.require_cuda(edge_index, "edge_index")

@@ -45,9 +45,9 @@ class SegmentPlan:
         self._bucket_dev = torch.empty(_lib.PLAN_BUCKETS + 2, dtype=torch.int32, device=device)
         self._elems_dev = torch.empty(_lib.PLAN_BUCKETS, dtype=torch.int64, device=device)
         ws = _ws(lib.fsw_plan_workspace_bytes(self.S), device)
-        check(lib.fsw_segment_plan(dtype_code(dtype), ptr(rowptr), self.n_fixed, ptr(W), self.S, self.thresh,
-                                   ptr(self.mass), ptr(self.info), ptr(self.order), ptr(self._bucket_dev),
-                                   ptr(self._elems_dev), ptr(ws), ws.numel(), stream_ptr(device)), "fsw_segment_plan")
+        _lib.call(device, "fsw_segment_plan", dtype_code(dtype), ptr(rowptr), self.n_fixed, ptr(W), self.S, self.thresh,
+                  ptr(self.mass), ptr(self.info), ptr(self.order), ptr(self._bucket_dev), ptr(self._elems_dev), ptr(ws),
+                  ws.numel(), stream_ptr(device))
         # one small D2H read per new plan (the reference syncs in every get_slice_info, :2655)
         host = self._bucket_dev.cpu()
         self.bucket_offsets = (ctypes.c_int * (_lib.PLAN_BUCKETS + 2))(*host.tolist())
@@ -87,12 +87,37 @@ class SegmentPlan:
             tslot = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
             tn = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
             ws = _ws(lib.fsw_transpose_workspace_bytes(key), dev)
-            check(lib.fsw_csr_transpose(ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E,
-                                        RANKT_NMAX if self.max_n_eff <= RANKT_NMAX else 4096,   # FSW_RANKT_ELIGIBLE
-                                        ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev)),
-                  "fsw_csr_transpose")
+            _lib.call(dev, "fsw_csr_transpose", ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E,
+                      RANKT_NMAX if self.max_n_eff <= RANKT_NMAX else 4096,   # FSW_RANKT_ELIGIBLE
+                      ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev))
             self._transpose = (key, tptr, tseg, tslot, tn)
         return self._transpose[1:]
+
+    def any_deficient(self):
+        """True when some segment has total mass below the pad threshold (one small D2H read, cached)."""
+        if getattr(self, "_any_def", None) is None:
+            self._any_def = bool((self.mass < self.thresh).any().item()) if self.S > 0 else False
+        return self._any_def
+
+    def segment_ids(self):
+        """[E] int64 segment of every element (for element-wise broadcasts / segment sums in torch)."""
+        if getattr(self, "_seg_ids", None) is None:
+            if self.rowptr is None:
+                self._seg_ids = torch.arange(self.S, device=self.device).repeat_interleave(self.n_fixed)
+            else:
+                counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+                self._seg_ids = torch.repeat_interleave(torch.arange(self.S, device=self.device), counts, output_size=self.E)
+        return self._seg_ids
+
+    def expand_to_elements(self, per_segment):
+        """[S] -> [E]: the segment's value for each of its elements"""
+        return per_segment.index_select(0, self.segment_ids())
+
+    def differentiable_mass(self, W_vals):
+        """Total mass per segment as a torch function of the element weights (autograd flows into W)"""
+        if self.rowptr is None:
+            return W_vals.reshape(self.S, self.n_fixed).sum(dim=1)
+        return torch.zeros(self.S, dtype=W_vals.dtype, device=W_vals.device).index_add(0, self.segment_ids(), W_vals)
 
     def uniform_fraction(self):
         bo = list(self.bucket_offsets)
@@ -105,8 +130,8 @@ def gemm(op, A, B, M, N, Kd, lda, ldb, out=None, ldc=None, accumulate=False):
     if out is None:
         ldc = N if ldc is None else ldc
         out = torch.empty((M, ldc), dtype=A.dtype, device=A.device)
-    check(lib.fsw_gemm(dtype_code(A.dtype), op, M, N, Kd, ptr(A), lda, ptr(B), ldb, ptr(out), ldc,
-                       1 if accumulate else 0, stream_ptr(A.device)), "fsw_gemm")
+    _lib.call(A.device, "fsw_gemm", dtype_code(A.dtype), op, M, N, Kd, ptr(A), lda, ptr(B), ldb, ptr(out), ldc,
+              1 if accumulate else 0, stream_ptr(A.device))
     return out
 
 
@@ -128,13 +153,12 @@ def embed_forward(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks=N
     lib = _lib.load()
     K = freqs.numel()
     scratch = plan.scratch(K, False)
-    check(lib.fsw_embed_forward(dtype_code(plan.dtype), ptr(Xp), ldp, ptr(Ep), ptr(plan.rowptr), plan.n_fixed,
-                                ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
-                                plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(out), ld_out, out_col0,
-                                ptr(bias), plan.max_n_eff, ptr(scratch), 0 if scratch is None else scratch.numel(),
-                                ptr(ranks), 0 if ranks is None else ranks.stride(0),
-                                ptr(dxi_out), 0 if dxi_out is None else dxi_out.stride(0), stream_ptr(plan.device)),
-          "fsw_embed_forward")
+    _lib.call(plan.device, "fsw_embed_forward", dtype_code(plan.dtype), ptr(Xp), ldp, ptr(Ep), ptr(plan.rowptr), plan.n_fixed,
+              ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
+              plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(out), ld_out, out_col0,
+              ptr(bias), plan.max_n_eff, ptr(scratch), 0 if scratch is None else scratch.numel(),
+              ptr(ranks), 0 if ranks is None else ranks.stride(0),
+              ptr(dxi_out), 0 if dxi_out is None else dxi_out.stride(0), stream_ptr(plan.device))
 
 
 def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_acc, ranks=None, dxi_from_forward=False,
@@ -142,16 +166,15 @@ def embed_backward(plan, Xp, ldp, Ep, freqs, g, ld_g, g_col0, dXp, dEp, dfreqs_a
     lib = _lib.load()
     K = freqs.numel()
     scratch = plan.scratch(K, True)
-    check(lib.fsw_embed_backward(dtype_code(plan.dtype), ptr(Xp), ldp, ptr(Ep), ptr(plan.rowptr), plan.n_fixed,
-                                 ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
-                                 plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(g), ld_g, g_col0,
-                                 ptr(dXp), ptr(dEp), ptr(dfreqs_acc), None, plan.max_n_eff, ptr(scratch),
-                                 0 if scratch is None else scratch.numel(), ptr(ranks),
-                                 0 if ranks is None else ranks.stride(0), 1 if dxi_from_forward else 0,
-                                 ptr(transpose[0]) if transpose else None, ptr(transpose[1]) if transpose else None,
-                                 ptr(transpose[2]) if transpose else None, ptr(transpose[3]) if transpose else None,
-                                 int(nrows), stream_ptr(plan.device)),
-          "fsw_embed_backward")
+    _lib.call(plan.device, "fsw_embed_backward", dtype_code(plan.dtype), ptr(Xp), ldp, ptr(Ep), ptr(plan.rowptr), plan.n_fixed,
+              ptr(plan.col), ptr(plan.W), ptr(plan.mass), ptr(plan.info), ptr(plan.order),
+              plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(g), ld_g, g_col0,
+              ptr(dXp), ptr(dEp), ptr(dfreqs_acc), None, plan.max_n_eff, ptr(scratch),
+              0 if scratch is None else scratch.numel(), ptr(ranks),
+              0 if ranks is None else ranks.stride(0), 1 if dxi_from_forward else 0,
+              ptr(transpose[0]) if transpose else None, ptr(transpose[1]) if transpose else None,
+              ptr(transpose[2]) if transpose else None, ptr(transpose[3]) if transpose else None,
+              int(nrows), stream_ptr(plan.device))
 
 
 def total_mass_function(T, name):
@@ -165,6 +188,17 @@ def total_mass_function(T, name):
     raise RuntimeError("This should not happen")
 
 
+def total_mass_function_derivative(T, name):
+    """d/dT of total_mass_function."""
+    if name == "identity":
+        return torch.ones_like(T)
+    if name == "sqrt":   # 2 T / (sqrt(T+1) + 1) = 2 (sqrt(T+1) - 1)
+        return 1.0 / torch.sqrt(T + 1)
+    if name == "log":
+        return 1.0 / (1 + T)
+    raise RuntimeError("This should not happen")
+
+
 # Rank saving (see include/fsw_embedding.h, fsw_embed_forward): on by default, bounded by free memory.
 SAVE_RANKS = True
 RANK_MEMORY_FRACTION = 0.35
@@ -175,12 +209,14 @@ class FSWEmbedFunction(torch.autograd.Function):
 
     Forward: K1 projection(s) + K2 fused kernel.  Backward: K3 fused kernel + the three contractions
     dX = dXp.theta, dtheta = dXp^T.X, and the edge-feature analogues.
-    Inputs that are None: E_feat, bias, tm_scale.  `tm_function` None disables the total-mass channel
+    Inputs that are None: E_feat, bias, tm_scale, W_vals.  `tm_function` None disables the total-mass channel
     ('plain' method only; the homogeneous variants are composed in torch by the caller).
+    W_vals: the raw weights of the plan's elements (same values and order as plan.W) when their gradient is wanted,
+    else None - the kernels read plan.W either way; the argument only makes the weights a differentiable input.
     """
 
     @staticmethod
-    def forward(ctx, X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function):
+    def forward(ctx, X, projVecs, freqs, bias, tm_scale, E_feat, W_vals, plan, tm_function):
         d = X.shape[1]
         K = projVecs.shape[0]
         tm_dim = 0 if tm_function is None else 1
@@ -198,7 +234,9 @@ class FSWEmbedFunction(torch.autograd.Function):
         if bias is not None:
             bias = bias.contiguous()
             bias_core = bias[tm_dim:]
-        needs_grad = any(ctx.needs_input_grad[:6])
+        # under torch.no_grad() needs_input_grad is still True for parameters: ask the grad mode as well, so that evaluation
+        # runs the inference kernels and records nothing
+        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[:7])
         Ep = None
         if E_feat is not None:
             E_feat = E_feat.contiguous()
@@ -248,25 +286,28 @@ class FSWEmbedFunction(torch.autograd.Function):
         ctx.plan, ctx.tm_dim = plan, tm_dim
         ctx.has_E, ctx.has_bias, ctx.has_scale = E_feat is not None, bias is not None, tm_scale is not None
         ctx.Ep = Ep   # only with edge features (then there is a single chunk)
-        ctx.save_for_backward(X, projVecs, freqs, E_feat, fT)
+        ctx.tm_function = tm_function
+        ctx.save_for_backward(X, projVecs, freqs, E_feat, fT, tm_scale)
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        X, projVecs, freqs, E_feat, fT = ctx.saved_tensors
+        X, projVecs, freqs, E_feat, fT, tm_scale = ctx.saved_tensors
         plan, tm_dim = ctx.plan, ctx.tm_dim
-        need_X, need_theta, need_xi, need_bias, need_scale, need_E = ctx.needs_input_grad[:6]
+        need_X, need_theta, need_xi, need_bias, need_scale, need_E, need_W = ctx.needs_input_grad[:7]
         d = X.shape[1]
         K = projVecs.shape[0]
         if not (g.dim() == 2 and g.stride(1) == 1 and g.stride(0) >= g.shape[1]):
             g = g.contiguous()   # row-strided views (e.g. a column slice handed back by torch.cat) are read in place
-        dX = dtheta = dxi = dbias = dscale = dE = None
+        dX = dtheta = dxi = dbias = dscale = dE = dW = None
         if need_bias and ctx.has_bias:
             dbias = g.sum(dim=0)
         if need_scale and ctx.has_scale and tm_dim:
             dscale = (g[:, 0] * fT).sum()
-        if (need_X or need_theta or need_xi or (need_E and ctx.has_E)) and K > 0 and plan.S > 0:
-            exch = getattr(plan, "exchange", None)
+        exch = getattr(plan, "exchange", None)
+        # a rank that owns no destination rows still takes part in the exchange (its peers block in the collective)
+        if (need_X or need_theta or need_xi or (need_E and ctx.has_E)) and K > 0 and (plan.S > 0 or exch is not None):
             n_local = X.shape[0]
             if need_xi:
                 dxi = torch.empty(K, dtype=X.dtype, device=X.device)
@@ -324,7 +365,38 @@ class FSWEmbedFunction(torch.autograd.Function):
                 dtheta = torch.zeros_like(projVecs)
             if need_xi:
                 dxi = torch.zeros_like(freqs)
-        return dX, dtheta, dxi, dbias, dscale, dE, None, None
+        if need_W:
+            dW = weight_gradient(plan, ctx.chunks, ctx.Ep, freqs, g, tm_dim)
+            if tm_dim:
+                # total-mass channel f(T) * scale (fsw_embedding.py:857-868): d/dW_e = g[s, 0] * scale * f'(T_s)
+                T = plan.mass_as(X.dtype)
+                dchan = g[:, 0] * tm_scale * total_mass_function_derivative(T, ctx.tm_function)
+                dW = dW + plan.expand_to_elements(dchan)
+        return dX, dtheta, dxi, dbias, dscale, dE, dW, None, None
+
+
+def weight_gradient(plan, chunks, Ep, freqs, g, tm_dim):
+    """dL/dW (raw weights, [E]) of the core embedding: K3w accumulates the gradient w.r.t. the normalised weights over the
+    column chunks, then one pass applies the normalisation chain (include/fsw_embedding.h section 6b)."""
+    lib = _lib.load()
+    dev, dtype = plan.device, plan.dtype
+    dwn = torch.zeros(max(plan.E, 1), dtype=torch.float64, device=dev)
+    dwn_pad = torch.zeros(max(plan.S, 1), dtype=torch.float64, device=dev)
+    out = torch.zeros(plan.E, dtype=dtype, device=dev)
+    if plan.E == 0 or plan.S == 0:
+        return out
+    max_n = plan.max_n_eff   # >= the largest element count (n_eff = n + pad)
+    any_def = plan.any_deficient()
+    scratch = _ws(lib.fsw_embed_weight_grad_scratch_bytes(dtype_code(dtype), max_n), dev)
+    for (k0, k1, ldc, Xp, _ranks, _dxi) in chunks:
+        if k1 <= k0:
+            continue
+        _lib.call(dev, "fsw_embed_backward_weights", dtype_code(dtype), ptr(Xp), ldc, ptr(Ep), ptr(plan.rowptr), plan.n_fixed,
+                  ptr(plan.col), ptr(plan.W), ptr(plan.mass), plan.S, k1 - k0, ptr(freqs[k0:k1]), plan.thresh, 1 if any_def else 0,
+                  ptr(g), g.stride(0), tm_dim + k0, ptr(dwn), ptr(dwn_pad), max_n, ptr(scratch), scratch.numel(), stream_ptr(dev))
+    _lib.call(dev, "fsw_embed_weight_grad_finish", dtype_code(dtype), ptr(plan.rowptr), plan.n_fixed, ptr(plan.W), ptr(plan.mass),
+              plan.S, plan.thresh, 1 if any_def else 0, ptr(dwn), ptr(dwn_pad), ptr(out), stream_ptr(dev))
+    return out
 
 
 def column_chunks(K, n):
@@ -339,8 +411,10 @@ def column_chunks(K, n):
     return out or [(0, 0)]
 
 
-def fsw_embed(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function):
-    return FSWEmbedFunction.apply(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function)
+def fsw_embed(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function, W_vals=None):
+    if W_vals is not None and not W_vals.requires_grad:
+        W_vals = None
+    return FSWEmbedFunction.apply(X, projVecs, freqs, bias, tm_scale, E_feat, W_vals, plan, tm_function)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -355,6 +429,6 @@ def segcumsum_cuda(values, segment_ids, in_place=False):
     if n == 0:
         return out
     ws = _ws(lib.fsw_segcumsum_workspace_bytes(n), values.device)
-    check(lib.fsw_segcumsum(dtype_code(values.dtype), ptr(vin), ptr(out), ptr(segment_ids), segment_ids.element_size(), n,
-                            ptr(ws), ws.numel(), stream_ptr(values.device)), "fsw_segcumsum")
+    _lib.call(values.device, "fsw_segcumsum", dtype_code(values.dtype), ptr(vin), ptr(out), ptr(segment_ids),
+              segment_ids.element_size(), n, ptr(ws), ws.numel(), stream_ptr(values.device))
     return out

@@ -188,7 +188,7 @@ int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, co
  *        must be zero-initialised by the caller)
  *  dEp  [E, ldp] or NULL: same value per element (no atomics)
  *  dfreqs_acc [K] float64 or NULL: += dL/dxi_k (atomics; caller zero-initialises)
- *  dW   [E] or NULL: dL/dW (raw weights) - written, not accumulated
+ *  dW   must be NULL: the gradient w.r.t. the weights has its own entry points (section 6b)
  *  ranks [E, ldr] uint16 or NULL: positions recorded by fsw_embed_forward; with them the backward of the
  *        covered segments is a streaming pass without any sort, otherwise everything is re-sorted.
  *  dxi_from_forward != 0: the forward was given dxi_out, so the covered segments skip the frequency gradient.
@@ -203,6 +203,27 @@ int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, c
                        void* dXp, void* dEp, double* dfreqs_acc, void* dW, int64_t max_n_eff, void* scratch,
                        size_t scratch_bytes, const void* ranks, int64_t ldr, int dxi_from_forward, const int32_t* tptr,
                        const int32_t* tseg, const int32_t* tslot, const int32_t* tn, int64_t nrows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 6b. K3w: gradient with respect to the WEIGHTS of the multisets (ag.cumsum_sparse.backward fsw_embedding.py:2160-2172,
+ *     ag.div_sparse_dense :1656, deficit padding with custom_lowclamp :787-829, :1735-1744)
+ *  fsw_embed_backward_weights accumulates d L / d w (NORMALISED weights) of the slices [0, K) of this call into
+ *     dwn_acc [E] float64 and, for the pad element of a segment, dwn_pad_acc [S] float64 (both zero-initialised by the
+ *     caller; several calls - column chunks - may accumulate into the same buffers);
+ *  fsw_embed_weight_grad_finish pushes them through the normalisation and writes dW [E] (raw weights, `dtype`).
+ *  any_deficient != 0: some segment of the batch has total mass < thresh (the reference then pads every row, which
+ *     changes the gradient of the segments whose mass equals thresh exactly).
+ *  max_n: the largest number of elements of a segment.  scratch: fsw_embed_weight_grad_scratch_bytes(dtype, max_n)
+ *     (0 when every tile fits shared memory).  Xp / Ep / rowptr / n_fixed / col / W / mass / freqs / g as in section 6.
+ * ---------------------------------------------------------------------------------------------- */
+size_t fsw_embed_weight_grad_scratch_bytes(int dtype, int64_t max_n);
+int fsw_embed_backward_weights(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr, int64_t n_fixed,
+                               const int32_t* col, const void* W, const double* mass, int64_t S, int64_t K, const void* freqs,
+                               double thresh, int any_deficient, const void* g, int64_t ld_g, int64_t g_col0, double* dwn_acc,
+                               double* dwn_pad_acc, int64_t max_n, void* scratch, size_t scratch_bytes, void* stream);
+int fsw_embed_weight_grad_finish(int dtype, const int32_t* rowptr, int64_t n_fixed, const void* W, const double* mass, int64_t S,
+                                 double thresh, int any_deficient, const double* dwn_acc, const double* dwn_pad_acc, void* dW,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 7. Counters and per-kernel timers (the reference has only unused wall-clock globals,

@@ -227,17 +227,26 @@ def fsw_embed_csr_backward(X, rowptr, col, W, theta, xi, g, thresh=1.0, E_feat=N
     dEp = np.zeros((nE, K))
     dxi = np.zeros(K)
     dW = np.zeros(nE)
+    # the reference pads EVERY row once any row is deficient (fsw_embedding.py:790-807); the extra element has weight
+    # max(thresh - T, 0).  It changes no value, but for a row with T == thresh EXACTLY its low clamp is still 'active'
+    # (custom_lowclamp, :1735-1744: input >= thresh with input = thresh - T = 0), so the weight gradient of such a row
+    # sees the pad element
+    any_deficient = any((float(np.sum(np.asarray(W[int(rowptr[s]):int(rowptr[s + 1])], dtype=np.float64))) if W is not None
+                         else float(rowptr[s + 1] - rowptr[s])) < thresh for s in range(S))
     for s in range(S):
         lo, hi = int(rowptr[s]), int(rowptr[s + 1])
         n = hi - lo
         idx = np.arange(lo, hi) if col is None else np.asarray(col[lo:hi])
         Wseg = np.ones(n) if W is None else np.asarray(W[lo:hi], dtype=np.float64)
         T, w, padded = mass_pad_normalise(Wseg, thresh)
+        zero_pad = (not padded) and any_deficient and T == thresh and n > 0
+        if zero_pad:
+            w = np.concatenate([w, [0.0]])
         Sp = max(T, thresh)
         P = Xp[idx, :]
         if Ep is not None:
             P = P + Ep[lo:hi, :]
-        if padded:
+        if padded or zero_pad:
             P = np.concatenate([P, np.zeros((1, K))], axis=0)
         dw_total = np.zeros(P.shape[0])  # dL/dw (normalised weights, unsorted order)
         for k in range(K):
@@ -274,6 +283,9 @@ def fsw_embed_csr_backward(X, rowptr, col, W, theta, xi, g, thresh=1.0, E_feat=N
         if padded:
             # w_i = W_i/thresh, w_pad = (thresh - T)/thresh
             dW[lo:hi] = (dw_total[:n] - dw_total[n]) / thresh
+        elif zero_pad:
+            # w_i = W_i/T, w_pad = (thresh - T)/T with both clamps active at T == thresh
+            dW[lo:hi] = dw_total[:n] / Sp - float(np.dot(dw_total[:n], Wseg)) / (Sp * Sp) - dw_total[n] / Sp
         else:
             dW[lo:hi] = dw_total[:n] / Sp - float(np.dot(dw_total[:n], Wseg)) / (Sp * Sp)
     dX = dXp @ theta[:, :d]
@@ -354,10 +366,15 @@ def fsw_conv_forward(x, edge_index, params, cfg, edge_features=None):
         emb = np.concatenate([cfg.get("message_weight_vs_self", 1.0) * emb, x], axis=-1)
     if params.get("mlp"):
         h = emb
-        for (wt, b) in params["mlp"]:
+        nl = len(params["mlp"])
+        for li, (wt, b) in enumerate(params["mlp"]):
             h = h @ np.asarray(wt, dtype=np.float64).T
             if b is not None:
                 h = h + np.asarray(b, dtype=np.float64)
+            bn = params.get("bn_final") if li == nl - 1 else None
+            if bn is not None:
+                # BatchNorm1d in eval mode after the last Linear (fsw_conv.py:300-301): running statistics
+                h = (h - bn["mean"]) / np.sqrt(bn["var"] + bn.get("eps", 1e-5)) * bn["weight"] + bn["bias"]
             h = leaky_relu(h)
         return h
     if params.get("dim_reduct") is not None:

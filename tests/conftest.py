@@ -7,12 +7,32 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Print what the parity assertions measured (tests/parity.py) so that the GPU test record shows the deviations
+    and the reference's own fp32 noise floor, not just PASSED; also written to gpurun_out/parity_report.txt."""
+    import parity
+    if not parity.LOG:
+        return
+    terminalreporter.section("parity measurements (policy: tests/parity.py)")
+    for line in parity.LOG:
+        terminalreporter.write_line(line)
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.txt"), "w") as f:
+            f.write("\n".join(parity.LOG) + "\n")
+    except OSError:
+        pass
 
 
 def load_golden(name):

@@ -21,6 +21,7 @@ DENSE_CASES = {
     "emb_dense_deficient_tm": dict(encode_total_mass=True, total_mass_encoding_function="sqrt"),
     "emb_dense_n1": {},
     "emb_dense_big": {},
+    "emb_dense_homog_alt": dict(encode_total_mass=True, total_mass_encoding_method="homog_alt"),
 }
 
 
@@ -69,6 +70,20 @@ def test_dense_backward(name):
         np.testing.assert_allclose(r["dW"].reshape(g["dW_f64"].shape), g["dW_f64"], rtol=1e-8, atol=1e-9)
 
 
+def test_weight_gradient_at_exact_threshold():
+    """rows with total mass below, EXACTLY at and above the pad threshold in one batch: the reference pads every row once
+    one is deficient, and the row at the threshold then feels the (zero-weight) pad element in its weight gradient"""
+    g = load_golden("emb_dense_exact_thresh")
+    Xf, rowptr, col, W, bd, n, d = dense_inputs(g)
+    T = W.reshape(-1, n).sum(axis=1)
+    assert (T == 1.0).sum() >= 2 and (T < 1.0).any() and (T > 1.0).any()
+    out = O.fsw_embedding_forward(Xf, rowptr, col, W, emb_params(g), {})
+    np.testing.assert_allclose(out.reshape(g["out_f64"].shape), g["out_f64"], **TOL)
+    r = O.fsw_embed_csr_backward(Xf, rowptr, col, W, g["param_projVecs"], g["param_freqs"], g["gout"].reshape(-1, g["gout"].shape[-1]))
+    np.testing.assert_allclose(r["dW"].reshape(g["dW_f64"].shape), g["dW_f64"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r["dX"].reshape(g["dX_f64"].shape), g["dX_f64"], **TOL)
+
+
 def test_single_point_known_answer():
     g = load_golden("emb_dense_n1")
     X = g["X"]
@@ -81,6 +96,7 @@ GRAPH_CASES = {
     "emb_graph_unit": {},
     "emb_graph_weighted": dict(encode_total_mass=True, total_mass_encoding_function="log"),
     "emb_graph_homog": dict(encode_total_mass=True, total_mass_encoding_method="homog"),
+    "emb_graph_homog_alt": dict(encode_total_mass=True, total_mass_encoding_method="homog_alt", total_mass_encoding_function="sqrt"),
 }
 
 
@@ -116,6 +132,11 @@ def conv_params(g, prefix="param_"):
             break
         mlp.append((g[key], g.get(prefix + "mlp.%d.bias" % (2 * i))))
         i += 1
+    # batchNorm_final: the Sequential is Linear, act, ..., Linear, BatchNorm1d, act (fsw_conv.py:298-304)
+    bn_key = prefix + "mlp.%d.running_mean" % (2 * i - 1)
+    if i > 0 and bn_key in g:
+        b = prefix + "mlp.%d." % (2 * i - 1)
+        p["bn_final"] = dict(mean=g[b + "running_mean"], var=g[b + "running_var"], weight=g[b + "weight"], bias=g[b + "bias"])
     p["mlp"] = mlp
     p["dim_reduct"] = g.get(prefix + "dim_reduct")
     return p
@@ -137,6 +158,51 @@ def test_conv_forward(name):
     out = O.fsw_conv_forward(g["x"], g["edge_index"], conv_params(g), CONV_CASES[name],
                              edge_features=g.get("edge_features"))
     np.testing.assert_allclose(out, g["out_f64"], **TOL)
+
+
+ACCEPT_CASES = {
+    # test_conv.py:10-48
+    "conv_acceptance_testconv": (dict(encode_total_mass=True, total_mass_encoding_method="homog", total_mass_encoding_function="log",
+                                      self_loop_weight=0.2), "f64"),
+    # demo_conv.py:10-38 (fp32 in the demo: the oracle is compared with the reference in fp64 at the fp32-rounded point)
+    "conv_acceptance_democonv": (dict(encode_total_mass=True), "r64"),
+}
+
+
+@pytest.mark.parametrize("name", list(ACCEPT_CASES))
+def test_conv_acceptance_forward(name):
+    """the reference's own acceptance shapes (ER graph, 100 vertices, edge dim 11, 3 MLP layers)"""
+    g = load_golden(name)
+    cfg, tag = ACCEPT_CASES[name]
+    params = conv_params(g)
+    x, ef = g["x"], g["edge_features"]
+    if tag == "r64":   # inputs and parameters rounded to fp32, arithmetic in fp64
+        x, ef = x.astype(np.float32).astype(np.float64), ef.astype(np.float32).astype(np.float64)
+    out = O.fsw_conv_forward(x, g["edge_index"], params, cfg, edge_features=ef)
+    np.testing.assert_allclose(out, g["out_" + tag], **TOL)
+
+
+def test_demo_embedding_forward_and_weight_gradient():
+    """demo_fsw_embedding.py:10-25 (X [3,2,5,100,20], softmax weights, d_out = 1000): forward, dX and dW of the oracle
+    against the reference's fp64 arithmetic at the fp32-rounded point.  Softmax weights sum to 1 up to an ulp, so the batch
+    mixes padded rows (T < 1) and rows above the threshold: both branches of the normalisation chain occur."""
+    g = load_golden("emb_acceptance_demo")
+    X = g["X"].astype(np.float64)
+    W = g["W"].astype(np.float64)
+    bd = X.shape[:-2]
+    n, d = X.shape[-2:]
+    B = int(np.prod(bd))
+    rowptr, col = O.dense_to_csr(B, n)
+    theta, xi = g["param_projVecs"].astype(np.float64), g["param_freqs"].astype(np.float64)
+    Kc = 40   # a column subset keeps the pure-python oracle fast; outputs are independent per slice
+    out = O.fsw_embed_csr(X.reshape(B * n, d), rowptr, col, W.reshape(-1), theta[:Kc], xi[:Kc]) + g["param_bias"][:Kc].astype(np.float64)
+    np.testing.assert_allclose(out, g["out_r64"].reshape(B, -1)[:, :Kc], rtol=1e-9, atol=1e-10)
+    T = W.reshape(B, n).sum(axis=1)
+    assert (T < 1).any() and (T > 1).any()
+    # gradients need every slice: dX, dW of sum(gout * out) against the reference's autograd
+    r = O.fsw_embed_csr_backward(X.reshape(B * n, d), rowptr, col, W.reshape(-1), theta, xi, g["gout"].reshape(B, -1).astype(np.float64))
+    np.testing.assert_allclose(r["dX"].reshape(g["dX_r64"].shape), g["dX_r64"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(r["dW"].reshape(g["dW_r64"].shape), g["dW_r64"], rtol=1e-7, atol=1e-7)
 
 
 def test_readout_forward():
