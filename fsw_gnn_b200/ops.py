@@ -216,7 +216,7 @@ class FSWEmbedFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, X, projVecs, freqs, bias, tm_scale, E_feat, W_vals, plan, tm_function):
+    def forward(ctx, X, projVecs, freqs, bias, tm_scale, E_feat, W_vals, plan, tm_function, grad_mode=True):
         d = X.shape[1]
         K = projVecs.shape[0]
         tm_dim = 0 if tm_function is None else 1
@@ -234,9 +234,10 @@ class FSWEmbedFunction(torch.autograd.Function):
         if bias is not None:
             bias = bias.contiguous()
             bias_core = bias[tm_dim:]
-        # under torch.no_grad() needs_input_grad is still True for parameters: ask the grad mode as well, so that evaluation
-        # runs the inference kernels and records nothing
-        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[:7])
+        # under torch.no_grad() needs_input_grad is still True for parameters, and inside forward() grad mode is always
+        # off: the caller's grad mode is sampled before apply() (fsw_embed) so that evaluation runs the inference
+        # kernels and records nothing
+        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad[:7])
         Ep = None
         if E_feat is not None:
             E_feat = E_feat.contiguous()
@@ -372,7 +373,7 @@ class FSWEmbedFunction(torch.autograd.Function):
                 T = plan.mass_as(X.dtype)
                 dchan = g[:, 0] * tm_scale * total_mass_function_derivative(T, ctx.tm_function)
                 dW = dW + plan.expand_to_elements(dchan)
-        return dX, dtheta, dxi, dbias, dscale, dE, dW, None, None
+        return dX, dtheta, dxi, dbias, dscale, dE, dW, None, None, None
 
 
 def weight_gradient(plan, chunks, Ep, freqs, g, tm_dim):
@@ -414,7 +415,7 @@ def column_chunks(K, n):
 def fsw_embed(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function, W_vals=None):
     if W_vals is not None and not W_vals.requires_grad:
         W_vals = None
-    return FSWEmbedFunction.apply(X, projVecs, freqs, bias, tm_scale, E_feat, W_vals, plan, tm_function)
+    return FSWEmbedFunction.apply(X, projVecs, freqs, bias, tm_scale, E_feat, W_vals, plan, tm_function, torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------------------------------------

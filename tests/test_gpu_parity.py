@@ -638,10 +638,16 @@ def test_inference_path_equals_training_forward():
     torch.manual_seed(5)
     mod = FSW_embedding(d_in=d, d_out=K, device=dev(), dtype=torch.float32, learnable_slices=True, learnable_freqs=True)
     X = t(rng.standard_normal((N, d)), torch.float32)
-    out_train = mod.embed_plan(X.clone().requires_grad_(True), plan).detach()
+    out_t = mod.embed_plan(X.clone().requires_grad_(True), plan)
+    # the training forward must have recorded ranks (the sort-free backward depends on them) ...
+    fn = out_t.grad_fn
+    while fn is not None and not hasattr(fn, "chunks"):
+        fn = fn.next_functions[0][0] if fn.next_functions else None
+    assert fn is not None and all(ch[4] is not None for ch in fn.chunks), "training forward did not record ranks"
+    out_train = out_t.detach()
     with torch.no_grad():
         out_inf = mod.embed_plan(X, plan)
-    assert not out_inf.requires_grad
+    assert not out_inf.requires_grad and out_inf.grad_fn is None   # ... and evaluation records nothing
     torch.testing.assert_close(out_inf, out_train, rtol=1e-6, atol=1e-6)
     # dense batch, both paths
     Xd = t(rng.standard_normal((4, 300, d)), torch.float32)
