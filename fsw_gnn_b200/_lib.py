@@ -48,6 +48,8 @@ _SIGNATURES = {
     "fsw_plan_workspace_bytes": (c_sz, [c_i64]),
     "fsw_segment_plan": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "fsw_gemm": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp]),
+    "fsw_gemm_fused": (c_i32, [c_i32, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp]),
+    "fsw_set_tensor_cores": (c_i32, [c_i32]),
     "fsw_embed_scratch_bytes": (c_sz, [c_i32, c_vp, c_i64, c_i64, c_i32]),
     "fsw_embed_backward_extra_bytes": (c_sz, [c_i32, c_i64, c_i64]),
     "fsw_embed_forward": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64,

@@ -31,6 +31,13 @@ void fsw_count_launch(int n = 1);
 void fsw_prof_begin(const char* label, cudaStream_t st);
 void fsw_prof_end(cudaStream_t st);
 
+// tensor-core contraction (fsw_umma.cu); FSW_UMMA_NA: shapes / alignment not covered, the SIMT kernels take over
+#define FSW_UMMA_NA 1
+int fsw_umma_gemm(int op, int64_t M, int64_t N, int nseg, const int64_t* Kd, const float* const* A, const int64_t* lda,
+                  const float* const* B, const int64_t* ldb, float* C, int64_t ldc, const float* bias, int accumulate,
+                  cudaStream_t st);
+bool fsw_umma_enabled();
+
 static inline int64_t fsw_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- info word of the segment plan ----------------------------------------------------------------

@@ -7,6 +7,8 @@
 // register-tiled SIMT kernels: a full-width strip kernel for the shapes of the path (small dimension <= 200, fp32)
 // and a generic 128x64x16 kernel for everything else (fp64, odd strides).
 // A tcgen05 3xTF32 variant for large d_in is future work.
+#include <stdlib.h>
+
 #include "fsw_common.cuh"
 
 namespace {
@@ -511,6 +513,13 @@ int gemm_t(int op, int64_t M, int64_t N, int64_t Kd, const T* A, int64_t lda, co
         return FSW_OK;
     }
     if constexpr (sizeof(T) == 4) {
+        if (fsw_umma_enabled()) {
+            // large fp32 contractions: tcgen05 + TMA at fp32 accuracy (fsw_umma.cu)
+            const float* Ap = A;
+            const float* Bp = B;
+            const int urc = fsw_umma_gemm(op, M, N, 1, &Kd, &Ap, &lda, &Bp, &ldb, C, ldc, nullptr, accumulate, st);
+            if (urc != FSW_UMMA_NA) return urc;
+        }
         int rc = gemm_small_n_f32(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
         if (rc >= 0) return rc;
         rc = gemm_strip_f32(op, M, N, Kd, A, lda, B, ldb, C, ldc, accumulate, st);
@@ -538,6 +547,48 @@ int gemm_t(int op, int64_t M, int64_t N, int64_t Kd, const T* A, int64_t lda, co
 }
 
 }  // namespace
+
+namespace {
+bool g_umma_on = getenv("FSW_DISABLE_UMMA") == nullptr;
+
+__global__ void fsw_add_bias_kernel(float* C, int64_t ldc, const float* bias, int64_t M, int64_t N) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M * N) C[(i / N) * ldc + (i % N)] += bias[i % N];
+}
+}  // namespace
+
+bool fsw_umma_enabled() { return g_umma_on; }
+
+extern "C" int fsw_set_tensor_cores(int on) {
+    g_umma_on = on != 0;
+    return FSW_OK;
+}
+
+// C[M, N] (ldc) (+)= sum_s A_s . B_s^T (+ bias): the contraction axis is the concatenation of up to two segments, so that
+// cat(A_0, A_1) . W^T runs without materialising the concatenation (fsw_conv.py:357-361); fp32 only.
+extern "C" int fsw_gemm_fused(int dtype, int64_t M, int64_t N, int nseg, const int64_t* Kd, const void* const* A, const int64_t* lda,
+                              const void* const* B, const int64_t* ldb, void* C, int64_t ldc, const void* bias, int accumulate,
+                              void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != FSW_F32) return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_gemm_fused: fp32 only");
+    if (nseg < 1 || nseg > 2) return fsw_fail(FSW_ERR_INVALID, "fsw_gemm_fused: nseg %d", nseg);
+    if (M == 0 || N == 0) return FSW_OK;
+    if (g_umma_on) {
+        const int rc = fsw_umma_gemm(0, M, N, nseg, Kd, (const float* const*)A, lda, (const float* const*)B, ldb, (float*)C, ldc,
+                                     (const float*)bias, accumulate, st);
+        if (rc != FSW_UMMA_NA) return rc;
+    }
+    for (int s = 0; s < nseg; ++s) {
+        const int rc = gemm_t<float>(0, M, N, Kd[s], (const float*)A[s], lda[s], (const float*)B[s], ldb[s], (float*)C, ldc,
+                                     (accumulate || s > 0) ? 1 : 0, st);
+        if (rc != FSW_OK) return rc;
+    }
+    if (bias) {
+        fsw_add_bias_kernel<<<(unsigned)fsw_cdiv(M * N, 256), 256, 0, st>>>((float*)C, ldc, (const float*)bias, M, N);
+        FSW_CHECK_LAUNCH("fsw_add_bias_kernel");
+    }
+    return FSW_OK;
+}
 
 extern "C" int fsw_gemm(int dtype, int op, int64_t M, int64_t N, int64_t Kd, const void* A, int64_t lda, const void* B,
                         int64_t ldb, void* C, int64_t ldc, int accumulate, void* stream) {

@@ -106,13 +106,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- tcgen05.mma (kind::tf32, cta_group::1, A and B from shared memory) ------------------------------------
 // shared-memory matrix descriptor, 128-byte swizzle (tile base 1024-byte aligned):
 //   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
-//   [46,48) version = 1 (Blackwell), [61,64) layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   [46,48) version = 1 (Blackwell), [61,64) layout type: 2 = SWIZZLE_128B (16-byte chunks; K-major tf32 operands),
+//   1 = SWIZZLE_128B_BASE32B (32-byte chunks: the only layout the tensor core accepts for MN-major tf32 operands)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(layout_type & 7) << 61;
     return d;
 }
 // instruction descriptor: fp32 accumulate (bits [4,6) = 1), A/B format TF32 (= 2 at [7,10) and [10,13)),

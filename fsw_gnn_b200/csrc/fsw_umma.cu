@@ -1,0 +1,477 @@
+// K1 on the 5th-generation tensor cores: C (+)= A . B at fp32 accuracy with tcgen05.mma (kind::tf32), operands staged
+// by TMA, accumulators in tensor memory (north star subsystem 1; replaces the cuBLAS sgemm behind torch.tensordot,
+// fsw_embedding.py:911, and behind nn.Linear in FSW_conv, fsw_conv.py:361).
+//
+// fp32 accuracy from TF32 tensor cores: every fp32 operand tile is split in shared memory into hi = tf32(a) and
+// lo = tf32(a - hi) (22 of the 24 mantissa bits survive), and three products are issued per k-step:
+//     D_main += A_hi . B_hi          D_corr += A_hi . B_lo + A_lo . B_hi
+// into TWO accumulators in tensor memory that are added in the epilogue, so the 2^-11-times smaller correction terms
+// never ride through the rounding of the large accumulator.  The dropped A_lo . B_lo term is 2^-22 relative.
+//
+// One persistent CTA per SM, 14 warps:
+//   warp 0      TMA producer   global -> shared (128-byte swizzle), ring of 2 stages, mbarrier complete_tx
+//   warps 2-5   splitter       hi/lo split of the landed tiles in place (generic proxy) + fence.proxy.async
+//   warp 1      MMA issuer     one thread: 3 tcgen05.mma per k-step, tcgen05.commit releases the stage / publishes the tile
+//   warps 6-13  epilogue       tcgen05.ld -> registers (main + corr [+ bias]) -> swizzled staging -> TMA store / reduce-add
+// Modes: 0 = NT (A [M,Kd], B [N,Kd]: both K-major), 1 = NN (B [Kd,N]: MN-major), 2 = TN (A [Kd,M], B [Kd,N]: both MN-major,
+// the long contraction split over CTAs; the TMEM accumulators are drained into registers every UM_FLUSH k-blocks so that no
+// accumulation chain in the tensor core is longer than UM_FLUSH * 4 k-steps, partial tiles are reduced with TMA reduce-add).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "fsw_common.cuh"
+#include "fsw_sm100.cuh"
+
+namespace {
+using namespace sm100;
+
+constexpr int UM_BM = 128;       // UMMA M = rows of the output tile
+constexpr int UM_BK = 32;        // floats per k-block = 128 bytes = one swizzle span
+constexpr int UM_STAGES = 2;
+constexpr int UM_THREADS = 448;
+constexpr int UM_FLUSH = 16;     // TN: k-blocks per accumulation round
+constexpr uint32_t UM_A_BYTES = UM_BM * 128;
+constexpr uint32_t UM_STAGING = 2 * UM_A_BYTES;
+constexpr uint32_t UM_TMEM_COLS = 512;
+constexpr uint32_t UM_CORR_COL = 256;
+
+struct UmmaParams {
+    int M, N;
+    int nseg;
+    int nkb[2];
+    int kd[2];
+    int BN;    // UMMA N (multiple of 16, <= 256)
+    int BNL;   // rows (K-major) / columns (MN-major) of B staged per k-block
+    int mtiles, ntiles, splits, kb_per_split;
+    int accumulate;
+    const float* bias;
+    uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;   // descriptor strides (bytes) of the staged tiles
+    uint32_t dbg_idesc_xor, dbg_print;
+};
+
+struct WorkItem {
+    int mt, nt, kb0, kb1;
+};
+
+__device__ __forceinline__ WorkItem decode_item(const UmmaParams& p, int item) {
+    WorkItem w;
+    const int sp = item % p.splits;
+    const int t = item / p.splits;
+    w.nt = t % p.ntiles;
+    w.mt = t / p.ntiles;
+    const int total = p.nkb[0] + p.nkb[1];
+    w.kb0 = sp * p.kb_per_split;
+    w.kb1 = min(total, w.kb0 + p.kb_per_split);
+    return w;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__ CUtensorMap tB0,
+                const __grid_constant__ CUtensorMap tA1, const __grid_constant__ CUtensorMap tB1,
+                const __grid_constant__ CUtensorMap tC, const UmmaParams p) {
+    constexpr bool A_MN = (MODE == 2), B_MN = (MODE >= 1);
+    extern __shared__ uint8_t um_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)um_smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t bbytes = (uint32_t)p.BNL * 128u;
+    const uint32_t stage_bytes = 2 * UM_A_BYTES + 2 * bbytes;
+    uint8_t* staging = smem + UM_STAGES * stage_bytes;
+    uint64_t* bars = (uint64_t*)(staging + UM_STAGING);
+    uint64_t* full = bars;                 // [UM_STAGES] TMA landed
+    uint64_t* xfrm = bars + UM_STAGES;     // [UM_STAGES] hi/lo split done
+    uint64_t* empty = bars + 2 * UM_STAGES;  // [UM_STAGES] MMAs reading the stage completed
+    uint64_t* tfull = bars + 3 * UM_STAGES;  // accumulators of a round complete
+    uint64_t* tempty = tfull + 1;            // accumulators drained
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tA0);
+        tma_prefetch_desc(&tB0);
+        tma_prefetch_desc(&tA1);
+        tma_prefetch_desc(&tB1);
+        tma_prefetch_desc(&tC);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < UM_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&xfrm[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 256);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, UM_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int nitems = p.mtiles * p.ntiles * p.splits;
+    const int round_len = (MODE == 2) ? UM_FLUSH : (1 << 30);
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer ------------------------------------------------
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const WorkItem w = decode_item(p, item);
+                for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int seg = (kb >= p.nkb[0]) ? 1 : 0;
+                    const int kk = (kb - (seg ? p.nkb[0] : 0)) * UM_BK;
+                    const CUtensorMap* ta = seg ? &tA1 : &tA0;
+                    const CUtensorMap* tb = seg ? &tB1 : &tB0;
+                    uint8_t* st = smem + s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], UM_A_BYTES + bbytes);
+                    if (A_MN) {
+#pragma unroll
+                        for (int b = 0; b < UM_BM / 32; ++b) tma_load_2d(st + b * 4096, ta, w.mt * UM_BM + 32 * b, kk, &full[s]);
+                    } else {
+                        tma_load_2d(st, ta, kk, w.mt * UM_BM, &full[s]);
+                    }
+                    uint8_t* sb = st + 2 * UM_A_BYTES;
+                    if (B_MN) {
+                        for (int b = 0; b < p.BNL / 32; ++b) tma_load_2d(sb + b * 4096, tb, w.nt * p.BN + 32 * b, kk, &full[s]);
+                    } else {
+                        tma_load_2d(sb, tb, kk, w.nt * p.BN, &full[s]);
+                    }
+                    if (++s == UM_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer ---------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(UM_BM, p.BN, A_MN, B_MN) ^ p.dbg_idesc_xor;
+            int s = 0;
+            uint32_t ph = 0, tph = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const WorkItem w = decode_item(p, item);
+                for (int r0 = w.kb0; r0 < w.kb1; r0 += round_len) {
+                    const int r1 = min(w.kb1, (round_len > (1 << 29)) ? w.kb1 : r0 + round_len);
+                    mbar_wait(tempty, tph ^ 1);
+                    tc_fence_after();
+                    for (int kb = r0; kb < r1; ++kb) {
+                        mbar_wait(&full[s], ph);
+                        mbar_wait(&xfrm[s], ph);
+                        tc_fence_after();
+                        const int seg = (kb >= p.nkb[0]) ? 1 : 0;
+                        const int kk = (kb - (seg ? p.nkb[0] : 0)) * UM_BK;
+                        const int nks = (min(UM_BK, p.kd[seg] - kk) + 7) >> 3;
+                        const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
+                        const uint32_t a_lo = a_hi + UM_A_BYTES;
+                        const uint32_t b_hi = a_hi + 2 * UM_A_BYTES;
+                        const uint32_t b_lo = b_hi + bbytes;
+                        if (p.dbg_print && blockIdx.x == 0 && kb == w.kb0) {
+                            const float* fa = (const float*)(smem + s * stage_bytes);
+                            const float* fb = (const float*)(smem + s * stage_bytes + 2 * UM_A_BYTES);
+                            printf("idesc %08x nks %d A: %g %g %g %g | %g %g  B: %g %g %g %g | row1 %g %g | box1 %g %g\n", idesc, nks, fa[0], fa[1], fa[2], fa[3],
+                                   fa[32], fa[33], fb[0], fb[1], fb[2], fb[3], fb[32], fb[33], fb[1024], fb[1025]);
+                        }
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint32_t aoff = ks * p.a_kstep, boff = ks * p.b_kstep;
+                            const uint64_t dAh = umma_desc_sw128(a_hi + aoff, p.a_lbo, p.a_sbo, A_MN ? 1u : 2u);
+                            const uint64_t dAl = umma_desc_sw128(a_lo + aoff, p.a_lbo, p.a_sbo, A_MN ? 1u : 2u);
+                            const uint64_t dBh = umma_desc_sw128(b_hi + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 2u);
+                            const uint64_t dBl = umma_desc_sw128(b_lo + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 2u);
+                            const uint32_t acc = (kb == r0 && ks == 0) ? 0u : 1u;
+                            umma_tf32(tmem, dAh, dBh, idesc, acc);
+                            umma_tf32(tmem + UM_CORR_COL, dAh, dBl, idesc, acc);
+                            umma_tf32(tmem + UM_CORR_COL, dAl, dBh, idesc, 1u);
+                        }
+                        umma_commit(&empty[s]);
+                        if (++s == UM_STAGES) { s = 0; ph ^= 1; }
+                    }
+                    umma_commit(tfull);
+                    tph ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ------------------------------------------------ hi / lo split -------------------------------------------------
+        const int t = threadIdx.x - 64;
+        int s = 0;
+        uint32_t ph = 0;
+        const int nvec = (int)((2 * UM_A_BYTES + 2 * bbytes) / 32);   // float4 count of the A tile + the B tile
+        const int nvecA = UM_A_BYTES / 16;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const WorkItem w = decode_item(p, item);
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(&full[s], ph);
+                uint8_t* st = smem + s * stage_bytes;
+#pragma unroll 4
+                for (int i = t; i < nvec; i += 128) {
+                    // the A tile is followed by its lo tile, then the B tile and its lo tile
+                    float4* src = (i < nvecA) ? (float4*)st + i : (float4*)(st + 2 * UM_A_BYTES) + (i - nvecA);
+                    float4* dst = (i < nvecA) ? (float4*)(st + UM_A_BYTES) + i : (float4*)(st + 2 * UM_A_BYTES + bbytes) + (i - nvecA);
+                    const float4 v = *src;
+                    float4 hi, lo;
+                    hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+                    lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+                    *src = hi;
+                    *dst = lo;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&xfrm[s]);
+                if (++s == UM_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue -------------------------------------------------------
+        const int e = warp - 6;
+        const int q = warp & 3;          // TMEM lane quarter this warp may read
+        const int h = e >> 2;            // column-chunk parity served by this group of 4 warps
+        const int row = q * 32 + lane;
+        uint8_t* stg = staging + h * UM_A_BYTES;
+        const bool issuer = ((e & 3) == 0) && lane == 0;
+        const int nchunks = (p.BN + 31) >> 5;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t tph = 0;
+        float acc[2][32];
+        (void)acc;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const WorkItem w = decode_item(p, item);
+            if (w.kb0 >= w.kb1) continue;
+            const int m0 = w.mt * UM_BM, n0 = w.nt * p.BN;
+            if (MODE == 2) {
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[ci][i] = 0.f;
+            }
+            for (int r0 = w.kb0; r0 < w.kb1; r0 += round_len) {
+                mbar_wait(tfull, tph);
+                tph ^= 1;
+                tc_fence_after();
+                if (MODE == 2) {
+#pragma unroll
+                    for (int ci = 0; ci < 2; ++ci) {
+                        const int c = h + 2 * ci;
+                        if (c < nchunks) {
+                            uint32_t v[32], u[32];
+                            tmem_ld32(lane_addr + c * 32, v);
+                            tmem_ld32(lane_addr + UM_CORR_COL + c * 32, u);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) acc[ci][i] += __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(tempty);
+                } else {
+                    for (int c = h; c < nchunks; c += 2) {
+                        uint32_t v[32], u[32];
+                        tmem_ld32(lane_addr + c * 32, v);
+                        tmem_ld32(lane_addr + UM_CORR_COL + c * 32, u);
+                        tmem_ld_wait();
+                        float x[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                        if (p.bias != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = n0 + c * 32 + i;
+                                if (col < p.N) x[i] += __ldg(p.bias + col);
+                            }
+                        }
+                        if (issuer) tma_wait_group_read0();
+                        named_bar_sync(1 + h, 128);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *(float4*)(stg + row * 128 + ((j ^ (row & 7)) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + h, 128);
+                        if (issuer) {
+                            if (p.accumulate) tma_reduce_add_2d(&tC, stg, n0 + c * 32, m0);
+                            else tma_store_2d(&tC, stg, n0 + c * 32, m0);
+                            tma_commit_group();
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(tempty);
+                }
+            }
+            if (MODE == 2) {
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci) {
+                    const int c = h + 2 * ci;
+                    if (c < nchunks) {
+                        if (issuer) tma_wait_group_read0();
+                        named_bar_sync(1 + h, 128);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *(float4*)(stg + row * 128 + ((j ^ (row & 7)) << 4)) =
+                                make_float4(acc[ci][4 * j], acc[ci][4 * j + 1], acc[ci][4 * j + 2], acc[ci][4 * j + 3]);
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + h, 128);
+                        if (issuer) {
+                            tma_reduce_add_2d(&tC, stg, n0 + c * 32, m0);
+                            tma_commit_group();
+                        }
+                    }
+                }
+            }
+        }
+        if (issuer) tma_wait_group0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem, UM_TMEM_COLS);
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major tensor [outer, inner] with row pitch `ld` elements; box [box_outer, box_inner], 128-byte swizzle:
+// 16-byte chunks (K-major operands, the output), or 32-byte chunks for operands the tensor core reads MN-major
+bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+              bool mn_major = false) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+// C[M, N] (+)= sum over segments of A_s . B_s (+ bias), fp32, on the tensor cores.  Returns FSW_UMMA_NA when the shapes / alignments do
+// not qualify (the caller then runs the SIMT kernels), FSW_OK or an error code otherwise.
+//   op 0: A_s [M, Kd_s] (lda_s), B_s [N, Kd_s] (ldb_s)      op 1: B_s [Kd_s, N]      op 2: A [Kd, M], B [Kd, N] (one segment)
+int fsw_umma_gemm(int op, int64_t M, int64_t N, int nseg, const int64_t* Kd, const float* const* A, const int64_t* lda,
+                  const float* const* B, const int64_t* ldb, float* C, int64_t ldc, const float* bias, int accumulate,
+                  cudaStream_t st) {
+    if (op < 0 || op > 2 || nseg < 1 || nseg > 2 || (op == 2 && nseg != 1)) return FSW_UMMA_NA;
+    if (M >= (1LL << 31) || N >= (1LL << 31)) return FSW_UMMA_NA;
+    int64_t kd_total = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (!aligned16(A[s]) || !aligned16(B[s]) || (lda[s] & 3) || (ldb[s] & 3) || Kd[s] < 1 || Kd[s] >= (1LL << 31)) return FSW_UMMA_NA;
+        kd_total += Kd[s];
+    }
+    if (!aligned16(C) || (ldc & 3) || (bias && op == 2)) return FSW_UMMA_NA;
+    if (op == 2) {
+        if (kd_total < 4096 || M < 16 || N < 16) return FSW_UMMA_NA;
+    } else {
+        if (M < 2048 || N < 32 || kd_total < 32) return FSW_UMMA_NA;
+    }
+    if (get_encode() == nullptr) return FSW_UMMA_NA;
+
+    UmmaParams p{};
+    p.M = (int)M;
+    p.N = (int)N;
+    p.nseg = nseg;
+    for (int s = 0; s < 2; ++s) {
+        p.kd[s] = s < nseg ? (int)Kd[s] : 0;
+        p.nkb[s] = s < nseg ? (int)fsw_cdiv(Kd[s], UM_BK) : 0;
+    }
+    const int bn_max = (op == 2) ? 128 : 256;
+    if (N <= bn_max) {
+        p.BN = (int)((N + 15) / 16 * 16);
+        p.ntiles = 1;
+    } else {
+        p.BN = bn_max;
+        p.ntiles = (int)fsw_cdiv(N, bn_max);
+    }
+    p.BNL = (op >= 1) ? (p.BN + 31) / 32 * 32 : p.BN;
+    p.mtiles = (int)fsw_cdiv(M, UM_BM);
+    const int total_kb = p.nkb[0] + p.nkb[1];
+    const int sms = num_sms();
+    p.splits = 1;
+    p.kb_per_split = total_kb;
+    if (op == 2) {
+        const int tiles = p.mtiles * p.ntiles;
+        int splits = (2 * sms + tiles - 1) / tiles;
+        const int max_splits = (total_kb + UM_FLUSH - 1) / UM_FLUSH;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        int per = (total_kb + splits - 1) / splits;
+        per = (per + UM_FLUSH - 1) / UM_FLUSH * UM_FLUSH;
+        p.kb_per_split = per;
+        p.splits = (total_kb + per - 1) / per;
+    }
+    p.accumulate = (accumulate || op == 2) ? 1 : 0;
+    p.bias = bias;
+    // K-major tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart, one k-step = 32 bytes inside the row.
+    // MN-major tile: TMA boxes of [32 k-rows][128 bytes] (32-byte-chunk swizzle, atoms of 4 k-rows = 512 bytes); 32-element
+    // MN groups one box (4096 bytes) apart, one k-step = 8 rows = two atoms.
+    p.a_lbo = (op == 2) ? 4096u : 16u;  p.a_sbo = (op == 2) ? 512u : 1024u;  p.a_kstep = (op == 2) ? 1024u : 32u;
+    p.b_lbo = (op >= 1) ? 4096u : 16u;  p.b_sbo = (op >= 1) ? 512u : 1024u;  p.b_kstep = (op >= 1) ? 1024u : 32u;
+    if (const char* dbg = getenv("FSW_UMMA_DBG")) {   // debug: "a_lbo a_sbo a_kstep b_lbo b_sbo b_kstep"
+        unsigned v[6];
+        unsigned x = 0, pr = 0;
+        if (sscanf(dbg, "%u %u %u %u %u %u %x %u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &x, &pr) >= 6) {
+            p.a_lbo = v[0]; p.a_sbo = v[1]; p.a_kstep = v[2]; p.b_lbo = v[3]; p.b_sbo = v[4]; p.b_kstep = v[5];
+            p.dbg_idesc_xor = x; p.dbg_print = pr;
+        }
+    }
+
+    CUtensorMap tA[2], tB[2], tC;
+    for (int s = 0; s < 2; ++s) {
+        const int u = s < nseg ? s : 0;
+        bool ok;
+        if (op == 2) ok = make_map(&tA[s], A[u], (uint64_t)M, (uint64_t)Kd[u], (uint64_t)lda[u], 32, 32, true);
+        else ok = make_map(&tA[s], A[u], (uint64_t)Kd[u], (uint64_t)M, (uint64_t)lda[u], 32, UM_BM);
+        if (op >= 1) ok = ok && make_map(&tB[s], B[u], (uint64_t)N, (uint64_t)Kd[u], (uint64_t)ldb[u], 32, 32, true);
+        else ok = ok && make_map(&tB[s], B[u], (uint64_t)Kd[u], (uint64_t)N, (uint64_t)ldb[u], 32, (uint32_t)p.BNL);
+        if (!ok) return FSW_UMMA_NA;
+    }
+    if (!make_map(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, UM_BM)) return FSW_UMMA_NA;
+
+    const size_t smem = 1024 + (size_t)UM_STAGES * (2 * UM_A_BYTES + 2 * (size_t)p.BNL * 128) + UM_STAGING + 128;
+    const int nitems = p.mtiles * p.ntiles * p.splits;
+    const int grid = nitems < sms ? nitems : sms;
+    static const char* labels[3] = {"umma_nt", "umma_nn", "umma_tn"};
+#define FSW_UMMA_LAUNCH(MODE)                                                                                              \
+    do {                                                                                                                   \
+        FSW_CUDA(cudaFuncSetAttribute(fsw_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        fsw_prof_begin(labels[MODE], st);                                                                                  \
+        fsw_umma_kernel<MODE><<<grid, UM_THREADS, smem, st>>>(tA[0], tB[0], tA[1], tB[1], tC, p);                          \
+        fsw_prof_end(st);                                                                                                  \
+    } while (0)
+    if (op == 0) FSW_UMMA_LAUNCH(0);
+    else if (op == 1) FSW_UMMA_LAUNCH(1);
+    else FSW_UMMA_LAUNCH(2);
+#undef FSW_UMMA_LAUNCH
+    FSW_CHECK_LAUNCH("fsw_umma_kernel");
+    return FSW_OK;
+}

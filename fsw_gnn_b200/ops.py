@@ -135,6 +135,24 @@ def gemm(op, A, B, M, N, Kd, lda, ldb, out=None, ldc=None, accumulate=False):
     return out
 
 
+def gemm_fused(As, Bs, bias=None, out=None, accumulate=False):
+    """out[M, N] (+)= sum_s As[s] . Bs[s]^T (+ bias): the first Linear of FSW_conv over cat(emb, x) without the concatenated
+    copy (fsw_conv.py:357-361).  As[s] [M, Kd_s], Bs[s] [N, Kd_s] (row-strided views are fine); fp32."""
+    lib = _lib.load()
+    nseg = len(As)
+    M, N = As[0].shape[0], Bs[0].shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=As[0].dtype, device=As[0].device)
+    I64 = ctypes.c_int64 * nseg
+    VP = ctypes.c_void_p * nseg
+    for a, b in zip(As, Bs):
+        assert a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1] and a.shape[0] == M and b.shape[0] == N
+    _lib.call(out.device, "fsw_gemm_fused", dtype_code(out.dtype), M, N, nseg, I64(*[a.shape[1] for a in As]),
+              VP(*[a.data_ptr() for a in As]), I64(*[a.stride(0) for a in As]), VP(*[b.data_ptr() for b in Bs]),
+              I64(*[b.stride(0) for b in Bs]), ptr(out), out.stride(0), ptr(bias), 1 if accumulate else 0, stream_ptr(out.device))
+    return out
+
+
 def project(X, theta_part, ldp):
     """Xp[:, :K] = X . theta_part^T  (fsw_embedding.py:911).  X [N, d] contiguous; theta_part [K, d] view
     with row stride theta_part.stride(0).  Columns K..ldp-1 of the result are zero."""

@@ -152,6 +152,18 @@ int fsw_segment_plan(int dtype, const int32_t* rowptr, int64_t n_fixed, const vo
  * ---------------------------------------------------------------------------------------------- */
 int fsw_gemm(int dtype, int op, int64_t M, int64_t N, int64_t Kd, const void* A, int64_t lda, const void* B,
              int64_t ldb, void* C, int64_t ldc, int accumulate, void* stream);
+/* Large fp32 contractions (M >= 2048 rows, or a reduction over >= 4096 rows for op 2; 16-byte aligned operands, leading
+ * dimensions multiples of 4) run on the tensor cores: tcgen05.mma kind::tf32 on TMA-staged tiles with a hi/lo split of
+ * both operands (3 products per k-step, two TMEM accumulators) that keeps fp32 accuracy - csrc/fsw_umma.cu.  Everything
+ * else, and fp64, runs the FMA kernels.  fsw_set_tensor_cores(0) forces the FMA kernels (tests, A/B timing).
+ *
+ * fsw_gemm_fused: C[M, N] (+)= sum_{s < nseg} A_s . B_s^T (+ bias[N]), nseg in {1, 2}: the contraction axis is the
+ * concatenation of the segments, so FSW_conv's cat(emb, x) . W^T (fsw_conv.py:357-361) needs no concatenated copy:
+ * A_0 = emb [M, Kd_0], A_1 = x [M, Kd_1], B_0 = W[:, :Kd_0], B_1 = W[:, Kd_0:] (views, ldb = row pitch of W).  fp32. */
+int fsw_set_tensor_cores(int on);
+int fsw_gemm_fused(int dtype, int64_t M, int64_t N, int nseg, const int64_t* Kd, const void* const* A, const int64_t* lda,
+                   const void* const* B, const int64_t* ldb, void* C, int64_t ldc, const void* bias, int accumulate,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 5. K2: fused gather -> per-(segment, slice) sort -> cumulative weights -> Fourier -> reduce
