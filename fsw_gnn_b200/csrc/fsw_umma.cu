@@ -14,8 +14,9 @@
 //   warp 1      MMA issuer     one thread: 3 tcgen05.mma per k-step, tcgen05.commit releases the stage / publishes the tile
 //   warps 6-13  epilogue       tcgen05.ld -> registers (main + corr [+ bias]) -> swizzled staging -> TMA store / reduce-add
 // Modes: 0 = NT (A [M,Kd], B [N,Kd]: both K-major), 1 = NN (B [Kd,N]: MN-major), 2 = TN (A [Kd,M], B [Kd,N]: both MN-major,
-// the long contraction split over CTAs; the TMEM accumulators are drained into registers every UM_FLUSH k-blocks so that no
-// accumulation chain in the tensor core is longer than UM_FLUSH * 4 k-steps, partial tiles are reduced with TMA reduce-add).
+// the long contraction split over CTAs; the TMEM accumulators are drained into registers every UM_FLUSH_TN k-blocks, partial
+// tiles are reduced with TMA reduce-add).  Output tiles of up to 128 columns ping-pong between two accumulator stages in
+// tensor memory, so the epilogue of one tile / round runs under the MMAs of the next.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -29,11 +30,15 @@ constexpr int UM_BM = 128;       // UMMA M = rows of the output tile
 constexpr int UM_BK = 32;        // floats per k-block = 128 bytes = one swizzle span
 constexpr int UM_STAGES = 2;
 constexpr int UM_THREADS = 448;
-constexpr int UM_FLUSH = 16;     // TN: k-blocks per accumulation round
+// The tensor core adds into the fp32 accumulator with truncation (measured: a chain of 1024 k-steps of positive terms ends
+// 5.5e-5 low, 5.4e-8 per k-step), so no chain is longer than a round: the accumulators are drained after UM_FLUSH_TN
+// k-blocks (32 k-steps) in the long reductions of mode 2, after UM_FLUSH k-blocks (contraction length 512) otherwise.
+constexpr int UM_FLUSH_TN = 8;
+constexpr int UM_FLUSH = 16;
+constexpr uint32_t UM_ACC_STAGE_COLS = 256;
 constexpr uint32_t UM_A_BYTES = UM_BM * 128;
 constexpr uint32_t UM_STAGING = 2 * UM_A_BYTES;
 constexpr uint32_t UM_TMEM_COLS = 512;
-constexpr uint32_t UM_CORR_COL = 256;
 
 struct UmmaParams {
     int M, N;
@@ -47,6 +52,9 @@ struct UmmaParams {
     const float* bias;
     uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;   // descriptor strides (bytes) of the staged tiles
     uint32_t dbg_idesc_xor, dbg_print;
+    int round_len;        // k-blocks accumulated in tensor memory before the accumulators are drained
+    int nacc;             // accumulator stages in tensor memory (2 when BN <= 128: drain under the next round's MMAs)
+    uint32_t corr_col;    // column offset of the correction accumulator inside an accumulator stage
 };
 
 struct WorkItem {
@@ -80,9 +88,9 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
     uint64_t* full = bars;                 // [UM_STAGES] TMA landed
     uint64_t* xfrm = bars + UM_STAGES;     // [UM_STAGES] hi/lo split done
     uint64_t* empty = bars + 2 * UM_STAGES;  // [UM_STAGES] MMAs reading the stage completed
-    uint64_t* tfull = bars + 3 * UM_STAGES;  // accumulators of a round complete
-    uint64_t* tempty = tfull + 1;            // accumulators drained
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+    uint64_t* tfull = bars + 3 * UM_STAGES;  // [2] accumulators of a round complete
+    uint64_t* tempty = tfull + 2;            // [2] accumulators drained
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -98,8 +106,10 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
             mbar_init(&xfrm[s], 128);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tfull, 1);
-        mbar_init(tempty, 256);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 256);
+        }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, UM_TMEM_COLS);
@@ -109,7 +119,7 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
     const uint32_t tmem = *tmem_slot;
 
     const int nitems = p.mtiles * p.ntiles * p.splits;
-    const int round_len = (MODE == 2) ? UM_FLUSH : (1 << 30);
+    const int round_len = p.round_len;
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -148,13 +158,15 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(UM_BM, p.BN, A_MN, B_MN) ^ p.dbg_idesc_xor;
             int s = 0;
-            uint32_t ph = 0, tph = 0;
+            uint32_t ph = 0, aph = 0;
+            int as = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const WorkItem w = decode_item(p, item);
                 for (int r0 = w.kb0; r0 < w.kb1; r0 += round_len) {
-                    const int r1 = min(w.kb1, (round_len > (1 << 29)) ? w.kb1 : r0 + round_len);
-                    mbar_wait(tempty, tph ^ 1);
+                    const int r1 = min(w.kb1, r0 + round_len);
+                    mbar_wait(&tempty[as], aph ^ 1);
                     tc_fence_after();
+                    const uint32_t d_main = tmem + as * UM_ACC_STAGE_COLS, d_corr = d_main + p.corr_col;
                     for (int kb = r0; kb < r1; ++kb) {
                         mbar_wait(&full[s], ph);
                         mbar_wait(&xfrm[s], ph);
@@ -179,15 +191,15 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
                             const uint64_t dBh = umma_desc_sw128(b_hi + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 2u);
                             const uint64_t dBl = umma_desc_sw128(b_lo + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 2u);
                             const uint32_t acc = (kb == r0 && ks == 0) ? 0u : 1u;
-                            umma_tf32(tmem, dAh, dBh, idesc, acc);
-                            umma_tf32(tmem + UM_CORR_COL, dAh, dBl, idesc, acc);
-                            umma_tf32(tmem + UM_CORR_COL, dAl, dBh, idesc, 1u);
+                            umma_tf32(d_main, dAh, dBh, idesc, acc);
+                            umma_tf32(d_corr, dAh, dBl, idesc, acc);
+                            umma_tf32(d_corr, dAl, dBh, idesc, 1u);
                         }
                         umma_commit(&empty[s]);
                         if (++s == UM_STAGES) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(tfull);
-                    tph ^= 1;
+                    umma_commit(&tfull[as]);
+                    if (++as == p.nacc) { as = 0; aph ^= 1; }
                 }
             }
         }
@@ -230,8 +242,9 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
         uint8_t* stg = staging + h * UM_A_BYTES;
         const bool issuer = ((e & 3) == 0) && lane == 0;
         const int nchunks = (p.BN + 31) >> 5;
-        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t tph = 0;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t aph = 0;
+        int as = 0;
         float acc[2][32];
         (void)acc;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -245,9 +258,12 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
                     for (int i = 0; i < 32; ++i) acc[ci][i] = 0.f;
             }
             for (int r0 = w.kb0; r0 < w.kb1; r0 += round_len) {
-                mbar_wait(tfull, tph);
-                tph ^= 1;
+                mbar_wait(&tfull[as], aph);
                 tc_fence_after();
+                const uint32_t lane_addr = lane_base + as * UM_ACC_STAGE_COLS;
+                uint64_t* drained = &tempty[as];
+                if (++as == p.nacc) { as = 0; aph ^= 1; }
+                const bool first_round = (r0 == w.kb0);
                 if (MODE == 2) {
 #pragma unroll
                     for (int ci = 0; ci < 2; ++ci) {
@@ -255,24 +271,24 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
                         if (c < nchunks) {
                             uint32_t v[32], u[32];
                             tmem_ld32(lane_addr + c * 32, v);
-                            tmem_ld32(lane_addr + UM_CORR_COL + c * 32, u);
+                            tmem_ld32(lane_addr + p.corr_col + c * 32, u);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 32; ++i) acc[ci][i] += __uint_as_float(v[i]) + __uint_as_float(u[i]);
                         }
                     }
                     tc_fence_before();
-                    mbar_arrive(tempty);
+                    mbar_arrive(drained);
                 } else {
                     for (int c = h; c < nchunks; c += 2) {
                         uint32_t v[32], u[32];
                         tmem_ld32(lane_addr + c * 32, v);
-                        tmem_ld32(lane_addr + UM_CORR_COL + c * 32, u);
+                        tmem_ld32(lane_addr + p.corr_col + c * 32, u);
                         tmem_ld_wait();
                         float x[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + __uint_as_float(u[i]);
-                        if (p.bias != nullptr) {
+                        if (p.bias != nullptr && first_round) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const int col = n0 + c * 32 + i;
@@ -287,13 +303,14 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
                         fence_proxy_async_smem();
                         named_bar_sync(1 + h, 128);
                         if (issuer) {
-                            if (p.accumulate) tma_reduce_add_2d(&tC, stg, n0 + c * 32, m0);
+                            // later rounds of a long contraction add onto the first round's tile
+                            if (p.accumulate || !first_round) tma_reduce_add_2d(&tC, stg, n0 + c * 32, m0);
                             else tma_store_2d(&tC, stg, n0 + c * 32, m0);
                             tma_commit_group();
                         }
                     }
                     tc_fence_before();
-                    mbar_arrive(tempty);
+                    mbar_arrive(drained);
                 }
             }
             if (MODE == 2) {
@@ -421,16 +438,19 @@ int fsw_umma_gemm(int op, int64_t M, int64_t N, int nseg, const int64_t* Kd, con
     if (op == 2) {
         const int tiles = p.mtiles * p.ntiles;
         int splits = (2 * sms + tiles - 1) / tiles;
-        const int max_splits = (total_kb + UM_FLUSH - 1) / UM_FLUSH;
+        const int max_splits = (total_kb + UM_FLUSH_TN - 1) / UM_FLUSH_TN;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
         int per = (total_kb + splits - 1) / splits;
-        per = (per + UM_FLUSH - 1) / UM_FLUSH * UM_FLUSH;
+        per = (per + UM_FLUSH_TN - 1) / UM_FLUSH_TN * UM_FLUSH_TN;
         p.kb_per_split = per;
         p.splits = (total_kb + per - 1) / per;
     }
     p.accumulate = (accumulate || op == 2) ? 1 : 0;
     p.bias = bias;
+    p.round_len = (op == 2) ? UM_FLUSH_TN : UM_FLUSH;
+    p.nacc = (p.BN <= 128) ? 2 : 1;
+    p.corr_col = (p.BN <= 128) ? 128u : 256u;
     // K-major tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart, one k-step = 32 bytes inside the row.
     // MN-major tile: TMA boxes of [32 k-rows][128 bytes] (32-byte-chunk swizzle, atoms of 4 k-rows = 512 bytes); 32-element
     // MN groups one box (4096 bytes) apart, one k-step = 8 rows = two atoms.

@@ -7,7 +7,8 @@ Same constructor keywords, parameter names (`fsw_embed.*`, `mlp.*`, `dim_reduct`
 The graph preparation (edge list -> destination-major CSR + plan, K0) runs once per distinct
 edge_index and is shared by all layers through a small cache (the reference rebuilds a coalesced
 sparse adjacency on every forward, fsw_conv.py:352, :384-447); the neighbourhood embedding is the
-fused K1/K2/K3 path; the concat + MLP after it stay torch/cuBLAS.
+fused K1/K2/K3 path; the concat + Linear layers after it run the K1 contraction kernels with the concatenation
+fused into the first contraction; BatchNorm / activations / dropout stay torch modules.
 
 torch_geometric is optional: when it is installed the classes derive from MessagePassing and are
 registered in GraphGym under the reference's names ('fsw_conv', 'fsw_readout'); when it is not
@@ -186,15 +187,32 @@ class FSW_conv(_Base):
         return self._combine(emb, vertex_features)
 
     def _combine(self, emb, vertex_features):
-        """fsw_conv.py:357-369."""
+        """fsw_conv.py:357-369.  fp32: the concatenation is never materialised - the first Linear (or `dim_reduct`) contracts over
+        the columns of `emb` and of `vertex_features` in one K1 launch (tensor cores for large graphs), and the remaining Linear
+        layers run the same kernels; BatchNorm / activation / dropout stay torch modules.  fp64 keeps torch's matmul."""
+        from . import ops as _ops
+        fused = emb.dtype == torch.float32 and emb.is_cuda
+        parts = [emb]
         if self.concat_self:
             if self.message_weight_vs_self != 1.0:
                 emb = self.message_weight_vs_self * emb
-            emb = torch.cat((emb, vertex_features), dim=-1)
+            parts = [emb, vertex_features]
+        if not fused:
+            parts = [torch.cat(parts, dim=-1)] if len(parts) > 1 else parts
         if self.mlp is not None:
-            out = self.mlp(emb)
+            out = None
+            for mod in self.mlp:
+                if fused and isinstance(mod, torch.nn.Linear):
+                    out = _ops.linear_cat(parts if out is None else [out], mod.weight, mod.bias)
+                else:
+                    out = mod(parts[0] if out is None else out)
+            if out is None:   # an empty Sequential cannot occur (mlp_layers >= 1), kept for safety
+                out = parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
         elif self.concat_self:
-            out = torch.matmul(emb, self.dim_reduct.transpose(0, 1))
+            if fused:
+                out = _ops.linear_cat(parts, self.dim_reduct, None)
+            else:
+                out = torch.matmul(parts[0], self.dim_reduct.transpose(0, 1))
         else:
             out = emb
         if self.bn_final is not None:

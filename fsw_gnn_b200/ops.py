@@ -153,6 +153,59 @@ def gemm_fused(As, Bs, bias=None, out=None, accumulate=False):
     return out
 
 
+class FSWLinearFunction(torch.autograd.Function):
+    """out = cat(inputs, dim=1) . W^T + b without the concatenated copy (FSW_conv combine, fsw_conv.py:357-361), fp32.
+    Forward: one K1 launch with the contraction axis made of the inputs' column ranges.  Backward: d input_s = g . W[:, seg_s]
+    (op 1), dW[:, seg_s] = g^T . input_s (op 2), db = column sums of g."""
+
+    @staticmethod
+    def forward(ctx, W, b, *inputs):
+        inputs = tuple(x if (x.stride(1) == 1 and x.stride(0) % 4 == 0) else x.contiguous() for x in inputs)
+        widths = [x.shape[1] for x in inputs]
+        bounds = [0]
+        for w_ in widths:
+            bounds.append(bounds[-1] + w_)
+        Wc = W if W.stride(1) == 1 else W.contiguous()
+        segs = [Wc[:, bounds[i]:bounds[i + 1]] for i in range(len(inputs))]
+        M, N = inputs[0].shape[0], W.shape[0]
+        out = torch.empty((M, N), dtype=W.dtype, device=W.device)
+        # up to two segments per launch; more (never in FSW_conv) accumulate
+        for i in range(0, len(inputs), 2):
+            gemm_fused(list(inputs[i:i + 2]), segs[i:i + 2], bias=b if i == 0 else None, out=out, accumulate=(i > 0))
+        ctx.save_for_backward(Wc, *inputs)
+        ctx.bounds, ctx.has_bias = bounds, b is not None
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        Wc, *inputs = ctx.saved_tensors
+        bounds = ctx.bounds
+        if not (g.stride(1) == 1 and g.stride(0) % 4 == 0):
+            g = g.contiguous()
+        M, N = g.shape
+        dW = db = None
+        if ctx.needs_input_grad[0]:
+            dW = torch.zeros_like(Wc)
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            db = g.sum(dim=0)
+        dins = []
+        for i, x in enumerate(inputs):
+            k0, k1 = bounds[i], bounds[i + 1]
+            if ctx.needs_input_grad[2 + i]:
+                dins.append(gemm(1, g, Wc[:, k0:k1], M, k1 - k0, N, g.stride(0), Wc.stride(0)))
+            else:
+                dins.append(None)
+            if dW is not None:
+                gemm(2, g, x, N, k1 - k0, M, g.stride(0), x.stride(0), out=dW[:, k0:k1], ldc=dW.stride(0), accumulate=True)
+        return (dW, db) + tuple(dins)
+
+
+def linear_cat(inputs, weight, bias):
+    """nn.Linear over the column-wise concatenation of `inputs` (K1 kernels; fp32 CUDA tensors)."""
+    return FSWLinearFunction.apply(weight, bias, *inputs)
+
+
 def project(X, theta_part, ldp):
     """Xp[:, :K] = X . theta_part^T  (fsw_embedding.py:911).  X [N, d] contiguous; theta_part [K, d] view
     with row stride theta_part.stride(0).  Columns K..ldp-1 of the result are zero."""

@@ -156,3 +156,72 @@ def test_umma_long_contraction_error_growth():
     e_fma = float(((Cf.double() - ref) / ref).abs().max())
     LOG.append("umma NT Kd=8192 positive terms: max rel err tensor cores %.2e (mean signed %.2e), FMA kernels %.2e" % (e_tc, b_tc, e_fma))
     assert e_tc <= 2e-5
+
+
+@pytest.mark.parametrize("M", [300, 6000])
+@pytest.mark.parametrize("widths", [(200, 100), (127, 64), (72,)])
+def test_linear_cat_autograd_vs_torch_fp64(M, widths):
+    """FSW_conv combine: Linear over cat(inputs) with the concatenation fused into the contraction; value and all gradients
+    against torch in fp64 (small M: FMA kernels, large M: tensor cores)"""
+    from fsw_gnn_b200 import ops
+    g = torch.Generator(device=dev()); g.manual_seed(M + sum(widths))
+    N = 100
+    xs = [torch.randn(M, w, device=dev(), generator=g).requires_grad_(True) for w in widths]
+    W = (torch.randn(N, sum(widths), device=dev(), generator=g) / 10).requires_grad_(True)
+    b = torch.randn(N, device=dev(), generator=g).requires_grad_(True)
+    gout = torch.randn(M, N, device=dev(), generator=g)
+    out = ops.linear_cat(xs, W, b)
+    (out * gout).sum().backward()
+    xs64 = [x.detach().double().requires_grad_(True) for x in xs]
+    W64, b64 = W.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.linear(torch.cat(xs64, dim=1), W64, b64)
+    (ref * gout.double()).sum().backward()
+
+    def rel(a, r):
+        return float((a.double() - r).abs().max()) / max(float(r.abs().max()), 1e-30)
+    errs = dict(out=rel(out, ref), dW=rel(W.grad, W64.grad), db=rel(b.grad, b64.grad))
+    for i, (x, x64) in enumerate(zip(xs, xs64)):
+        errs["dx%d" % i] = rel(x.grad, x64.grad)
+    LOG.append("linear_cat M=%d widths=%s: max err / max|ref| %s" % (M, widths, {k: "%.1e" % v for k, v in errs.items()}))
+    assert all(v <= 3e-6 for v in errs.values()), errs
+
+
+def test_fsw_conv_large_graph_combine_runs_on_tensor_cores():
+    """an FSW_conv step on a graph large enough for the tensor-core path: K1 + combine launch the UMMA kernel, and the result
+    equals the FMA-kernel result to fp32 rounding"""
+    from fsw_gnn_b200 import FSW_conv, _lib
+    torch.manual_seed(1)
+    N, E, d = 6000, 60000, 64
+    conv = FSW_conv(d, d, device=dev())
+    x = torch.randn(N, d, device=dev())
+    ei = torch.randint(0, N, (2, E), device=dev())
+    lib = _lib.load()
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        for p_ in conv.parameters():
+            p_.grad = None
+        out = conv(xx, ei)
+        out.square().sum().backward()
+        return out.detach(), xx.grad, conv.mlp[0].weight.grad.clone(), conv.fsw_embed.projVecs.grad.clone()
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    a = run()
+    torch.cuda.synchronize()
+    rec = _lib.profile_read()
+    _lib.profile_enable(False)
+    assert "umma_nt" in rec and "umma_nn" in rec and "umma_tn" in rec, sorted(rec)
+    try:
+        lib.fsw_set_tensor_cores(0)
+        b = run()
+    finally:
+        lib.fsw_set_tensor_cores(1)
+    # the two projections differ in the last bits of the keys, so pairs of keys that agree to within an ulp may sort the other
+    # way round: the value is continuous there, the gradient of the two affected source rows is not (tests/parity.py, KEYS)
+    for name, u, v in zip(("out", "dx", "dW_mlp", "dtheta"), a, b):
+        d = (u - v).abs()
+        lim = 1e-6 + 1e-5 * v.abs() + 1e-5 * float(v.abs().max())
+        frac = float((d > lim).float().mean())
+        LOG.append("FSW_conv N=6000 tensor cores vs FMA kernels, %s: max diff / max %.2e, entries beyond tolerance %.4f%%"
+                   % (name, float(d.max()) / float(v.abs().max()), 100 * frac))
+        assert frac <= (0.0 if name == "out" else 2e-3), (name, frac)
