@@ -126,12 +126,27 @@ def label_buckets(label):
     return [base + b for b in range(lo, hi + 1)]
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from `ncu --set full` captures of one layer of
-# THIS workload at full size (profiles/r1/README.md names the report each number comes from); None = not captured.
-NCU_TRAFFIC_FULL_SCALE = {
-    "bwd_rankT_u32768_f32": 99.0e9,   # profiles/r1/ncu_r1f_rankT_fullscale.txt: 86.2 GB for the 53.6M edges of segments <= 128,
-                                    # scaled to the 61.5M edges served since the limit went to 512 elements
-}
+def ncu_traffic():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch, by kernel label, from the `ncu --set full` capture of
+    THIS binary at full size: profiles/r2/ncu_traffic.json, written by profiles/r2/ncu_traffic.py from the .ncu-rep that
+    profiles/r2/ncu_fullscale.sh records (one layer of configs[3]).  Absent file / label -> None."""
+    p = os.path.join(ROOT, "profiles", "r2", "ncu_traffic.json")
+    try:
+        return {k: float(v["dram_bytes_per_launch"]) for k, v in json.load(open(p))["kernels"].items()}
+    except Exception:
+        return {}
+
+
+def class_fill(label, plan):
+    """elements / sorting slots of a forward size class (the networks sort `size` slots per segment; the merge path has none)"""
+    parts = label.split("_")
+    bs = label_buckets(label)
+    if not bs or parts[1] not in ("small", "coop"):
+        return None
+    size = int(parts[2][1:])
+    segs = sum(plan.bucket_counts[b] for b in bs)
+    elems = sum(plan.bucket_elems[b] for b in bs)
+    return round(elems / max(segs * size, 1), 3)
 
 
 def algorithmic_bytes(label, plan, K):
@@ -154,6 +169,7 @@ def cpu_conv_step(sample_edges, seed=0):
     Linear/LeakyReLU part.  Returns (seconds, edges in the sample, threads)."""
     import numpy as np
     from oracle import c_oracle as C
+    C.set_threads()   # every host core, whatever OMP_NUM_THREADS the launcher exported (torchrun sets 1)
     rng = np.random.default_rng(seed)
     mean_deg = N_EDGE / N_VERT
     mu = np.log(mean_deg) - 0.5
@@ -185,6 +201,41 @@ def cpu_conv_step(sample_edges, seed=0):
     return dt, E * 1, C.threads()
 
 
+def reference_python_c2(steps=1):
+    """The UNMODIFIED reference (fsw_conv.py / fsw_embedding.py, torch on the host cores, load_custom_cuda_lib off) on
+    BASELINE.json configs[1]: FSW_conv(64, 64) fwd+bwd, N = 10k, E = 100k, fp32 - the largest configuration its
+    ~126 B per (edge, slice) of live memory lets it run whole.  Needs the git-ignored copy baseline/_ref/ (made by
+    __graft_entry__.build() where /root/reference exists); returns None when it is absent."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "fsw_conv.py")):
+        return None
+    try:
+        os.environ["FSW_REFERENCE_DIR"] = ref_dir
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        import ref_loader
+        emb_mod, conv_mod = ref_loader.load_reference()
+        emb_mod.fsw_embedding_produce_error_on_custom_library_loading_failure = False   # public switch (fsw_embedding.py:116)
+        torch.manual_seed(0)
+        conv = conv_mod.FSW_conv(64, 64, device="cpu", dtype=torch.float32)
+        emb_mod.libfsw_embedding = None   # CPU tensors: the reference's pure-torch segcumsum (its .so holds CUDA kernels only)
+        x = torch.randn(10000, 64, requires_grad=True)
+        ei = torch.randint(0, 10000, (2, 100000))
+        ts = []
+        for i in range(1 + steps):
+            x.grad = None
+            t0 = time.perf_counter()
+            conv(x, ei).square().sum().backward()
+            if i > 0:
+                ts.append(time.perf_counter() - t0)
+        t = sum(ts) / len(ts)
+        return {"value": 100000 / t, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": "configs[1] whole (N=10k, E=100k, d=64, K=127, one layer fwd+bwd), reference Python on the host cores, %.1f s per step after one warm-up" % t}
+    except Exception as e:   # the arm must never fail the bench
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's algorithm on the host cores (oracle port; the reference is a
     Python/torch program that cannot travel to the GPU box - DESIGN.md 'Reference arm')."""
@@ -211,6 +262,9 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    ref_py = reference_python_c2()
+    if ref_py is not None:
+        line["reference_python_c2"] = ref_py
     print(json.dumps(line))
 
 
@@ -366,7 +420,7 @@ def main():
     d2h = 4
 
     # ---- roofline of the dominant kernel: per-kernel CUDA-event timers of the library, separate pass ----
-    roofline = None
+    roofline = roofline_forward = None
     plan = graph.plan if world > 1 else cached_graph(ei_local, Nv, 0, "unit", 1.0, torch.float32)[1]
     _lib.profile_enable(True)
     nprof = 2
@@ -376,6 +430,7 @@ def main():
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     peaks, peak_kind = measured_peaks()
+    traffic = ncu_traffic()
     kern = {k: v for k, v in prof.items() if k.startswith(("fwd", "bwd"))}
     breakdown = {k: round(v[1] / nprof, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     if kern:
@@ -385,7 +440,7 @@ def main():
         ach = bytes_per_launch / (tot_ms / cnt * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"],
-                    "traffic": (NCU_TRAFFIC_FULL_SCALE.get(top) if (world == 1 and args.scale == 1.0) else None),
+                    "traffic": (traffic.get(top) if (world == 1 and args.scale == 1.0) else None),
                     "peak_source": peak_kind,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": tot_ms / cnt,
                     "share_of_step": (tot_ms / nprof) / ms_step}
@@ -394,6 +449,15 @@ def main():
         fb = sum(algorithmic_bytes(k, plan, K) * v[0] for k, v in fwd.items())
         ft = sum(v[1] for v in fwd.values()) * 1e-3
         roofline["fused_forward_all_classes"] = {"achieved": fb / ft / 1e9, "frac": fb / ft / 1e9 / peaks["hbm_gbs"]}
+        # the kernel family the north star sets its 70 % target on, as a roofline object of its own, with every size class
+        ftraffic = [traffic.get(k) for k in fwd]
+        roofline_forward = {"bound": "hbm", "kernel": "fused sort->cumsum->Fourier forward, all size classes (fwd*)",
+                            "achieved": fb / ft / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fb / ft / 1e9 / peaks["hbm_gbs"],
+                            "traffic": (sum(ftraffic) if ftraffic and all(t is not None for t in ftraffic) and world == 1 and args.scale == 1.0 else None),
+                            "ms_per_step": ft * 1e3 / nprof, "share_of_step": ft * 1e3 / nprof / ms_step,
+                            "classes": {k: {"ms_per_launch": v[1] / v[0], "GBps": algorithmic_bytes(k, plan, K) / (v[1] / v[0] * 1e-3) / 1e9,
+                                            "elements": int(sum(plan.bucket_elems[b] for b in label_buckets(k))),
+                                            "slot_fill": class_fill(k, plan)} for k, v in sorted(fwd.items())}}
 
     line = {
         "metric": METRIC, "value": E_total * N_LAYERS / (ms_step * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": args.steps,
@@ -406,10 +470,11 @@ def main():
                    "l2": "inputs (>= 1 GB per tensor) far exceed the 126 MB L2", "scale": args.scale},
         "clocks": clocks,
         "e2e": {"value": E_total * N_LAYERS / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "d2h_is": "the 4-byte loss of the training step (the step's only host-visible result)",
                 "includes": "H2D of edge_index, then of the vertex features (side stream, under K0) from pinned memory, graph preparation (K0: CSR, plan, transposition), fwd+bwd, D2H of the loss"},
         "gpu_launches": int(gpu_launches),
         "roofline": roofline,
+        "roofline_forward": roofline_forward,
         "kernel_ms_per_step": breakdown,
     }
 
@@ -455,9 +520,65 @@ def main():
             ms_c2 = a.elapsed_time(b) / 20
             extras["conv_c2"] = {"edges_per_s": 100000 / (ms_c2 * 1e-3), "ms_per_step": ms_c2,
                                  "config": "configs[1]: FSW_conv(64,64) fwd+bwd, N=10k, E=100k (launch-latency bound)"}
-    if world > 1:
-        # all ranks took part in the timed sections above; only rank 0 reports
-        pass
+        if rank == 0 and world == 1:
+            # C5: configs[4] - power-law graph, 1M vertices, one 100 000-edge hub, d_in = 256 -> d_out = 512 (K = 511 slices):
+            # the skewed segment sort and the tensor-core projection.  One FSW_embedding layer fwd+bwd through embed_plan.
+            from fsw_gnn_b200.ops import SegmentPlan
+            N5, d5 = 1_000_000, 256
+            g5 = torch.Generator(device=dev); g5.manual_seed(5)
+            u = torch.rand(N5, device=dev, generator=g5).clamp_(min=1e-9)
+            deg5 = torch.floor(u.pow(-1.0 / 1.1)).clamp_(1, 100000).to(torch.int64)
+            deg5[123] = 100000
+            rowptr5 = torch.zeros(N5 + 1, dtype=torch.int32, device=dev)
+            rowptr5[1:] = torch.cumsum(deg5, 0).to(torch.int32)
+            E5 = int(rowptr5[-1])
+            col5 = torch.randint(0, N5, (E5,), device=dev, generator=g5, dtype=torch.int32)
+            plan5 = SegmentPlan(N5, E5, rowptr5, 0, col5, None, 1.0, torch.float32, dev)
+            torch.manual_seed(5)
+            emb5 = FSW_embedding(d_in=d5, d_out=512, encode_total_mass=True, learnable_slices=True, learnable_freqs=True,
+                                 freqs_init="spread", minimize_slice_coherence=False, device=dev)
+            X5 = torch.randn(N5, d5, device=dev, generator=g5).requires_grad_(True)
+
+            def c5_step():
+                X5.grad = None
+                for p_ in emb5.parameters():
+                    p_.grad = None
+                emb5.embed_plan(X5, plan5).square().sum().backward()
+            for _ in range(2):
+                c5_step()
+            ms_c5 = timed(c5_step, 3)
+            _lib.profile_enable(True)
+            _lib.profile_read()
+            c5_step()
+            torch.cuda.synchronize()
+            p5 = _lib.profile_read()
+            _lib.profile_enable(False)
+            K5 = emb5.projVecs.shape[0]
+            flops5 = 2.0 * N5 * d5 * K5
+            tf32_peak = peaks.get("bf16_tflops_sustained", 1389.6) / 2.0
+            umma = {k: {"ms": round(v[1] / v[0], 4), "fp32_tflops": round(flops5 / (v[1] / v[0] * 1e-3) / 1e12, 1),
+                        "tensor_pipe_frac_of_tf32_peak": round(3 * flops5 / (v[1] / v[0] * 1e-3) / 1e12 / tf32_peak, 3)}
+                    for k, v in p5.items() if k.startswith("umma")}
+            extras["powerlaw_c5"] = {"edges_per_s": E5 / (ms_c5 * 1e-3), "ms_per_step": ms_c5, "edges": E5, "max_degree": int(deg5.max()),
+                                     "K1_tensor_cores": umma, "tf32_peak_tflops_assumed": tf32_peak,
+                                     "kernel_ms": {k: round(v[1], 3) for k, v in sorted(p5.items(), key=lambda kv: -kv[1][1])[:8]},
+                                     "config": "configs[4]: FSW_embedding(256, 512) graph mode fwd+bwd, N=1M vertices, power-law in-degrees "
+                                               "(Pareto 1.1, mean %.1f) with a 100 000-edge hub; K1 = 3xTF32 tcgen05 kernels, tensor-pipe "
+                                               "fraction = 3 x fp32 flops / time / (bf16_tflops_sustained / 2)" % (E5 / N5)}
+            del X5, plan5, emb5, col5
+            torch.cuda.empty_cache()
+            # Kseg: the standalone segmented scan behind segcumsum() (4 B read + 4 B written + 8 B of int64 segment id per element)
+            from fsw_gnn_b200.ops import segcumsum_cuda
+            nseg_el = 1 << 27
+            vals = torch.rand(nseg_el, device=dev)
+            ids = torch.repeat_interleave(torch.arange(nseg_el // 37 + 1, device=dev), 37)[:nseg_el].contiguous()
+            for _ in range(3):
+                segcumsum_cuda(vals, ids)
+            ms_seg = timed(lambda: segcumsum_cuda(vals, ids), 10)
+            extras["segcumsum_kseg"] = {"elements": nseg_el, "ms": ms_seg, "GBps": 16.0 * nseg_el / (ms_seg * 1e-3) / 1e9,
+                                        "frac_of_hbm_peak": 16.0 * nseg_el / (ms_seg * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                        "model": "4 B read + 4 B written + 8 B int64 id per element, fp32, segments of 37"}
+            del vals, ids
     if rank == 0 and world == 1 and not args.no_extras:
         dt, E_s, thr = cpu_conv_step(250_000, seed=0)  # warm
         dts = []
@@ -468,6 +589,9 @@ def main():
         line["cpu_baseline"] = {"value": E_s * N_LAYERS / t, "unit": "edges/s", "cores": thr, "kind": "port",
                                 "sample": "destination-row subsample with ~%d edges x %d layers per step (rows are independent), fp32, "
                                           "oracle/fsw_oracle.c (OpenMP) + numpy MLP; %.1f s per step" % (E_s, N_LAYERS, t)}
+        ref_py = reference_python_c2()
+        if ref_py is not None:
+            line["cpu_baseline"]["reference_python_c2"] = ref_py
     line["extra"] = extras
     if rank == 0:
         print(json.dumps(line))

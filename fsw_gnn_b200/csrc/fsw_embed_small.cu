@@ -15,6 +15,8 @@
 //     backward without any sorting: dL/dp_i = g (1+xi) A0(n) cos(pi xi (2 r_i + 1)/n) with r_i read back;
 //     streaming, one coalesced 128-byte row per element (red.add for graphs, plain store for dense
 //     batches); d/dxi from the same table pass.
+#include <stdlib.h>
+
 #include "fsw_sortnet.cuh"
 
 namespace {
@@ -845,8 +847,8 @@ struct FswPairBatch {
 };
 
 // V slices per lane: 4 (rows of up to 128 slices per warp) or 8 (up to 256: one warp per row for K = 199)
-template <int V, int U>
-__global__ void __launch_bounds__(128, 5) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
+template <int V, int U, int MINB, bool PF>
+__global__ void __launch_bounds__(128, MINB) fsw_rank_bwdT_kernel(SegArgs<float> a, int64_t Nrows, int nchunks,
                                                             const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
                                                             const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
                                                             const unsigned short* __restrict__ ranks, int64_t ldr,
@@ -861,17 +863,22 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdT_kernel(SegArgs<float> a,
     const int k0 = (chunk * 32 + lane) * V;
     if (k0 >= a.ldp) return;
     const int ldp = (int)a.ldp, ldri = (int)ldr;
-    float acc[V];
+    float2 acc2[V / 2], xi2[V / 2];
 #pragma unroll
-    for (int q = 0; q < V; ++q) acc[q] = 0.f;
+    for (int q = 0; q < V / 2; ++q) {
+        acc2[q] = make_float2(0.f, 0.f);
+        const int ka = k0 + 2 * q;
+        xi2[q] = make_float2(ka < a.K ? __ldg(a.freqs + ka) : 0.f, ka + 1 < a.K ? __ldg(a.freqs + ka + 1) : 0.f);
+    }
     const int t_beg = __ldg(tptr + j), t_end = __ldg(tptr + j + 1);
     const unsigned lanemask = __activemask();  // lanes beyond the padded row width have left
     const int nlanes = __popc(lanemask);       // active lanes are a prefix 0..nlanes-1
     const int step = nlanes >= U ? (nlanes & ~(U - 1)) : nlanes;
     const unsigned short* rbase = ranks + k0;
     const float* gbase = GA + k0;
-    const float2* ubase = tab_u + k0;
     int my_seg = 0, my_slot = 0, my_n = 0, cnt = 0;
+    const int kc0 = chunk * 32 * V;                                     // first slice of this warp's chunk
+    const int pf_bytes_r = PF ? min(ldp - kc0, 32 * V) * 2 : 0;         // bytes of a rank row inside the chunk (gradient row: twice)
 
     // ranks and gradients of the batch starting at triple t0 (loads only: issued one batch ahead of their use)
     auto load_batch = [&](int t0, FswPairBatch<U, P>& B) {
@@ -892,50 +899,64 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdT_kernel(SegArgs<float> a,
         }
     };
     // coefficients cos(pi (2r+1) xi / n) evaluated directly: a table lookup would scatter the 32 lanes of a warp over
-    // 32 cache lines (each lane has its own rank) and bind the kernel on L1 wavefronts.  The phase is formed in fp32
-    // from the double-float xi/n = hi + lo: (2r+1) hi is split exactly with an FMA.  Padding columns carry GA = 0
-    // and xi/n = 0, so whatever their (never written) ranks hold contributes exactly 0.
+    // 32 cache lines (each lane has its own rank) and bind the kernel on L1 wavefronts.  All of the arithmetic runs on PAIRS
+    // of slices with Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2: one issue slot for two slices) - the kernel
+    // is bound by issue slots, not by DRAM:
+    //   xi/n = uh + ul   double-float, from 1/n = ih + il (Newton residual), formed with negated constants so that no
+    //                    per-slice sign flip is needed (nul = -ul);
+    //   m = 2r+1         exact float through the mantissa trick, nm = -m by one FMA;
+    //   ph = m uh, npl = -(m ul + (m uh - ph))   phase = ph + pl in units of pi, |pl| ~ 1e-7 ph;
+    //   k = rint(ph) by the magic-number add, red = ph - k in [-1/2, 1/2], cos(pi ph) = (-1)^k cos(pi red): the parity
+    //   of k is the low mantissa bit of ph + 1.5 * 2^23 and is XORed into the sign of the gradient factor;
+    //   cos(pi x) on [-1/2, 1/2]: even Taylor polynomial up to x^12 (truncation < 1e-8), Horner in x^2.
+    // Padding columns carry GA = 0 and xi = 0, so whatever their (never written) ranks hold contributes exactly 0.
+    auto f2c = [](float c) { return make_float2(c, c); };
     auto consume = [&](const FswPairBatch<U, P>& B) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (B.nn[u] > 0) {
-                const bool tabled = B.nn[u] <= FSW_RANKT_TAB;   // warp-uniform
-                const float4* up = reinterpret_cast<const float4*>(ubase + fsw_rowoff(min(B.nn[u], FSW_RANKT_TAB) - 1, ldp));
+                const float nf = (float)B.nn[u];                   // exact: n <= 32768
+                const float ih = __frcp_rn(nf);
+                const float il = fmaf(-nf, ih, 1.0f) * ih;         // 1/n = ih + il
+                const float2 ih2 = f2c(ih), nih2 = f2c(-ih), nil2 = f2c(-il);
                 float v[V];
+                (void)v;
 #pragma unroll
-                for (int h = 0; h < P; ++h) {
-                    float uh[4], ul[4];
-                    if (tabled) {
-                        const float4 u01 = __ldg(up + 2 * h);
-                        const float4 u23 = __ldg(up + 2 * h + 1);
-                        uh[0] = u01.x, uh[1] = u01.z, uh[2] = u23.x, uh[3] = u23.z;
-                        ul[0] = u01.y, ul[1] = u01.w, ul[2] = u23.y, ul[3] = u23.w;
-                    } else {  // the few large segments: xi / n as a double-float pair on the fly, in fp32 arithmetic only
-                        const float nf = (float)B.nn[u];                  // exact: n <= 32768
-                        const float ih = __frcp_rn(nf);
-                        const float il = fmaf(-nf, ih, 1.0f) * ih;        // 1/n = ih + il (Newton residual)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int k = k0 + 4 * h + q;
-                            const float xq = (k < a.K) ? __ldg(a.freqs + k) : 0.f;
-                            uh[q] = xq * ih;
-                            ul[q] = fmaf(xq, il, fmaf(xq, ih, -uh[q]));
-                        }
-                    }
-                    const uint2 rk = B.rk[u][h];
-                    const unsigned m2[4] = {(rk.x & 0xffffu) * 2u + 1u, (rk.x >> 16) * 2u + 1u, (rk.y & 0xffffu) * 2u + 1u, (rk.y >> 16) * 2u + 1u};
-                    const float gq[4] = {B.ga[u][h].x, B.ga[u][h].y, B.ga[u][h].z, B.ga[u][h].w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        // 2r+1 -> float without an I2F: exact below 2^23 through the mantissa trick
-                        const float m = __uint_as_float(0x4B000000u | m2[q]) - 8388608.0f;
-                        const float ph = m * uh[q];
-                        const float pe = fmaf(m, uh[q], -ph);  // exact rounding error of the product
-                        const float pl = fmaf(m, ul[q], pe);
-                        const float hq = (0.5f * ph + 12582912.0f) - 12582912.0f;  // rint(ph / 2) without an FRND
-                        const float red = fmaf(hq, -2.0f, ph);                      // exact: ph reduced to [-1, 1]
-                        v[4 * h + q] = gq[q] * fsw_cospi_unit(red + pl);
-                        acc[4 * h + q] += v[4 * h + q];
+                for (int pr = 0; pr < V / 2; ++pr) {
+                    const float2 uh = __fmul2_rn(xi2[pr], ih2);
+                    const float2 nue = __ffma2_rn(xi2[pr], nih2, uh);          // -(xi ih - uh), exact
+                    const float2 nul = __ffma2_rn(xi2[pr], nil2, nue);         // -ul
+                    const uint2 rk = B.rk[u][pr >> 1];
+                    const unsigned w = (pr & 1) ? rk.y : rk.x;                 // two uint16 ranks
+                    const float2 mb = make_float2(__uint_as_float(0x4B000001u | ((w << 1) & 0x1fffeu)),
+                                                  __uint_as_float(0x4B000001u | ((w >> 15) & 0x1fffeu)));
+                    const float2 m = __fadd2_rn(mb, f2c(-8388608.0f));         // 2r+1, exact below 2^23
+                    const float2 nm = __ffma2_rn(mb, f2c(-1.0f), f2c(8388608.0f));
+                    const float2 ph = __fmul2_rn(m, uh);
+                    const float2 nqe = __ffma2_rn(nm, uh, ph);                 // ph - m uh, exact
+                    const float2 npl = __ffma2_rn(m, nul, nqe);                // -(m ul + m uh - ph)
+                    const float2 t = __fadd2_rn(ph, f2c(12582912.0f));
+                    const float2 kk = __fadd2_rn(t, f2c(-12582912.0f));        // rint(ph)
+                    const float2 red = __ffma2_rn(kk, f2c(-1.0f), ph);         // exact
+                    const float2 x = __ffma2_rn(npl, f2c(-1.0f), red);
+                    const float2 y2 = __fmul2_rn(x, x);
+                    float2 c = __ffma2_rn(y2, f2c(1.929574e-3f), f2c(-2.580689e-2f));
+                    c = __ffma2_rn(y2, c, f2c(2.353306e-1f));
+                    c = __ffma2_rn(y2, c, f2c(-1.335263f));
+                    c = __ffma2_rn(y2, c, f2c(4.058712f));
+                    c = __ffma2_rn(y2, c, f2c(-4.934802f));
+                    c = __ffma2_rn(y2, c, f2c(1.0f));
+                    const float4 g4 = B.ga[u][pr >> 1];
+                    const float g0 = (pr & 1) ? g4.z : g4.x, g1 = (pr & 1) ? g4.w : g4.y;
+                    const float2 gs = make_float2(__uint_as_float(__float_as_uint(g0) ^ (__float_as_uint(t.x) << 31)),
+                                                  __uint_as_float(__float_as_uint(g1) ^ (__float_as_uint(t.y) << 31)));
+                    if (dEp) {
+                        const float2 vv = __fmul2_rn(gs, c);
+                        v[2 * pr] = vv.x;
+                        v[2 * pr + 1] = vv.y;
+                        acc2[pr] = __fadd2_rn(acc2[pr], vv);
+                    } else {
+                        acc2[pr] = __ffma2_rn(gs, c, acc2[pr]);
                     }
                 }
                 if (dEp) {
@@ -954,6 +975,17 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdT_kernel(SegArgs<float> a,
             my_seg = __ldg(tseg + tb + lane);
             my_slot = __ldg(tslot + tb + lane);
             my_n = __ldg(tn + tb + lane);
+            // lane l pulls the rank row and the gradient row of pair l towards L2 now: the demand loads of load_batch, two
+            // pairs at a time, then find them there instead of paying a DRAM round trip each (more loads in flight
+            // without spending registers on them)
+            if (pf_bytes_r > 0) {
+                const char* rrow = reinterpret_cast<const char*>(ranks + fsw_rowoff(my_slot, ldri) + kc0);
+                const char* grow = reinterpret_cast<const char*>(GA + fsw_rowoff(my_seg, ldp) + kc0);
+                for (int off = 0; off < pf_bytes_r; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + pf_bytes_r - 1));
+                for (int off = 0; off < 2 * pf_bytes_r; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(grow + 2 * pf_bytes_r - 1));
+            }
         }
         FswPairBatch<U, P> A, B;
         load_batch(0, A);
@@ -969,7 +1001,8 @@ __global__ void __launch_bounds__(128, 5) fsw_rank_bwdT_kernel(SegArgs<float> a,
     }
     float* op = dXp + fsw_rowoff(j, ldp) + k0;
 #pragma unroll
-    for (int h = 0; h < P; ++h) reinterpret_cast<float4*>(op)[h] = make_float4(acc[4 * h], acc[4 * h + 1], acc[4 * h + 2], acc[4 * h + 3]);
+    for (int h = 0; h < P; ++h)
+        reinterpret_cast<float4*>(op)[h] = make_float4(acc2[2 * h].x, acc2[2 * h].y, acc2[2 * h + 1].x, acc2[2 * h + 1].y);
 }
 
 template <bool HAS_COL, bool NEED_DXI>
@@ -1152,10 +1185,20 @@ int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, int n
     const int64_t warps = Nrows * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
     fsw_prof_begin("bwd_rankT_u32768_f32", st);
-    if (wide)
-        fsw_rank_bwdT_kernel<8, 2><<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
-    else
-        fsw_rank_bwdT_kernel<4, 4><<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u);
+    // 4 CTAs per SM: 125 registers, no spills (5 CTAs at 96 registers spill inside the pair loop: 28.2 vs 22.9 ms per launch)
+    // L2 prefetch of every pair row of a block of triples: measured SLOWER (25.2 vs 22.9 ms per launch at configs[3]) - the
+    // kernel is not waiting on those loads; kept behind a knob for other shapes
+    static const bool pf = getenv("FSW_RANKT_PREFETCH") != nullptr;
+#define FSW_RANKT_LAUNCH(V_, U_, PF_) \
+    fsw_rank_bwdT_kernel<V_, U_, 4, PF_><<<(unsigned)blocks, 128, 0, st>>>(a, Nrows, nchunks, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp, tab_u)
+    if (wide) {
+        if (pf) FSW_RANKT_LAUNCH(8, 2, true);
+        else FSW_RANKT_LAUNCH(8, 2, false);
+    } else {
+        if (pf) FSW_RANKT_LAUNCH(4, 4, true);
+        else FSW_RANKT_LAUNCH(4, 4, false);
+    }
+#undef FSW_RANKT_LAUNCH
     fsw_prof_end(st);
     FSW_CHECK_LAUNCH("fsw_rank_bwdT_kernel");
     return FSW_OK;

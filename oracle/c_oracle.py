@@ -26,11 +26,21 @@ def load():
             for fn in ("project", "embed_forward", "embed_backward", "project_backward"):
                 getattr(_lib, "fsw_oracle_%s%s" % (fn, sfx)).restype = None
             getattr(_lib, "fsw_oracle_threads" + sfx).restype = ctypes.c_int
+            getattr(_lib, "fsw_oracle_set_threads" + sfx).argtypes = [ctypes.c_int]
+            getattr(_lib, "fsw_oracle_set_threads" + sfx).restype = None
     return _lib
 
 
 def threads():
     return int(load().fsw_oracle_threads_f64())
+
+
+def set_threads(n=None):
+    """use n OpenMP threads (default: every host core) whatever OMP_NUM_THREADS says"""
+    n = int(n or os.cpu_count() or 1)
+    load().fsw_oracle_set_threads_f64(n)
+    load().fsw_oracle_set_threads_f32(n)
+    return threads()
 
 
 def _p(a):
