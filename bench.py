@@ -116,7 +116,7 @@ def label_buckets(label):
         return [base + b for b in range(0, size + 1)]
     if parts[1] == "rankT":   # source-major rank backward: every uniform segment (up to 32768 elements)
         return [b for b in range(0, 517)]
-    if parts[1] == "coop":   # packed-key classes: two per power of two (3/4 and all of the slots)
+    if parts[1] in ("coop", "cloud"):   # packed-key classes: two per power of two (3/4 and all of the slots)
         coop = {48: (33, 48), 64: (49, 64), 96: (65, 96), 128: (97, 128), 192: (129, 192), 256: (193, 256), 384: (257, 384),
                 512: (385, 512), 1024: (513, 513)}
         lo, hi = coop.get(size, (516, 516))

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfsw_embedding.so")
-SOURCES = ["fsw_api.cu", "fsw_umma.cu", "fsw_prep.cu", "fsw_gemm.cu", "fsw_segcumsum.cu", "fsw_embed.cu", "fsw_embed_medium.cu", "fsw_embed_small.cu", "fsw_embed_packed.cu", "fsw_wgrad.cu"]
+SOURCES = ["fsw_api.cu", "fsw_umma.cu", "fsw_prep.cu", "fsw_gemm.cu", "fsw_segcumsum.cu", "fsw_embed.cu", "fsw_embed_medium.cu", "fsw_embed_small.cu", "fsw_embed_packed.cu", "fsw_wgrad.cu", "fsw_cloud.cu"]
 NVCC_FLAGS = ["-std=c++17", "--expt-relaxed-constexpr", "-O3", "-lineinfo",
               "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
 

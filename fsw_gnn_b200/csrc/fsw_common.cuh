@@ -158,6 +158,14 @@ struct SegArgs {
     int64_t n_fixed;
     int K;
     double thresh;
+    // point-cloud mode (dense batches of low-dimensional points, fsw_embed_forward_cloud): the packed-key forward forms the keys
+    // <x_e, theta_k> on the fly from the points instead of reading a projected matrix, and records the ranks slice-major
+    // [S][K][n] so that its stores and the backward's loads are contiguous
+    const T* projX = nullptr;       // [S * n, proj_d] points (Xp is not read)
+    const T* projTheta = nullptr;   // [K, proj_ldt] slices
+    int proj_d = 0;
+    int64_t proj_ldt = 0;
+    int rank_transposed = 0;
 };
 
 // medium / large path (fsw_embed_medium.cu): uniform-weight fp32 segments of more than 64 elements

@@ -732,6 +732,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                         continue;
                     }
                 }
+                if (a.projX != nullptr) return fsw_fail(FSW_ERR_UNSUPPORTED, "point-cloud mode: only the packed-key classes (33..1024 points) form keys on the fly");
                 int rc = fsw_small_forward_u<T>(a, c.np, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, st);
                 if (rc) return rc;
             }
@@ -740,6 +741,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 if (c.np > msn) continue;
                 const int lo = bo[base + c.lo], hi = bo[base + c.hi + 1];
                 if (hi <= lo) continue;
+                if (a.projX != nullptr) return fsw_fail(FSW_ERR_UNSUPPORTED, "point-cloud mode needs uniform weights and total mass >= the pad threshold");
                 int rc = dispatch_fwd_small<T, false>(a, c.np, lo, hi, out, ld_out, out_col0, bias, st);
                 if (rc) return rc;
             }
@@ -767,6 +769,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                     if (rc) return rc;
                     continue;
                 }
+                if (a.projX != nullptr) return fsw_fail(FSW_ERR_UNSUPPORTED, "point-cloud mode: segment class %d is not served by the packed-key kernels", cap);
                 if (kind == 0 && cap >= 128) {  // medium / large path: uniform weights, more than 128 elements
                     int rc = fsw_medium_forward_f32(a, lo, hi, cap, out, ld_out, out_col0, bias, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, nullptr, nullptr, st);
                     if (rc) return rc;
@@ -1016,6 +1019,29 @@ extern "C" int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const v
         return embed_forward_t<double>(a, bucket_offsets_host, (double*)out, ld_out, out_col0, (const double*)bias, max_n_eff, scratch, scratch_bytes, (unsigned short*)ranks_out, ldr, (double*)dxi_out, ld_dxi, st);
     }
     return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward: dtype %d", dtype);
+}
+
+// Point-cloud mode of the forward (include/fsw_embedding.h section 5b): dense batch of S multisets of n points each, unit
+// weights, d <= 4: keys formed on the fly from the points, ranks recorded slice-major.
+extern "C" int fsw_embed_forward_cloud(int dtype, const void* X, int64_t d, const void* theta, int64_t ldt, int64_t n,
+                                       const double* mass, const int32_t* info, const int32_t* order,
+                                       const int32_t* bucket_offsets_host, int64_t S, int64_t K, const void* freqs, double thresh,
+                                       void* out, int64_t ld_out, int64_t out_col0, const void* bias, void* scratch,
+                                       size_t scratch_bytes, void* ranksT_out, void* dxi_out, int64_t ld_dxi, void* stream) {
+    if (S == 0 || K == 0) return FSW_OK;
+    if (dtype != FSW_F32) return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_embed_forward_cloud: fp32 only");
+    if (!X || !theta || !mass || !info || !bucket_offsets_host || !freqs || !out)
+        return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward_cloud: null argument");
+    if (d < 1 || d > 4 || n < 33 || n > 1024)
+        return fsw_fail(FSW_ERR_INVALID, "fsw_embed_forward_cloud: needs 1 <= d <= 4 and 33 <= n <= 1024 (got d=%lld n=%lld)", (long long)d, (long long)n);
+    auto a = make_args<float>(X, d, nullptr, nullptr, n, nullptr, nullptr, mass, info, order, freqs, K, thresh);
+    a.projX = (const float*)X;
+    a.projTheta = (const float*)theta;
+    a.proj_d = (int)d;
+    a.proj_ldt = ldt;
+    a.rank_transposed = 1;
+    return embed_forward_t<float>(a, bucket_offsets_host, (float*)out, ld_out, out_col0, (const float*)bias, n, scratch, scratch_bytes,
+                                  (unsigned short*)ranksT_out, 0, (float*)dxi_out, ld_dxi, (cudaStream_t)stream);
 }
 
 extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,

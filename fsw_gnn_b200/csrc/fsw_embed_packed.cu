@@ -147,7 +147,7 @@ __device__ __forceinline__ void fsw_store_ranks(unsigned short* dst, const int* 
         x = lo_;                 \
     }
 
-template <int R, int L, bool HAS_COL, bool SAVE_RANK>
+template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool CLOUD>
 __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
     SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks, float* __restrict__ out, int64_t ld_out, int64_t out_col0,
     const float* __restrict__ bias, unsigned short* __restrict__ ranks, int64_t ldr, float* __restrict__ dxi_out, int64_t ld_dxi,
@@ -197,6 +197,25 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
     const float* tck = gtab_c + (int64_t)(g * (R / 4)) * tstride + kk * 4;
     const float* ttk = gtab_t + (int64_t)(g * (R / 4)) * tstride + kk * 4;
 
+    // point-cloud mode: the slices this lane projects onto (theta rows k0 + part .. + VW - 1), kept in registers
+    // (a separate template instance: the registers and branches of this mode cost the graph kernels 12 % when they shared one)
+    constexpr bool cloud = CLOUD;
+    float th[CLOUD ? VW : 1][4];
+#pragma unroll
+    for (int j = 0; j < (CLOUD ? VW : 1); ++j)
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) th[j][dd] = 0.f;
+    if constexpr (CLOUD) {
+        const int part0 = (lane % LPR) * VW;
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {
+            const int ks = min(k0 + part0 + j, a.K - 1);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd)
+                if (dd < a.proj_d) th[j][dd] = __ldg(a.projTheta + fsw_rowoff(ks, a.proj_ldt) + dd);
+        }
+    }
+
     // software pipeline over segments: order two ahead, row range one ahead, column ids one ahead
     PkMeta cur, nx1;
     int s2;
@@ -226,7 +245,22 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
             float v[VW];
             int row = 0;
             if (HAS_COL) row = (LPR == 1) ? c[t] : __shfl_sync(FSW_FULL, c[(t * RPI) >> 5], ((t * RPI) & 31) + lane / LPR);
-            if (e < n) {
+            if (CLOUD && e < n) {
+                // keys on the fly: <x_e, theta_k>, same FMA order as the projection kernel (fsw_project_small_kernel), so the
+                // keys are bit-identical to a materialised projection; the point rows are read contiguously
+                const float* xr = a.projX + fsw_rowoff(cur.e0 + e, a.proj_d);
+                float x[4];
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd) x[dd] = dd < a.proj_d ? __ldg(xr + dd) : 0.f;
+#pragma unroll
+                for (int j = 0; j < VW; ++j) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int dd = 0; dd < 4; ++dd)
+                        if (dd < a.proj_d) acc = fmaf(x[dd], th[CLOUD ? j : 0][dd], acc);
+                    v[j] = acc + 0.0f;
+                }
+            } else if (e < n) {
                 const int64_t r64 = HAS_COL ? (int64_t)row : cur.e0 + e;
                 fsw_ldg_words<VW>(xp0 + fsw_rowoff(r64, ldp) + part, v);
                 if (ep0 != nullptr) {  // edge features: per-slot additive projection (rare path)
@@ -458,11 +492,26 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
         }
         __syncwarp();
         if constexpr (SAVE_RANK) {
-            // row-wise again: lane l writes the SW ranks of elements 32 t + l with one vector store
+            if (CLOUD) {
+                // slice-major ranks [S][K][n]: consecutive lanes store consecutive elements of one slice
 #pragma unroll
-            for (int t = 0; t < NC; ++t) {
-                const int e = t * 32 + lane;
-                if (e < n) fsw_store_ranks<SW>(ranks + fsw_rowoff(cur.e0 + e, ldr) + k0, reinterpret_cast<const int*>(fkw) + e * SW);
+                for (int j = 0; j < SW; ++j) {
+                    if (k0 + j < a.K) {
+                        unsigned short* rt = ranks + ((int64_t)cur.s * a.K + (k0 + j)) * n;
+#pragma unroll
+                        for (int t = 0; t < NC; ++t) {
+                            const int e = t * 32 + lane;
+                            if (e < n) rt[e] = (unsigned short)reinterpret_cast<const int*>(fkw)[e * SW + j];
+                        }
+                    }
+                }
+            } else {
+                // row-wise again: lane l writes the SW ranks of elements 32 t + l with one vector store
+#pragma unroll
+                for (int t = 0; t < NC; ++t) {
+                    const int e = t * 32 + lane;
+                    if (e < n) fsw_store_ranks<SW>(ranks + fsw_rowoff(cur.e0 + e, ldr) + k0, reinterpret_cast<const int*>(fkw) + e * SW);
+                }
             }
             __syncwarp();  // the next segment's gather overwrites the slots
         }
@@ -503,7 +552,7 @@ __global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* 
     }
 }
 
-template <int R, int L, bool HAS_COL, bool SAVE_RANK>
+template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool CLOUD = false>
 int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_out, int64_t out_col0, const float* bias,
                     unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
                     int tab_n0, int tab_ld4, cudaStream_t st) {
@@ -516,9 +565,9 @@ int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t
     constexpr int WPB = 4;
     const int64_t blocks = fsw_cdiv(warps, WPB);
     const size_t smem = (size_t)WPB * R * 32 * sizeof(float);
-    auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK>;
+    auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK, CLOUD>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static const std::string label = std::string(SAVE_RANK ? "fwdr_coop_u" : "fwd_coop_u") + std::to_string(R * L) + "_f32";  // R x L slots
+    static const std::string label = std::string(SAVE_RANK ? "fwdr_" : "fwd_") + (CLOUD ? "cloud_u" : "coop_u") + std::to_string(R * L) + "_f32";  // R x L slots
     fsw_prof_begin(label.c_str(), st);
     kern<<<(unsigned)blocks, WPB * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4);
     fsw_prof_end(st);
@@ -531,6 +580,11 @@ int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_
                 unsigned short* ranks, int64_t ldr, float* dxi_out, int64_t ld_dxi, const float* gtab_c, const float* gtab_t,
                 int tab_n0, int tab_ld4, cudaStream_t st) {
     const bool has_col = a.col != nullptr;
+    if (a.projX != nullptr) {   // point-cloud mode: dense batches only, keys formed on the fly
+        if (has_col) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: point-cloud mode needs a dense batch");
+        return ranks ? launch_coop_fwd<R, L, false, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
+                     : launch_coop_fwd<R, L, false, false, true>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+    }
     if constexpr (R * L > 512) {
         // more than 512 slots: dense batches only (a column-id register per 32 slots would not fit)
         if (has_col) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: %d slots need a dense batch", R * L);

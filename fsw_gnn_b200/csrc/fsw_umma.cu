@@ -27,17 +27,23 @@ namespace {
 using namespace sm100;
 
 constexpr int UM_BM = 128;       // UMMA M = rows of the output tile
-constexpr int UM_BK = 32;        // floats per k-block = 128 bytes = one swizzle span
-constexpr int UM_STAGES = 2;
+// k-blocks of 16 floats (two k-steps): half-size stages, twice as many of them in the same shared memory - the kernel is
+// bound by the TMA -> split -> MMA latency chain of a stage, not by bytes (measured: 2 stages of 32 floats 1.21 ms for the
+// configs[3] projection)
+constexpr int UM_BK = 16;
+constexpr int UM_ROWB = UM_BK * 4;       // bytes of one K-major tile row (64: SWIZZLE_64B)
+constexpr int UM_BOXB = 32 * UM_ROWB;    // bytes of one MN-major TMA box: [UM_BK k-rows][32 floats]
+constexpr int UM_MAX_STAGES = 8;
 constexpr int UM_THREADS = 448;
 // The tensor core adds into the fp32 accumulator with truncation (measured: a chain of 1024 k-steps of positive terms ends
 // 5.5e-5 low, 5.4e-8 per k-step), so no chain is longer than a round: the accumulators are drained after UM_FLUSH_TN
 // k-blocks (32 k-steps) in the long reductions of mode 2, after UM_FLUSH k-blocks (contraction length 512) otherwise.
-constexpr int UM_FLUSH_TN = 8;
-constexpr int UM_FLUSH = 16;
+constexpr int UM_FLUSH_TN = 16;
+constexpr int UM_FLUSH = 32;
 constexpr uint32_t UM_ACC_STAGE_COLS = 256;
-constexpr uint32_t UM_A_BYTES = UM_BM * 128;
-constexpr uint32_t UM_STAGING = 2 * UM_A_BYTES;
+constexpr uint32_t UM_A_BYTES = UM_BM * UM_ROWB;
+constexpr uint32_t UM_STG_BYTES = UM_BM * 128;   // one epilogue staging buffer: [128 rows][32 columns]
+constexpr uint32_t UM_STAGING = 2 * UM_STG_BYTES;
 constexpr uint32_t UM_TMEM_COLS = 512;
 
 struct UmmaParams {
@@ -52,6 +58,7 @@ struct UmmaParams {
     const float* bias;
     uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;   // descriptor strides (bytes) of the staged tiles
     uint32_t dbg_idesc_xor, dbg_print;
+    int nstages;          // depth of the TMA -> split -> MMA ring
     int round_len;        // k-blocks accumulated in tensor memory before the accumulators are drained
     int nacc;             // accumulator stages in tensor memory (2 when BN <= 128: drain under the next round's MMAs)
     uint32_t corr_col;    // column offset of the correction accumulator inside an accumulator stage
@@ -81,14 +88,15 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
     constexpr bool A_MN = (MODE == 2), B_MN = (MODE >= 1);
     extern __shared__ uint8_t um_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)um_smem_raw + 1023) & ~(uintptr_t)1023);
-    const uint32_t bbytes = (uint32_t)p.BNL * 128u;
+    const uint32_t bbytes = (uint32_t)p.BNL * UM_ROWB;
     const uint32_t stage_bytes = 2 * UM_A_BYTES + 2 * bbytes;
+    const int UM_STAGES = p.nstages;
     uint8_t* staging = smem + UM_STAGES * stage_bytes;
     uint64_t* bars = (uint64_t*)(staging + UM_STAGING);
-    uint64_t* full = bars;                 // [UM_STAGES] TMA landed
-    uint64_t* xfrm = bars + UM_STAGES;     // [UM_STAGES] hi/lo split done
-    uint64_t* empty = bars + 2 * UM_STAGES;  // [UM_STAGES] MMAs reading the stage completed
-    uint64_t* tfull = bars + 3 * UM_STAGES;  // [2] accumulators of a round complete
+    uint64_t* full = bars;                       // [nstages] TMA landed
+    uint64_t* xfrm = bars + UM_MAX_STAGES;       // [nstages] hi/lo split done
+    uint64_t* empty = bars + 2 * UM_MAX_STAGES;  // [nstages] MMAs reading the stage completed
+    uint64_t* tfull = bars + 3 * UM_MAX_STAGES;  // [2] accumulators of a round complete
     uint64_t* tempty = tfull + 2;            // [2] accumulators drained
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
@@ -138,13 +146,13 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
                     mbar_arrive_expect_tx(&full[s], UM_A_BYTES + bbytes);
                     if (A_MN) {
 #pragma unroll
-                        for (int b = 0; b < UM_BM / 32; ++b) tma_load_2d(st + b * 4096, ta, w.mt * UM_BM + 32 * b, kk, &full[s]);
+                        for (int b = 0; b < UM_BM / 32; ++b) tma_load_2d(st + b * UM_BOXB, ta, w.mt * UM_BM + 32 * b, kk, &full[s]);
                     } else {
                         tma_load_2d(st, ta, kk, w.mt * UM_BM, &full[s]);
                     }
                     uint8_t* sb = st + 2 * UM_A_BYTES;
                     if (B_MN) {
-                        for (int b = 0; b < p.BNL / 32; ++b) tma_load_2d(sb + b * 4096, tb, w.nt * p.BN + 32 * b, kk, &full[s]);
+                        for (int b = 0; b < p.BNL / 32; ++b) tma_load_2d(sb + b * UM_BOXB, tb, w.nt * p.BN + 32 * b, kk, &full[s]);
                     } else {
                         tma_load_2d(sb, tb, kk, w.nt * p.BN, &full[s]);
                     }
@@ -186,10 +194,11 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
                         }
                         for (int ks = 0; ks < nks; ++ks) {
                             const uint32_t aoff = ks * p.a_kstep, boff = ks * p.b_kstep;
-                            const uint64_t dAh = umma_desc_sw128(a_hi + aoff, p.a_lbo, p.a_sbo, A_MN ? 1u : 2u);
-                            const uint64_t dAl = umma_desc_sw128(a_lo + aoff, p.a_lbo, p.a_sbo, A_MN ? 1u : 2u);
-                            const uint64_t dBh = umma_desc_sw128(b_hi + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 2u);
-                            const uint64_t dBl = umma_desc_sw128(b_lo + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 2u);
+                            // layout type: 1 = 128-byte swizzle of 32-byte chunks (MN-major tf32), 4 = 64-byte swizzle (K-major rows)
+                            const uint64_t dAh = umma_desc_sw128(a_hi + aoff, p.a_lbo, p.a_sbo, A_MN ? 1u : 4u);
+                            const uint64_t dAl = umma_desc_sw128(a_lo + aoff, p.a_lbo, p.a_sbo, A_MN ? 1u : 4u);
+                            const uint64_t dBh = umma_desc_sw128(b_hi + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 4u);
+                            const uint64_t dBl = umma_desc_sw128(b_lo + boff, p.b_lbo, p.b_sbo, B_MN ? 1u : 4u);
                             const uint32_t acc = (kb == r0 && ks == 0) ? 0u : 1u;
                             umma_tf32(d_main, dAh, dBh, idesc, acc);
                             umma_tf32(d_corr, dAh, dBl, idesc, acc);
@@ -239,7 +248,7 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
         const int q = warp & 3;          // TMEM lane quarter this warp may read
         const int h = e >> 2;            // column-chunk parity served by this group of 4 warps
         const int row = q * 32 + lane;
-        uint8_t* stg = staging + h * UM_A_BYTES;
+        uint8_t* stg = staging + h * UM_STG_BYTES;
         const bool issuer = ((e & 3) == 0) && lane == 0;
         const int nchunks = (p.BN + 31) >> 5;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -365,8 +374,9 @@ EncodeTiledFn get_encode() {
 
 // 2-D fp32 row-major tensor [outer, inner] with row pitch `ld` elements; box [box_outer, box_inner], 128-byte swizzle:
 // 16-byte chunks (K-major operands, the output), or 32-byte chunks for operands the tensor core reads MN-major
+enum MapKind { MAP_OUT = 0, MAP_KMAJOR = 1, MAP_MNMAJOR = 2 };
 bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
-              bool mn_major = false) {
+              MapKind kind) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {inner, outer};
@@ -374,7 +384,8 @@ bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer,
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               kind == MAP_MNMAJOR ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (kind == MAP_KMAJOR ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -451,11 +462,11 @@ int fsw_umma_gemm(int op, int64_t M, int64_t N, int nseg, const int64_t* Kd, con
     p.round_len = (op == 2) ? UM_FLUSH_TN : UM_FLUSH;
     p.nacc = (p.BN <= 128) ? 2 : 1;
     p.corr_col = (p.BN <= 128) ? 128u : 256u;
-    // K-major tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart, one k-step = 32 bytes inside the row.
-    // MN-major tile: TMA boxes of [32 k-rows][128 bytes] (32-byte-chunk swizzle, atoms of 4 k-rows = 512 bytes); 32-element
-    // MN groups one box (4096 bytes) apart, one k-step = 8 rows = two atoms.
-    p.a_lbo = (op == 2) ? 4096u : 16u;  p.a_sbo = (op == 2) ? 512u : 1024u;  p.a_kstep = (op == 2) ? 1024u : 32u;
-    p.b_lbo = (op >= 1) ? 4096u : 16u;  p.b_sbo = (op >= 1) ? 512u : 1024u;  p.b_kstep = (op >= 1) ? 1024u : 32u;
+    // K-major tile: rows of 64 bytes (64-byte swizzle), 8-row atoms 512 bytes apart, one k-step = 32 bytes inside the row.
+    // MN-major tile: TMA boxes of [16 k-rows][128 bytes] (32-byte-chunk swizzle, atoms of 4 k-rows = 512 bytes); 32-element
+    // MN groups one box apart, one k-step = 8 rows = two atoms.
+    p.a_lbo = (op == 2) ? (uint32_t)UM_BOXB : 16u;  p.a_sbo = 512u;  p.a_kstep = (op == 2) ? 1024u : 32u;
+    p.b_lbo = (op >= 1) ? (uint32_t)UM_BOXB : 16u;  p.b_sbo = 512u;  p.b_kstep = (op >= 1) ? 1024u : 32u;
     if (const char* dbg = getenv("FSW_UMMA_DBG")) {   // debug: "a_lbo a_sbo a_kstep b_lbo b_sbo b_kstep"
         unsigned v[6];
         unsigned x = 0, pr = 0;
@@ -469,15 +480,20 @@ int fsw_umma_gemm(int op, int64_t M, int64_t N, int nseg, const int64_t* Kd, con
     for (int s = 0; s < 2; ++s) {
         const int u = s < nseg ? s : 0;
         bool ok;
-        if (op == 2) ok = make_map(&tA[s], A[u], (uint64_t)M, (uint64_t)Kd[u], (uint64_t)lda[u], 32, 32, true);
-        else ok = make_map(&tA[s], A[u], (uint64_t)Kd[u], (uint64_t)M, (uint64_t)lda[u], 32, UM_BM);
-        if (op >= 1) ok = ok && make_map(&tB[s], B[u], (uint64_t)N, (uint64_t)Kd[u], (uint64_t)ldb[u], 32, 32, true);
-        else ok = ok && make_map(&tB[s], B[u], (uint64_t)Kd[u], (uint64_t)N, (uint64_t)ldb[u], 32, (uint32_t)p.BNL);
+        if (op == 2) ok = make_map(&tA[s], A[u], (uint64_t)M, (uint64_t)Kd[u], (uint64_t)lda[u], 32, UM_BK, MAP_MNMAJOR);
+        else ok = make_map(&tA[s], A[u], (uint64_t)Kd[u], (uint64_t)M, (uint64_t)lda[u], UM_BK, UM_BM, MAP_KMAJOR);
+        if (op >= 1) ok = ok && make_map(&tB[s], B[u], (uint64_t)N, (uint64_t)Kd[u], (uint64_t)ldb[u], 32, UM_BK, MAP_MNMAJOR);
+        else ok = ok && make_map(&tB[s], B[u], (uint64_t)Kd[u], (uint64_t)N, (uint64_t)ldb[u], UM_BK, (uint32_t)p.BNL, MAP_KMAJOR);
         if (!ok) return FSW_UMMA_NA;
     }
-    if (!make_map(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, UM_BM)) return FSW_UMMA_NA;
+    if (!make_map(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, UM_BM, MAP_OUT)) return FSW_UMMA_NA;
 
-    const size_t smem = 1024 + (size_t)UM_STAGES * (2 * UM_A_BYTES + 2 * (size_t)p.BNL * 128) + UM_STAGING + 128;
+    const size_t stage_bytes = 2 * UM_A_BYTES + 2 * (size_t)p.BNL * UM_ROWB;
+    const size_t fixed = 1024 + UM_STAGING + 512;   // alignment slack, epilogue staging, barriers
+    int nst = (int)((232448 - fixed) / stage_bytes);
+    if (const char* e = getenv("FSW_UMMA_STAGES")) nst = atoi(e) < nst ? atoi(e) : nst;   // tuning knob
+    p.nstages = nst > UM_MAX_STAGES ? UM_MAX_STAGES : (nst < 2 ? 2 : nst);
+    const size_t smem = fixed + (size_t)p.nstages * stage_bytes;
     const int nitems = p.mtiles * p.ntiles * p.splits;
     const int grid = nitems < sms ? nitems : sms;
     static const char* labels[3] = {"umma_nt", "umma_nn", "umma_tn"};

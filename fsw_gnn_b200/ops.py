@@ -275,6 +275,88 @@ SAVE_RANKS = True
 RANK_MEMORY_FRACTION = 0.35
 
 
+CLOUD_MODE = True   # point-cloud mode for dense batches of low-dimensional points (include/fsw_embedding.h section 5b)
+
+
+def cloud_eligible(X, plan, E_feat, K):
+    """dense batch of unit-weight multisets of 33..1024 points, d <= 4, fp32, total mass >= pad threshold, one GPU"""
+    return (CLOUD_MODE and X.dtype == torch.float32 and E_feat is None and plan.rowptr is None and plan.col is None
+            and plan.W is None and 1 <= X.shape[1] <= 4 and 33 <= plan.n_fixed <= 1024 and plan.n_fixed >= plan.thresh
+            and plan.S <= 65535 and K > 0 and getattr(plan, "exchange", None) is None)
+
+
+class FSWCloudFunction(torch.autograd.Function):
+    """FSWEmbedFunction for point clouds: no projected matrix, no projected gradient (csrc/fsw_cloud.cu).
+    out[S, tm_dim + K] like FSWEmbedFunction ('plain' total-mass channel and bias included)."""
+
+    @staticmethod
+    def forward(ctx, X, projVecs, freqs, bias, tm_scale, plan, tm_function, grad_mode):
+        lib = _lib.load()
+        d = X.shape[1]
+        K = projVecs.shape[0]
+        tm_dim = 0 if tm_function is None else 1
+        X = X.contiguous()
+        freqs = freqs.contiguous()
+        theta = projVecs if projVecs.stride(1) == 1 else projVecs.contiguous()
+        out = torch.empty((plan.S, K + tm_dim), dtype=X.dtype, device=X.device)
+        bias_core = None
+        if bias is not None:
+            bias = bias.contiguous()
+            bias_core = bias[tm_dim:]
+        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad[:5])
+        n = plan.n_fixed
+        ranksT = dxi_out = None
+        if needs_grad:
+            ranksT = torch.empty(plan.S * K * n, dtype=torch.int16, device=X.device)
+            if ctx.needs_input_grad[2]:
+                dxi_out = torch.zeros((plan.S, K), dtype=X.dtype, device=X.device)
+        scratch = plan.scratch(K, False)
+        _lib.call(X.device, "fsw_embed_forward_cloud", dtype_code(X.dtype), ptr(X), d, ptr(theta), theta.stride(0), n, ptr(plan.mass),
+                  ptr(plan.info), ptr(plan.order), plan.bucket_offsets, plan.S, K, ptr(freqs), plan.thresh, ptr(out), out.stride(0),
+                  tm_dim, ptr(bias_core), ptr(scratch), 0 if scratch is None else scratch.numel(), ptr(ranksT), ptr(dxi_out),
+                  0 if dxi_out is None else dxi_out.stride(0), stream_ptr(X.device))
+        fT = None
+        if tm_dim:
+            fT = total_mass_function(plan.mass_as(X.dtype), tm_function)
+            col0 = fT * tm_scale
+            if bias is not None:
+                col0 = col0 + bias[0]
+            out[:, 0] = col0
+        ctx.plan, ctx.tm_dim = plan, tm_dim
+        ctx.has_bias, ctx.has_scale = bias is not None, tm_scale is not None
+        ctx.ranksT, ctx.dxi_out = ranksT, dxi_out
+        ctx.save_for_backward(X, theta, freqs, fT)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        X, theta, freqs, fT = ctx.saved_tensors
+        plan, tm_dim = ctx.plan, ctx.tm_dim
+        need_X, need_theta, need_xi, need_bias, need_scale = ctx.needs_input_grad[:5]
+        if not (g.dim() == 2 and g.stride(1) == 1):
+            g = g.contiguous()
+        K, d, n = theta.shape[0], X.shape[1], plan.n_fixed
+        dX = dtheta = dxi = dbias = dscale = None
+        if need_bias and ctx.has_bias:
+            dbias = g.sum(dim=0)
+        if need_scale and ctx.has_scale and tm_dim:
+            dscale = (g[:, 0] * fT).sum()
+        if need_X:
+            dX = torch.empty_like(X)
+        if need_theta:
+            dtheta = torch.zeros_like(theta)
+        if (need_X or need_theta) and ctx.ranksT is None:
+            raise RuntimeError("FSWCloudFunction.backward: the forward ran without gradient recording")
+        if need_X or need_theta:
+            _lib.call(X.device, "fsw_embed_backward_cloud", dtype_code(X.dtype), ptr(X), d, ptr(theta), theta.stride(0), n, plan.S, K,
+                      ptr(freqs), ptr(g), g.stride(0), tm_dim, ptr(ctx.ranksT), ptr(dX), ptr(dtheta),
+                      0 if dtheta is None else dtheta.stride(0), stream_ptr(X.device))
+        if need_xi:
+            dxi = (g[:, tm_dim:tm_dim + K] * ctx.dxi_out).sum(dim=0)
+        return dX, dtheta, dxi, dbias, dscale, None, None, None
+
+
 class FSWEmbedFunction(torch.autograd.Function):
     """out[S, d_out] = [ total-mass channel | (1+xi_k) sum_j p_(j) D_j ] + bias   (+ autograd).
 
@@ -486,6 +568,8 @@ def column_chunks(K, n):
 def fsw_embed(X, projVecs, freqs, bias, tm_scale, E_feat, plan, tm_function, W_vals=None):
     if W_vals is not None and not W_vals.requires_grad:
         W_vals = None
+    if W_vals is None and cloud_eligible(X, plan, E_feat, projVecs.shape[0]):
+        return FSWCloudFunction.apply(X, projVecs, freqs, bias, tm_scale, plan, tm_function, torch.is_grad_enabled())
     return FSWEmbedFunction.apply(X, projVecs, freqs, bias, tm_scale, E_feat, W_vals, plan, tm_function, torch.is_grad_enabled())
 
 

@@ -216,6 +216,22 @@ int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, c
                        size_t scratch_bytes, const void* ranks, int64_t ldr, int dxi_from_forward, const int32_t* tptr,
                        const int32_t* tseg, const int32_t* tslot, const int32_t* tn, int64_t nrows, void* stream);
 
+/* 5b. Point-cloud mode (BASELINE.json configs[2]; reference: the dense path of forward_helper, fsw_embedding.py:925, :989-1004):
+ * dense batch of S unit-weight multisets of n points each (33 <= n <= 1024, n >= thresh), d <= 4, fp32.  The keys
+ * <x_e, theta_k> are formed inside the sort kernel (no projected matrix), the ranks are recorded slice-major
+ * ranksT [S][K][n] uint16, and the backward evaluates dL/dp where it is consumed (no projected gradient):
+ *   fsw_embed_forward_cloud:  X [S*n, d], theta [K, ldt]; mass/info/order/bucket_offsets_host: the plan of the dense batch;
+ *                             scratch: fsw_embed_scratch_bytes of that plan; ranksT_out / dxi_out may be NULL (inference).
+ *   fsw_embed_backward_cloud: dX [S*n, d] overwritten, dtheta [K, ld_dt] added to (either may be NULL). */
+int fsw_embed_forward_cloud(int dtype, const void* X, int64_t d, const void* theta, int64_t ldt, int64_t n, const double* mass,
+                            const int32_t* info, const int32_t* order, const int32_t* bucket_offsets_host, int64_t S, int64_t K,
+                            const void* freqs, double thresh, void* out, int64_t ld_out, int64_t out_col0, const void* bias,
+                            void* scratch, size_t scratch_bytes, void* ranksT_out, void* dxi_out, int64_t ld_dxi, void* stream);
+int fsw_embed_backward_cloud(int dtype, const void* X, int64_t d, const void* theta, int64_t ldt, int64_t n, int64_t S, int64_t K,
+                             const void* freqs, const void* g, int64_t ld_g, int64_t g_col0, const void* ranksT, void* dX,
+                             void* dtheta, int64_t ld_dt, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------------
  * 6b. K3w: gradient with respect to the WEIGHTS of the multisets (ag.cumsum_sparse.backward fsw_embedding.py:2160-2172,
  *     ag.div_sparse_dense :1656, deficit padding with custom_lowclamp :787-829, :1735-1744)

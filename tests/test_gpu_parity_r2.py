@@ -441,6 +441,44 @@ def test_config3_pointcloud_gradients_k256():
     check("C3 K=256 dxi", mod.freqs.grad.cpu().numpy(), dxi, mode="scaled", grad=True)
 
 
+@pytest.mark.parametrize("n,d,K", [(33, 1, 9), (100, 3, 37), (512, 4, 64), (777, 2, 40), (1024, 3, 256)])
+def test_cloud_mode_equals_projected_path(n, d, K):
+    """point-cloud mode (keys formed inside the sort kernel, slice-major ranks, dL/dp evaluated where it is consumed) against the
+    general dense path (projected matrix + row-major ranks + contractions): identical keys, so the values are bit-identical and
+    the gradients agree to fp32 summation order"""
+    from fsw_gnn_b200 import FSW_embedding, ops, _lib
+    rng = np.random.default_rng(n + d)
+    B = 7
+    torch.manual_seed(n)
+    mod = FSW_embedding(d_in=d, d_out=K, device=dev(), dtype=torch.float32, encode_total_mass=(d == 3), learnable_slices=True,
+                        learnable_freqs=True)
+    X = rng.standard_normal((B, n, d)).astype(np.float32)
+    gout = torch.as_tensor(rng.standard_normal((B, K)).astype(np.float32), device=dev())
+    res = {}
+    for mode in (True, False):
+        ops.CLOUD_MODE = mode
+        try:
+            for p_ in mod.parameters():
+                p_.grad = None
+            Xt = torch.as_tensor(X, device=dev()).requires_grad_(True)
+            _lib.profile_enable(True)
+            _lib.profile_read()
+            out = mod(Xt)
+            (out * gout).sum().backward()
+            torch.cuda.synchronize()
+            rec = _lib.profile_read()
+            _lib.profile_enable(False)
+            res[mode] = (out.detach(), Xt.grad, mod.projVecs.grad.clone(), mod.freqs.grad.clone(), rec)
+        finally:
+            ops.CLOUD_MODE = True
+    assert "bwd_cloud_dx" in res[True][4] and "bwd_cloud_dx" not in res[False][4]
+    assert not any(k.startswith(("gemm", "project", "umma")) for k in res[True][4]), sorted(res[True][4])
+    assert torch.equal(res[True][0], res[False][0])
+    for name, i_ in (("dX", 1), ("dtheta", 2), ("dxi", 3)):
+        a, b = res[True][i_], res[False][i_]
+        check("cloud vs projected n=%d d=%d K=%d %s" % (n, d, K, name), a.cpu().numpy(), b.cpu().numpy().astype(np.float64), mode="scaled", grad=True)
+
+
 def test_config5_powerlaw_gradients_subsample():
     """configs[4] on a row subsample: power-law in-degrees with a 100 000-edge hub, d_in = 256 -> K = 511 slices
     (two 256-slice chunks in the source-major backward, the re-sorting backward for the hub)."""
