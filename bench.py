@@ -108,21 +108,22 @@ def label_buckets(label):
         return []
     kind = 0 if parts[2][0] == "u" else 1
     size = int(parts[2][1:])
-    base = kind * 517
+    base = kind * 519
     if parts[1] == "small":
         lo = ({4: 0, 8: 5, 12: 9, 16: 13, 24: 17, 32: 25, 48: 33, 64: 49} if kind == 0 else {4: 0, 8: 5, 16: 9, 32: 17, 64: 33})[size]
         return [base + b for b in range(lo, size + 1)]
     if parts[1] == "rank" and size <= 64:
         return [base + b for b in range(0, size + 1)]
     if parts[1] == "rankT":   # source-major rank backward: every uniform segment (up to 32768 elements)
-        return [b for b in range(0, 517)]
+        return [b for b in range(0, 519)]
     if parts[1] in ("coop", "cloud"):   # packed-key classes: two per power of two (3/4 and all of the slots)
         coop = {48: (33, 48), 64: (49, 64), 96: (65, 96), 128: (97, 128), 192: (129, 192), 256: (193, 256), 384: (257, 384),
                 512: (385, 512), 1024: (513, 513)}
-        lo, hi = coop.get(size, (516, 516))
+        lo, hi = coop.get(size, (518, 518))
         return [base + b for b in range(lo, hi + 1)]
-    ranges = {64: (33, 64), 128: (65, 128), 256: (129, 256), 512: (257, 512), 1024: (513, 513), 2048: (514, 514), 4096: (515, 515)}
-    lo, hi = ranges.get(size, (516, 516))
+    ranges = {64: (33, 64), 128: (65, 128), 256: (129, 256), 512: (257, 512), 1024: (513, 513), 2048: (514, 514), 4096: (515, 515),
+              8192: (516, 516), 32768: (517, 517)}
+    lo, hi = ranges.get(size, (518, 518))
     return [base + b for b in range(lo, hi + 1)]
 
 

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfsw_embedding.so")
 
 FSW_F32, FSW_F64 = 0, 1
-PLAN_BUCKETS_PER_KIND = 517
+PLAN_BUCKETS_PER_KIND = 519
 PLAN_BUCKETS = 2 * PLAN_BUCKETS_PER_KIND
 
 _lib = None

@@ -44,13 +44,15 @@ static inline int64_t fsw_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 #define FSW_INFO_UNIFORM (1 << 30)
 #define FSW_INFO_NMASK ((1 << 30) - 1)
 
-// plan bucket of a segment of n_eff elements (0..512 exact, then power-of-two ranges)
+// plan bucket of a segment of n_eff elements (0..512 exact, then power-of-two ranges up to 8192, <= 32768, hubs beyond)
 __host__ __device__ static inline int fsw_size_bucket(int n_eff) {
     if (n_eff < FSW_PLAN_EXACT) return n_eff;
     if (n_eff <= 1024) return 513;
     if (n_eff <= 2048) return 514;
     if (n_eff <= 4096) return 515;
-    return 516;
+    if (n_eff <= 8192) return 516;
+    if (n_eff <= 32768) return 517;
+    return 518;
 }
 
 // ---- numeric helpers --------------------------------------------------------------------------------

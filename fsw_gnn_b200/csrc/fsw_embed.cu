@@ -572,9 +572,11 @@ int generic_ranges(int msn, int64_t max_n_eff, SizeRange* out) {
     out[c++] = {513, 513, 1024};
     out[c++] = {514, 514, 2048};
     out[c++] = {515, 515, 4096};
-    int64_t big = 8192;
+    out[c++] = {516, 516, 8192};
+    out[c++] = {517, 517, 32768};
+    int64_t big = 65536;   // hubs: one class, sized for the largest segment
     while (big < max_n_eff) big <<= 1;
-    out[c++] = {516, 516, (int)big};
+    out[c++] = {518, 518, (int)big};
     return c;
 }
 
@@ -971,6 +973,7 @@ extern "C" size_t fsw_embed_scratch_bytes(int dtype, const int32_t* bo, int64_t 
                 size_t want = grid * tb;
                 const size_t cap_bytes = (size_t)2 << 30;  // never ask for more than 2 GiB: fewer resident CTAs instead
                 if (want > cap_bytes) want = (cap_bytes / tb ? cap_bytes / tb : 1) * tb;
+                want += 1024;   // the grid-wide (team) mode keeps its global accumulators behind the tile
                 if (want > need) need = want;
                 continue;
             }

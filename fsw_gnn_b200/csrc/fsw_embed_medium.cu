@@ -17,11 +17,21 @@
 // with the two ping-pong buffers in an L2-resident global scratch slice per CTA (GLOBAL = true; the
 // coefficient table is then replaced by direct evaluation) on a persistent grid.
 // Non-uniform weights and fp64 use the generic path (fsw_embed.cu).
+// TEAM = true (hubs: more than FSW_TEAM_MIN_CAP elements): the whole grid, launched cooperatively with one CTA per SM, works
+// on ONE tile at a time - runs and merge units are dealt to the warps of all CTAs, the phases are separated by grid-wide
+// barriers, partial sums meet in a few global double accumulators.  A 100 000-element hub (configs[4]) otherwise keeps one
+// CTA busy for 12 merge passes over an L2-resident tile while 147 SMs idle.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "fsw_sortnet.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int UNIT = 32;  // output rows per merge work unit
+constexpr int FSW_TEAM_MIN_CAP = 8192;
 
 // merge-path split: number of A elements among the first `oo` outputs of merge(A, B), ties -> A first
 template <typename T>
@@ -91,7 +101,7 @@ __host__ __device__ constexpr size_t fsw_medium_tile_bytes_t(int cap) {
     return (size_t)cap * 32 * (2 * sizeof(T) + (MODE >= 1 ? 2 * sizeof(IdxT) : 0) + (USE_TABLE ? sizeof(T) : 0));
 }
 
-template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE>
+template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE, bool TEAM>
 __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks, int cap,
                                                             int64_t nwork, T* __restrict__ out, int64_t ld_out,
                                                             int64_t out_col0, const T* __restrict__ bias,
@@ -107,7 +117,17 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
     constexpr bool BWD = MODE == 2;
     constexpr bool PAY = MODE >= 1;
     const size_t tile_bytes = fsw_medium_tile_bytes_t<MODE, USE_TABLE, T, IdxT>(cap);
-    unsigned char* basep = GLOBAL ? gscratch + (size_t)blockIdx.x * tile_bytes : fsw_smem_raw;
+    static_assert(!TEAM || GLOBAL, "team mode works on a tile in global scratch");
+    unsigned char* basep = GLOBAL ? gscratch + (TEAM ? (size_t)0 : (size_t)blockIdx.x * tile_bytes) : fsw_smem_raw;
+    double* gacc = reinterpret_cast<double*>(gscratch + tile_bytes);   // TEAM: [3][32] accumulators behind the tile, zero on entry
+    (void)gacc;
+    // work distribution inside a tile: the warps of this CTA, or of the whole grid
+    const int gw = TEAM ? (int)blockIdx.x * W + (int)(threadIdx.x >> 5) : (int)(threadIdx.x >> 5);
+    const int GW = TEAM ? (int)gridDim.x * W : W;
+    auto phase_sync = [&]() {
+        if constexpr (TEAM) cg::this_grid().sync();
+        else __syncthreads();
+    };
     T* bufA = reinterpret_cast<T*>(basep);
     T* bufB = bufA + (size_t)cap * 32;
     IdxT* idxA = reinterpret_cast<IdxT*>(bufB + (size_t)cap * 32);          // payload (MODE >= 1)
@@ -127,7 +147,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
     const T INF = fsw_inf<T>();
     const int ldb = (int)(a.ldp * (int64_t)sizeof(T));
 
-  for (int64_t work = blockIdx.x; work < nwork; work += gridDim.x) {   // persistent over (item, chunk) work groups
+  for (int64_t work = TEAM ? 0 : blockIdx.x; work < nwork; work += TEAM ? 1 : gridDim.x) {   // persistent over (item, chunk) work groups
     const int item = (int)(work / nchunks);
     const int chunk = (int)(work - (int64_t)item * nchunks);
     const int64_t first = (int64_t)seg_lo + (int64_t)item * G;
@@ -166,7 +186,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
         }
 
         // ---- 1. runs of 32 rows: gather -> registers -> network sort -> shared ----
-        for (int run = warp; run < R; run += W) {
+        for (int run = gw; run < R; run += GW) {
             const int base = run << 5;
             const int cnt = min(32, n - base);
             int c0, c1;
@@ -204,7 +224,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                 if (PAY) idxA[(base + j) * 32 + lane] = (IdxT)idx[j];
             }
         }
-        __syncthreads();
+        phase_sync();
 
         // ---- 2. merge passes that store their output ----
         T* src = bufA;
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
         int len = 32;
         while ((len << 1) < Ntot) {
             const int iters = 33 - __clz(len);
-            for (int un = warp; un < nunits; un += W) {
+            for (int un = gw; un < nunits; un += GW) {
                 const int o = un * UNIT;
                 const int p0 = (o / (2 * len)) * 2 * len;
                 const int La = min(len, Ntot - p0);
@@ -230,7 +250,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                                                  if (PAY) di[t * 32] = (IdxT)id;
                                              });
             }
-            __syncthreads();
+            phase_sync();
             T* tk = src;
             src = dst;
             dst = tk;
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
             const int iters = 33 - __clz(len);
             const int La = min(len, Ntot);
             const int Lb = Ntot - La;
-            for (int un = warp; un < nunits; un += W) {
+            for (int un = gw; un < nunits; un += GW) {
                 const int o = un * UNIT;
                 const int ia = (o > 0) ? fsw_merge_path(src, La, src + (size_t)La * 32, Lb, o, iters, lane) : 0;
                 T facc = (T)0, fSc = (T)0, fSs = (T)0;
@@ -315,30 +335,53 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                 if (MODE == 1) Ss += (double)fSs;
             }
         }
-        __syncthreads();
+        if constexpr (TEAM) {
+            // partial sums of all CTAs meet in global double accumulators (zero on entry, re-zeroed by their reader)
+            if (!BWD) {
+                atomicAdd(gacc + lane, acc);
+                if (MODE == 1) atomicAdd(gacc + 32 + lane, Ss);
+            } else if (NEED_DXI) {
+                atomicAdd(gacc + lane, Sc);
+                atomicAdd(gacc + 32 + lane, Ss);
+            }
+        }
+        phase_sync();
 
         if (MODE == 1) {
-            for (int r = warp; r < n; r += W)
+            for (int r = gw; r < n; r += GW)
                 if (act) ranks[fsw_rowoff(e0 + r, ldr) + k] = (unsigned short)__float_as_int(dst[r * 32 + lane]);
         }
         if (!BWD) {
-            red[warp][lane] = acc;
-            if (MODE == 1) red2[warp][lane] = Ss;
-            __syncthreads();
-            if (warp == 0 && act) {
-                double tot = 0.0, tots = 0.0;
-#pragma unroll
-                for (int w2 = 0; w2 < W; ++w2) {
-                    tot += red[w2][lane];
-                    if (MODE == 1) tots += red2[w2][lane];
+            if constexpr (TEAM) {
+                if (blockIdx.x == 0 && warp == 0) {
+                    const double tot = gacc[lane], tots = (MODE == 1) ? gacc[32 + lane] : 0.0;
+                    gacc[lane] = 0.0;
+                    if (MODE == 1) gacc[32 + lane] = 0.0;
+                    if (act) {
+                        out[fsw_rowoff(s, ld_out) + out_col0 + k] = ((T)1 + xi) * A0 * (T)tot + bk;
+                        if (MODE == 1 && want_dxi)
+                            dxi_out[fsw_rowoff(s, ld_dxi) + k] = (T)((double)A0 * tot + (1.0 + xid) * ((double)A0p * tot - (double)A0 * tots));
+                    }
                 }
-                out[fsw_rowoff(s, ld_out) + out_col0 + k] = ((T)1 + xi) * A0 * (T)tot + bk;
-                if (MODE == 1 && want_dxi)
-                    dxi_out[fsw_rowoff(s, ld_dxi) + k] = (T)((double)A0 * tot + (1.0 + xid) * ((double)A0p * tot - (double)A0 * tots));
+            } else {
+                red[warp][lane] = acc;
+                if (MODE == 1) red2[warp][lane] = Ss;
+                __syncthreads();
+                if (warp == 0 && act) {
+                    double tot = 0.0, tots = 0.0;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) {
+                        tot += red[w2][lane];
+                        if (MODE == 1) tots += red2[w2][lane];
+                    }
+                    out[fsw_rowoff(s, ld_out) + out_col0 + k] = ((T)1 + xi) * A0 * (T)tot + bk;
+                    if (MODE == 1 && want_dxi)
+                        dxi_out[fsw_rowoff(s, ld_dxi) + k] = (T)((double)A0 * tot + (1.0 + xid) * ((double)A0p * tot - (double)A0 * tots));
+                }
             }
         } else {
             // dst now holds dL/dp in ORIGINAL row order
-            for (int r = warp; r < n; r += W) {
+            for (int r = gw; r < n; r += GW) {
                 if (act) {
                     const T v = dst[r * 32 + lane];
                     if (a.col)
@@ -349,29 +392,38 @@ __global__ void __launch_bounds__(W * 32) fsw_medium_kernel(SegArgs<T> a, int se
                 }
             }
             if (NEED_DXI) {
-                red[warp][lane] = Sc;
-                red2[warp][lane] = Ss;
-                __syncthreads();
-                if (warp == 0) {
-                    double tc = 0.0, ts = 0.0;
-#pragma unroll
-                    for (int w2 = 0; w2 < W; ++w2) {
-                        tc += red[w2][lane];
-                        ts += red2[w2][lane];
+                if constexpr (TEAM) {
+                    if (blockIdx.x == 0 && warp == 0) {
+                        const double tc = gacc[lane], ts = gacc[32 + lane];
+                        gacc[lane] = 0.0;
+                        gacc[32 + lane] = 0.0;
+                        dxi_acc += (double)gk * ((double)A0 * tc + (1.0 + xid) * ((double)A0p * tc - (double)A0 * ts));
                     }
-                    dxi_acc += (double)gk * ((double)A0 * tc + (1.0 + xid) * ((double)A0p * tc - (double)A0 * ts));
+                } else {
+                    red[warp][lane] = Sc;
+                    red2[warp][lane] = Ss;
+                    __syncthreads();
+                    if (warp == 0) {
+                        double tc = 0.0, ts = 0.0;
+#pragma unroll
+                        for (int w2 = 0; w2 < W; ++w2) {
+                            tc += red[w2][lane];
+                            ts += red2[w2][lane];
+                        }
+                        dxi_acc += (double)gk * ((double)A0 * tc + (1.0 + xid) * ((double)A0p * tc - (double)A0 * ts));
+                    }
                 }
             }
         }
-        __syncthreads();
+        phase_sync();
     }
-    if (BWD && NEED_DXI && warp == 0 && act) atomicAdd(dfreqs + k, dxi_acc);
+    if (BWD && NEED_DXI && warp == 0 && act && (!TEAM || blockIdx.x == 0)) atomicAdd(dfreqs + k, dxi_acc);
   }
 }
 
 const int kPersistentGrid = 148 * 2;
 
-template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE>
+template <typename T, typename IdxT, int W, int MODE, bool NEED_DXI, bool GLOBAL, bool USE_TABLE, bool TEAM = false>
 int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
                   const T* g, int64_t ld_g, int64_t g_col0, T* dXp, T* dEp, double* dfreqs, void* scratch,
                   size_t scratch_bytes, unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, const T* gtab_c,
@@ -383,9 +435,35 @@ int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t 
     if (G > 16) G = 16;
     const int64_t nwork = fsw_cdiv(cnt, G) * nchunks;
     const size_t tile = fsw_medium_tile_bytes_t<MODE, USE_TABLE, T, IdxT>(cap);
-    auto kern = fsw_medium_kernel<T, IdxT, W, MODE, NEED_DXI, GLOBAL, USE_TABLE>;
+    auto kern = fsw_medium_kernel<T, IdxT, W, MODE, NEED_DXI, GLOBAL, USE_TABLE, TEAM>;
     int64_t blocks = nwork;
     size_t smem = tile;
+    static const char* names[3] = {"fwd_medium_u", "fwdr_medium_u", "bwd_medium_u"};
+    const std::string label = std::string(names[MODE]) + std::to_string(cap) + (TEAM ? "_team_f32" : "_f32");
+    if constexpr (TEAM) {
+        // one tile at a time, the whole machine on it: cooperative launch, every CTA resident (grid-wide barriers)
+        const size_t need = tile + 3 * 32 * sizeof(double);
+        if (need > scratch_bytes) return fsw_fail(FSW_ERR_WORKSPACE, "embed scratch too small: need >= %zu bytes", need);
+        int dev = 0, sms = 0, per_sm = 0;
+        FSW_CUDA(cudaGetDevice(&dev));
+        FSW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FSW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, 0));
+        if (per_sm < 1) return fsw_fail(FSW_ERR_CUDA, "fsw_medium_kernel (team): no resident CTA");
+        const int grid = sms * (per_sm > 2 ? 2 : per_sm);
+        FSW_CUDA(cudaMemsetAsync((unsigned char*)scratch + tile, 0, 3 * 32 * sizeof(double), st));
+        int seg_lo = lo, seg_hi = hi, Gi = (int)G, nch = nchunks, capi = cap;
+        int64_t nw = nwork;
+        SegArgs<T> aa = a;
+        unsigned char* gs = (unsigned char*)scratch;
+        void* args[] = {&aa, &seg_lo, &seg_hi, &Gi, &nch, &capi, &nw, &out, &ld_out, &out_col0, &bias, &g, &ld_g, &g_col0,
+                        &dXp, &dEp, &dfreqs, &gs, &ranks, &ldr, &dxi_out, &ld_dxi, &gtab_c, &gtab_t};
+        fsw_prof_begin(label.c_str(), st);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(W * 32), args, 0, st);
+        fsw_prof_end(st);
+        if (e != cudaSuccess) return fsw_fail(FSW_ERR_CUDA, "fsw_medium_kernel (team): cooperative launch failed: %s", cudaGetErrorString(e));
+        fsw_count_launch();
+        return FSW_OK;
+    }
     if (GLOBAL) {
         smem = 0;
         if (blocks > kPersistentGrid) blocks = kPersistentGrid;
@@ -394,8 +472,6 @@ int launch_medium(const SegArgs<T>& a, int lo, int hi, int cap, T* out, int64_t 
     } else {
         FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    static const char* names[3] = {"fwd_medium_u", "fwdr_medium_u", "bwd_medium_u"};
-    const std::string label = std::string(names[MODE]) + std::to_string(cap) + "_f32";
     fsw_prof_begin(label.c_str(), st);
     kern<<<(unsigned)blocks, W * 32, smem, st>>>(a, lo, hi, (int)G, nchunks, cap, nwork, out, ld_out, out_col0, bias, g, ld_g, g_col0,
                                                   dXp, dEp, dfreqs, (unsigned char*)scratch, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t);
@@ -415,8 +491,18 @@ int dispatch_medium(const SegArgs<float>& a, int lo, int hi, int cap, float* out
     if (cap <= 128) return FSW_MED(unsigned short, 4, false, TAB);
     if (cap <= 256) return FSW_MED(unsigned short, 8, false, TAB);
     if (cap <= 512) return FSW_MED(unsigned short, 16, false, TAB);
+#define FSW_MED_TEAM(IDX) \
+    launch_medium<float, IDX, 16, MODE, NEED_DXI, true, false, true>(a, lo, hi, cap, out, ld_out, out_col0, bias, g, ld_g, g_col0, dXp, dEp, dfreqs, scratch, scratch_bytes, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, st)
+    // hubs: few tiles, each too long for one CTA -> the whole grid works on one tile at a time
+    static const bool team_ok = getenv("FSW_NO_TEAM") == nullptr;
+    const int64_t tiles = (int64_t)(hi - lo) * ((a.K + 31) / 32);
+    if (team_ok && cap >= FSW_TEAM_MIN_CAP && tiles < 2 * 148) {
+        if (cap <= 32768) return FSW_MED_TEAM(unsigned short);
+        return FSW_MED_TEAM(int);
+    }
     if (cap <= 32768) return FSW_MED(unsigned short, 16, true, false);
     return FSW_MED(int, 16, true, false);
+#undef FSW_MED_TEAM
 #undef FSW_MED
 }
 

@@ -39,7 +39,7 @@ extern "C" {
 
 /* Number of buckets of the segment plan (section 3). */
 #define FSW_PLAN_EXACT 513                        /* buckets 0..512: exact n_eff                   */
-#define FSW_PLAN_BUCKETS_PER_KIND 517             /* 513..516: n_eff <=1024, <=2048, <=4096, >4096  */
+#define FSW_PLAN_BUCKETS_PER_KIND 519             /* 513..518: n_eff <=1024, <=2048, <=4096, <=8192, <=32768, beyond */
 #define FSW_PLAN_BUCKETS (2 * FSW_PLAN_BUCKETS_PER_KIND) /* kind 0 = uniform weights, 1 = general   */
 
 /* ------------------------------------------------------------------------------------------------

@@ -334,19 +334,19 @@ def test_plan_buckets():
     assert np.array_equal((info >> 30) & 1, uni.astype(np.int64))
     assert np.array_equal(np.sort(order), np.arange(len(lens)))
     bo = np.array(list(plan.bucket_offsets))
-    NB = 2 * 517
+    NB = 2 * 519
     assert bo[NB] == len(lens) and bo[NB + 1] == n_eff.max() and plan.max_n_eff == n_eff.max()
 
     def bucket(ne):
         if ne <= 512:
             return ne
-        for i, c in enumerate([1024, 2048, 4096]):
+        for i, c in enumerate([1024, 2048, 4096, 8192, 32768]):
             if ne <= c:
                 return 513 + i
-        return 516
+        return 518
     for b in range(NB):
         for s in order[bo[b]:bo[b + 1]]:
-            assert (0 if uni[s] else 517) + bucket(n_eff[s]) == b
+            assert (0 if uni[s] else 519) + bucket(n_eff[s]) == b
     assert plan.bucket_counts == [int(bo[b + 1] - bo[b]) for b in range(NB)]
     assert sum(plan.bucket_elems) == int(n_eff.sum())
 

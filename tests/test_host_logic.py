@@ -35,24 +35,24 @@ def test_bench_label_buckets_partition_the_uniform_buckets():
     # every forward class label of the C4 run maps to a disjoint bucket range; together they cover 0..516
     labels = (["fwdr_small_u%d_f32" % n for n in (4, 8, 12, 16, 24, 32)] +
               ["fwdr_coop_u%d_f32" % n for n in (48, 64, 96, 128, 192, 256, 384, 512)] +
-              ["fwdr_medium_u%d_f32" % n for n in (1024, 2048, 4096, 8192)])
+              ["fwdr_medium_u%d_f32" % n for n in (1024, 2048, 4096, 8192, 32768, 131072)])
     seen = []
     for lab in labels:
         bs = b.label_buckets(lab)
         assert bs, lab
         seen += bs
-    assert sorted(seen) == list(range(0, 517)), "forward labels must tile the uniform-weight buckets exactly once"
-    assert b.label_buckets("bwd_rankT_u32768_f32") == list(range(0, 517))
+    assert sorted(seen) == list(range(0, 519)), "forward labels must tile the uniform-weight buckets exactly once"
+    assert b.label_buckets("bwd_rankT_u32768_f32") == list(range(0, 519))
     assert b.label_buckets("bwd_rank_dense_f32") == [] and b.label_buckets("coef_tables") == []
     # general-weight labels live in the second kind
-    assert b.label_buckets("fwd_small_g16_f32") == [517 + n for n in range(9, 17)]
+    assert b.label_buckets("fwd_small_g16_f32") == [519 + n for n in range(9, 17)]
 
 
 def test_python_constants_match_the_header():
     from fsw_gnn_b200 import _lib, ops
     hdr = open(os.path.join(ROOT, "include", "fsw_embedding.h")).read()
     per_kind = int(re.search(r"#define FSW_PLAN_BUCKETS_PER_KIND (\d+)", hdr).group(1))
-    assert _lib.PLAN_BUCKETS_PER_KIND == per_kind == 517
+    assert _lib.PLAN_BUCKETS_PER_KIND == per_kind == 519
     assert ops.RANKT_NMAX == int(re.search(r"#define FSW_RANKT_NMAX (\d+)", hdr).group(1))
     assert "FSW_RANKT_ELIGIBLE" in hdr
 
