@@ -451,7 +451,8 @@ def main():
         ft = sum(v[1] for v in fwd.values()) * 1e-3
         roofline["fused_forward_all_classes"] = {"achieved": fb / ft / 1e9, "frac": fb / ft / 1e9 / peaks["hbm_gbs"]}
         # the kernel family the north star sets its 70 % target on, as a roofline object of its own, with every size class
-        ftraffic = [traffic.get(k) for k in fwd]
+        # DRAM bytes of one layer's forward: one launch per size class; the merge-path classes share one entry in the capture
+        ftraffic = [traffic.get(k, traffic.get("fwdr_medium_all") if "_medium_" in k else None) for k in fwd]
         roofline_forward = {"bound": "hbm", "kernel": "fused sort->cumsum->Fourier forward, all size classes (fwd*)",
                             "achieved": fb / ft / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": fb / ft / 1e9 / peaks["hbm_gbs"],
                             "traffic": (sum(ftraffic) if ftraffic and all(t is not None for t in ftraffic) and world == 1 and args.scale == 1.0 else None),
