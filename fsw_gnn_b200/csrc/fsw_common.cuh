@@ -79,8 +79,12 @@ struct Num<double> {
 
 // row * stride for operands known to fit 31 bits (node / edge indices of the int32 CSR, padded widths): one
 // IMAD.WIDE where an int64 stride would cost a full 64x64 multiply (5-7 instructions) per address.
+// (Spelled as mul.wide.s32: written as a C++ product of two sign-extended ints the compiler still emitted the full 64 x 64
+// sequence - IMAD.WIDE.U32 plus two sign fix-ups - in several kernels, profiles/r2/README.md.)
 __device__ __forceinline__ int64_t fsw_rowoff(int64_t row, int64_t ld) {
-    return (int64_t)(int)row * (int64_t)(int)ld;
+    int64_t r;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(r) : "r"((int)row), "r"((int)ld));
+    return r;
 }
 
 // cos(pi t) for |t| <= 1 (phase already reduced): no conversions, no range reduction - fold to [0, 1/2] and

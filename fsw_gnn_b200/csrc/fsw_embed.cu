@@ -860,8 +860,13 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
                         scratch_bytes = ga_off;
                         int rc = fsw_rank_backward_T(a, tr.S, tr.nrows, tnmax, tr.tptr, tr.tseg, tr.tslot, tr.tn, ranks, ldr, g, ld_g, g_col0, dXp, dEp, scratch, ga_buf, st);
                         if (rc) return rc;
+                    } else {
+                        // contract: when the transposition is passed the caller need not zero dXp - nothing will be written
+                        // by the source-major kernel here, so clear it before the atomics
+                        FSW_CUDA(cudaMemsetAsync(dXp, 0, (size_t)tr.nrows * a.ldp * sizeof(T), st));
                     }
                 } else {
+                    if (tr.tptr != nullptr) FSW_CUDA(cudaMemsetAsync(dXp, 0, (size_t)tr.nrows * a.ldp * sizeof(T), st));
                     const int lo0 = bo[base + 0], hi0 = bo[base + 128 + 1];
                     if (hi0 > lo0) {
                         int rc = fsw_rank_backward_g128(a, lo0, hi0, ranks, ldr, g, ld_g, g_col0, dXp, dEp, dfreqs_cov, scratch, st);
@@ -1055,7 +1060,15 @@ extern "C" int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const 
                                   int64_t max_n_eff, void* scratch, size_t scratch_bytes, const void* ranks, int64_t ldr,
                                   int dxi_from_forward, const int32_t* tptr, const int32_t* tseg, const int32_t* tslot,
                                   const int32_t* tn, int64_t nrows, void* stream) {
-    if (S == 0 || K == 0) return FSW_OK;
+    if (S == 0 || K == 0) {
+        // with the transposition passed, dXp [nrows, ldp] is an output that need not be initialised: an empty shard yields zeros
+        if (tptr != nullptr && dXp != nullptr && nrows > 0 && ldp > 0) {
+            const size_t es = dtype == FSW_F64 ? 8 : 4;
+            if (cudaMemsetAsync(dXp, 0, (size_t)nrows * ldp * es, (cudaStream_t)stream) != cudaSuccess)
+                return fsw_fail(FSW_ERR_CUDA, "fsw_embed_backward: memset failed");
+        }
+        return FSW_OK;
+    }
     if (dW != nullptr)
         return fsw_fail(FSW_ERR_INVALID, "fsw_embed_backward: dW must be NULL (use fsw_embed_backward_weights)");
     if (!Xp || !mass || !info || !bucket_offsets_host || !freqs || !g || !dXp)

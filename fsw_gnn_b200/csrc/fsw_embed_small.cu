@@ -216,10 +216,14 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
             }
         }
         if constexpr (SAVE_RANK) {
-            unsigned short* rp = ranks + fsw_rowoff(cur.e0, ldr) + k;
+            // one base address per segment, then a 32-bit byte offset per element: the 64 x 64-bit row arithmetic per store
+            // that `rp[i * ldr]` compiled to was 31 % of all instructions of this kernel (profiles/r2/README.md)
+            char* rb = reinterpret_cast<char*>(ranks + fsw_rowoff(cur.e0, ldr) + k);
+            const unsigned ldrb = (unsigned)ldr * 2u;
+            const int nst = act ? n : 0;
 #pragma unroll
             for (int i = 0; i < NP; ++i)
-                if (i < n && act) rp[fsw_rowoff(i, ldr)] = (unsigned short)srank[i * 32 + lane];
+                if (i < nst) *reinterpret_cast<unsigned short*>(rb + (size_t)(i * ldrb)) = (unsigned short)srank[i * 32 + lane];
         }
         // rotate the pipeline
         cur = nx1;
@@ -1040,7 +1044,9 @@ template <typename T, int NP, bool HAS_COL, bool SAVE_RANK>
 int launch_small_fwd(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out, int64_t out_col0, const T* bias,
                      unsigned short* ranks, int64_t ldr, T* dxi_out, int64_t ld_dxi, cudaStream_t st) {
     const int nchunks = (a.K + 31) / 32;
-    const int G = pick_G(hi - lo, nchunks, 148 * 32, 32);
+    // up to 128 segments per warp: the coefficient table is rebuilt at the start of a warp's run and when n changes (with 32
+    // segments per warp the rebuilds were 7 % of the instructions of the 13..16 class)
+    const int G = pick_G(hi - lo, nchunks, 148 * 32, 128);
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
     const size_t smem = (size_t)4 * NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + sizeof(int) : 0));

@@ -468,17 +468,21 @@ class FSWEmbedFunction(torch.autograd.Function):
             done = []
             for (k0, k1, ldc, Xp, ranks, dxi_out) in ctx.chunks:
                 Nrows = Xp.shape[0]   # rows the segments index (all ranks' rows when the projected rows were exchanged)
-                # dXp is accumulated with atomics in graph mode -> must start from zero
-                dXp = torch.zeros((Nrows, ldc), dtype=X.dtype, device=X.device) if plan.col is not None \
-                    else torch.empty((Nrows, ldc), dtype=X.dtype, device=X.device)
-                if plan.col is None and ldc != k1 - k0:
-                    dXp.zero_()
-                dEp = torch.zeros((plan.E, ldc), dtype=X.dtype, device=X.device) if ctx.has_E else None
-                dxi_acc = torch.zeros(k1 - k0, dtype=torch.float64, device=X.device) if need_xi else None
                 dxi_fwd = dxi_out is not None
                 transpose = None
                 if ranks is not None and X.dtype == torch.float32 and plan.col is not None and (dxi_fwd or not need_xi):
                     transpose = plan.transpose(Nrows)
+                # graph mode accumulates dXp with atomics -> it must start from zero, UNLESS the source-major kernel runs: that
+                # one writes every row (padding columns included) with plain stores before anything is added (1.9 GB of memset
+                # per layer at configs[3] otherwise)
+                if plan.col is not None and transpose is None:
+                    dXp = torch.zeros((Nrows, ldc), dtype=X.dtype, device=X.device)
+                else:
+                    dXp = torch.empty((Nrows, ldc), dtype=X.dtype, device=X.device)
+                if plan.col is None and ldc != k1 - k0:
+                    dXp.zero_()
+                dEp = torch.zeros((plan.E, ldc), dtype=X.dtype, device=X.device) if ctx.has_E else None
+                dxi_acc = torch.zeros(k1 - k0, dtype=torch.float64, device=X.device) if need_xi else None
                 embed_backward(plan, Xp, ldc, ctx.Ep, freqs[k0:k1], g, g.stride(0), tm_dim + k0, dXp, dEp, dxi_acc, ranks,
                                dxi_from_forward=(dxi_fwd or not need_xi), transpose=transpose, nrows=Nrows)
                 if need_xi:

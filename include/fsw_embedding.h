@@ -205,8 +205,9 @@ int fsw_embed_forward(int dtype, const void* Xp, int64_t ldp, const void* Ep, co
  *        covered segments is a streaming pass without any sort, otherwise everything is re-sorted.
  *  dxi_from_forward != 0: the forward was given dxi_out, so the covered segments skip the frequency gradient.
  *  tptr/tseg/tslot/tn (fsw_csr_transpose) or NULL: with them (fp32 graphs, ranks, dxi_from_forward) the segments
- *        of up to 128 elements run SOURCE-major: every row of dXp is written once with a plain store instead
- *        of scattered atomics (dXp then needs no zero-initialisation).
+ *        of up to FSW_RANKT_ELIGIBLE(max_n_eff) elements run SOURCE-major: every row of dXp is written once with a plain
+ *        store instead of scattered atomics.  dXp [nrows, ldp] then need NOT be initialised by the caller (the library
+ *        clears it itself in the cases where that kernel does not run, e.g. an empty shard).
  * ---------------------------------------------------------------------------------------------- */
 int fsw_embed_backward(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr,
                        int64_t n_fixed, const int32_t* col, const void* W, const double* mass,
