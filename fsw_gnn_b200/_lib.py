@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsw_embedding.so")
+LIB_PATH = os.environ.get("FSW_LIB_PATH") or os.path.join(_HERE, "libfsw_embedding.so")   # FSW_LIB_PATH: development builds (profiles/)
 
 FSW_F32, FSW_F64 = 0, 1
 PLAN_BUCKETS_PER_KIND = 519

@@ -30,6 +30,8 @@
 //     * SAVE_RANK: the slot of each consumed key is overwritten by its sorted position; the ranks leave row-wise,
 //       one vector store of SW uint16 per element, for the sort-free backward (fsw_embed_small.cu).
 //   Bound (ncu, profiles/r1): ALU pipe 66-74 % and L1 72-82 % busy at once; DRAM < 20 %.
+#include <stdlib.h>
+
 #include "fsw_sortnet.cuh"
 
 namespace {
@@ -147,13 +149,65 @@ __device__ __forceinline__ void fsw_store_ranks(unsigned short* dst, const int* 
         x = lo_;                 \
     }
 
+// asynchronous copy global -> shared (LDGSTS), BYTES = 4, 8 or 16 at a BYTES-aligned address; completes before cp.async.wait_all returns
+template <int BYTES>
+__device__ __forceinline__ void fsw_cp_async(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void fsw_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// a bitonic run s[R0 .. R0 + LEN) in ascending order: half-cleaners while the length is even (valid for every even length,
+// not only powers of two), a sorting network on what remains (24 comparators for 12 elements instead of the 41 of a full
+// network, 60 instead of 127 for 24)
+template <int R0, int LEN, typename CE>
+__device__ __forceinline__ void fsw_bitonic_merge(CE&& ce) {
+    if constexpr (LEN <= 1) {
+    } else if constexpr (LEN % 2 == 0) {
+        fsw_static_for<LEN / 2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            ce(R0 + i, R0 + i + LEN / 2);
+        });
+        fsw_bitonic_merge<R0, LEN / 2>(ce);
+        fsw_bitonic_merge<R0 + LEN / 2, LEN / 2>(ce);
+    } else {
+        fsw_sort_network<LEN>([&](int i, int l) { ce(R0 + i, R0 + l); });
+    }
+}
+
+// Per-run-length policy, from the measurements in profiles/r2/README.md (the kernels are bound by the shared-memory data
+// pipe - shuffles cost two wavefronts each - and by the integer ALU; DRAM is < 25 % busy):
+//   R = 12: synchronous gather (all loads issued before the first use), the lane's coefficients staged in shared memory
+//   R = 16: asynchronous gather (LDGSTS) of the next segment into a second key buffer, coefficients through L1
+//   R >= 24: synchronous gather, coefficients through L1 (shared memory per warp limits the residency otherwise)
+#ifndef FSW_COOP_ASYNC
+#define FSW_COOP_ASYNC(R) ((R) == 16)
+#endif
+#ifndef FSW_COOP_TABS
+#define FSW_COOP_TABS(R) ((R) == 12)
+#endif
+#ifndef FSW_COOP_MINB
+#define FSW_COOP_MINB(R) ((R) <= 16 ? 8 : ((R) <= 24 ? 5 : 4))   // resident CTAs per SM asked of the compiler (register cap: 64 / 96 / 128; R = 24 at 80 registers and R = 32 at 96 spill ~150 bytes and lose 5-15 %)
+#endif
+
+// shared memory of one warp, in floats: key buffers [NBUF][R L][32 / L] + the lane-private coefficient rows [TABF][R / 4][32] float4
+template <int R, bool SAVE_RANK, bool CLOUD>
+struct FswCoopSmem {
+    static constexpr bool ASYNC = FSW_COOP_ASYNC(R) && !CLOUD;
+    static constexpr int NBUF = ASYNC ? 2 : 1;                             // graphs: the gather of the next segment lands while this one is sorted
+    static constexpr int TABF = (FSW_COOP_TABS(R) && !CLOUD) ? (SAVE_RANK ? 2 : 1) : 0;  // tables staged in shared memory (reloaded when n changes)
+    static constexpr int KEYS = R * 32;
+    static constexpr int PER_WARP = (NBUF + TABF) * KEYS;
+};
+
 template <int R, int L, bool HAS_COL, bool SAVE_RANK, bool CLOUD>
-__global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
+__global__ void __launch_bounds__(128, FSW_COOP_MINB(R)) fsw_coop_fwd_kernel(
     SegArgs<float> a, int seg_lo, int seg_hi, int G, int nchunks, float* __restrict__ out, int64_t ld_out, int64_t out_col0,
     const float* __restrict__ bias, unsigned short* __restrict__ ranks, int64_t ldr, float* __restrict__ dxi_out, int64_t ld_dxi,
     const float* __restrict__ gtab_c, const float* __restrict__ gtab_t, int tab_n0, int tab_ld4) {
     static_assert(R % 4 == 0 && R >= 4, "a lane reads its table positions as float4s");
     static_assert((L & (L - 1)) == 0 && L >= 4 && L <= 32, "lanes per slice: power of two; 32 / L <= 8 slices tile the padded width");
+    using SM = FswCoopSmem<R, SAVE_RANK, CLOUD>;
     constexpr int SW = 32 / L;            // slices per warp
     constexpr int NS = R * L;             // element slots per (segment, slice)
     constexpr int NC = (NS + 31) / 32;    // column-id registers per lane (element 32 m + lane)
@@ -164,15 +218,16 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
     constexpr int IDXB = fsw_clog2(NS);   // low bits that carry the element index
     constexpr int IMASK = (1 << IDXB) - 1;
     constexpr int LOGL = fsw_clog2(L);
+    constexpr bool TABS = SM::TABF > 0;
+    constexpr bool ASYNC = SM::ASYNC;
     extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane / SW;   // which run of the slice this lane holds
     const int sl = lane % SW;  // slice within the warp
-    float* fkw = reinterpret_cast<float*>(fsw_smem_raw) + (size_t)warp * NS * SW;  // full keys [NS][SW] of this warp
-    float* fks = fkw + sl;                                                          // column of this lane's slice
-    const float* fkl = fkw + lane;                                                  // element i*L+g of this lane: fkl[i*32]
-    int* fksi = reinterpret_cast<int*>(fks);
+    float* kbase = reinterpret_cast<float*>(fsw_smem_raw) + (size_t)warp * SM::PER_WARP;  // key buffers [NBUF][NS][SW] of this warp
+    float4* tabC = reinterpret_cast<float4*>(kbase + SM::NBUF * SM::KEYS) + lane;           // this lane's coefficients: tabC[32 (i4 / 4)]
+    float4* tabT = tabC + (R / 4) * 32;
 
     const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const int64_t item = wglobal / nchunks;
@@ -199,7 +254,6 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
 
     // point-cloud mode: the slices this lane projects onto (theta rows k0 + part .. + VW - 1), kept in registers
     // (a separate template instance: the registers and branches of this mode cost the graph kernels 12 % when they shared one)
-    constexpr bool cloud = CLOUD;
     float th[CLOUD ? VW : 1][4];
 #pragma unroll
     for (int j = 0; j < (CLOUD ? VW : 1); ++j)
@@ -216,18 +270,103 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
         }
     }
 
-    // software pipeline over segments: order two ahead, row range one ahead, column ids one ahead
-    PkMeta cur, nx1;
-    int s2;
-    int c[NC];
+    // ---- gather of one segment into a key buffer [element][slice], row-wise: LPR adjacent lanes take the SW slices of one row
+    //      (one sector-aligned piece each), 32/LPR rows per instruction.  Graphs: asynchronous copies (LDGSTS) - no register
+    //      staging, nothing waits here; the consumer canonicalises -0 to +0 when it packs (zeros tie, torch.sort compares
+    //      values).  Slots beyond n get a huge finite key whose upper bits differ per slot (their own tie groups).
+    auto fill = [&](float* buf, const PkMeta& m, const int (&cc)[NC]) {
+        float vv[(!CLOUD && !ASYNC) ? NS / RPI : 1][VW];
+#pragma unroll
+        for (int t = 0; t < NS / RPI; ++t) {
+            const int e = t * RPI + lane / LPR;
+            const int part = (lane % LPR) * VW;
+            float* dst = buf + e * SW + part;
+            int row = 0;
+            if (HAS_COL) row = (LPR == 1) ? cc[t] : __shfl_sync(FSW_FULL, cc[(t * RPI) >> 5], ((t * RPI) & 31) + lane / LPR);
+            if constexpr (CLOUD) {
+                // keys on the fly: <x_e, theta_k>, same FMA order as the projection kernel (fsw_project_small_kernel), so the
+                // keys are bit-identical to a materialised projection; the point rows are read contiguously (clamped row:
+                // the loads carry no predicate and are issued back to back)
+                const float* xr = a.projX + fsw_rowoff(m.e0 + min(e, m.n - 1), a.proj_d);
+                float x[4];
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd) x[dd] = dd < a.proj_d ? __ldg(xr + dd) : 0.f;
+                float v[VW];
+#pragma unroll
+                for (int j = 0; j < VW; ++j) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int dd = 0; dd < 4; ++dd)
+                        if (dd < a.proj_d) acc = fmaf(x[dd], th[CLOUD ? j : 0][dd], acc);
+                    v[j] = (e < m.n) ? acc : __int_as_float(0x7f000000 | (e << IDXB));
+                }
+                fsw_sts_words<VW>(dst, v);
+            } else if constexpr (ASYNC) {
+                if (e < m.n) {
+                    const int64_t r64 = HAS_COL ? (int64_t)row : m.e0 + e;
+                    const float* src = xp0 + fsw_rowoff(r64, ldp) + part;
+                    if (ep0 == nullptr) {
+                        fsw_cp_async<VW * 4>(dst, src);
+                    } else {  // edge features: per-slot additive projection (rare path, synchronous)
+                        float v[VW], w[VW];
+                        fsw_ldg_words<VW>(src, v);
+                        fsw_ldg_words<VW>(ep0 + fsw_rowoff(m.e0 + e, ldp) + part, w);
+#pragma unroll
+                        for (int j = 0; j < VW; ++j) v[j] += w[j];
+                        fsw_sts_words<VW>(dst, v);
+                    }
+                } else {
+                    float v[VW];
+                    const float pad = __int_as_float(0x7f000000 | (e << IDXB));
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) v[j] = pad;
+                    fsw_sts_words<VW>(dst, v);
+                }
+            } else {
+                // synchronous: the loads carry no predicate (column ids are clamped, so every lane holds a valid row) and are
+                // all issued before the first one is consumed
+                const int64_t r64 = HAS_COL ? (int64_t)row : m.e0 + min(e, m.n - 1);
+                fsw_ldg_words<VW>(xp0 + fsw_rowoff(r64, ldp) + part, vv[t]);
+            }
+        }
+        if constexpr (!CLOUD && !ASYNC) {
+#pragma unroll
+            for (int t = 0; t < NS / RPI; ++t) {
+                const int e = t * RPI + lane / LPR;
+                const int part = (lane % LPR) * VW;
+                if (ep0 != nullptr && e < m.n) {  // edge features: per-slot additive projection (rare path)
+                    float w[VW];
+                    fsw_ldg_words<VW>(ep0 + fsw_rowoff(m.e0 + e, ldp) + part, w);
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) vv[t][j] += w[j];
+                }
+                const float pad = __int_as_float(0x7f000000 | (e << IDXB));
+#pragma unroll
+                for (int j = 0; j < VW; ++j) vv[t][j] = (e < m.n) ? vv[t][j] : pad;
+                fsw_sts_words<VW>(buf + e * SW + part, vv[t]);
+            }
+        }
+    };
+
+    // software pipeline over segments: order four ahead, row range three ahead, column ids two ahead, keys one ahead
+    PkMeta cur, nx1, nx2;
+    int s3;
+    int c[NC] = {};
     cur.s = fsw_pk_order(a, first, last);
     fsw_pk_range(a, cur.s, cur.e0, cur.n);
-    fsw_pk_cols<NC, HAS_COL>(a.col, cur.e0, cur.n, lane, c);
     nx1.s = fsw_pk_order(a, first + 1, last);
     fsw_pk_range(a, nx1.s, nx1.e0, nx1.n);
-    s2 = fsw_pk_order(a, first + 2, last);
+    nx2.s = fsw_pk_order(a, first + 2, last);
+    fsw_pk_range(a, nx2.s, nx2.e0, nx2.n);
+    s3 = fsw_pk_order(a, first + 3, last);
+    if constexpr (!CLOUD) fsw_pk_cols<NC, HAS_COL>(a.col, cur.e0, cur.n, lane, c);
+    if constexpr (ASYNC) {
+        fill(kbase, cur, c);
+        fsw_pk_cols<NC, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c);
+    }
 
     int n_prev = -1;
+    int pb = 0;  // key buffer of the current segment
     float A = 0.f, A0 = 0.f, A0p = 0.f;
     const float* tc = tck;
     const float* tt = ttk;
@@ -235,57 +374,25 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
 #pragma unroll 1
     for (int q = first; q < last; ++q) {
         const int n = cur.n;
-        // ---- gather, row-wise: LPR adjacent lanes read the SW slices of one row (one sector-aligned vector each), 32/LPR
-        //      rows per instruction; the keys go to shared memory as [element][slice].  -0 becomes +0 (zeros tie, torch.sort compares
-        //      values); slots beyond n get a huge finite key whose upper bits differ per slot (their own tie groups).
-#pragma unroll
-        for (int t = 0; t < NS / RPI; ++t) {
-            const int e = t * RPI + lane / LPR;
-            const int part = (lane % LPR) * VW;
-            float v[VW];
-            int row = 0;
-            if (HAS_COL) row = (LPR == 1) ? c[t] : __shfl_sync(FSW_FULL, c[(t * RPI) >> 5], ((t * RPI) & 31) + lane / LPR);
-            if (CLOUD && e < n) {
-                // keys on the fly: <x_e, theta_k>, same FMA order as the projection kernel (fsw_project_small_kernel), so the
-                // keys are bit-identical to a materialised projection; the point rows are read contiguously
-                const float* xr = a.projX + fsw_rowoff(cur.e0 + e, a.proj_d);
-                float x[4];
-#pragma unroll
-                for (int dd = 0; dd < 4; ++dd) x[dd] = dd < a.proj_d ? __ldg(xr + dd) : 0.f;
-#pragma unroll
-                for (int j = 0; j < VW; ++j) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int dd = 0; dd < 4; ++dd)
-                        if (dd < a.proj_d) acc = fmaf(x[dd], th[CLOUD ? j : 0][dd], acc);
-                    v[j] = acc + 0.0f;
-                }
-            } else if (e < n) {
-                const int64_t r64 = HAS_COL ? (int64_t)row : cur.e0 + e;
-                fsw_ldg_words<VW>(xp0 + fsw_rowoff(r64, ldp) + part, v);
-                if (ep0 != nullptr) {  // edge features: per-slot additive projection (rare path)
-                    float w[VW];
-                    fsw_ldg_words<VW>(ep0 + fsw_rowoff(cur.e0 + e, ldp) + part, w);
-#pragma unroll
-                    for (int j = 0; j < VW; ++j) v[j] += w[j];
-                }
-#pragma unroll
-                for (int j = 0; j < VW; ++j) v[j] += 0.0f;
-            } else {
-                const float pad = __int_as_float(0x7f000000 | (e << IDXB));
-#pragma unroll
-                for (int j = 0; j < VW; ++j) v[j] = pad;
-            }
-            fsw_sts_words<VW>(fkw + e * SW + part, v);
-        }
-        // prefetches for the following segments (their addresses were loaded one iteration ago); with more than 8
-        // column-id registers the ids are fetched at the end of the iteration instead (long segments hide it)
+        float* fkw = kbase + pb * SM::KEYS;       // full keys [NS][SW] of this segment
+        float* fks = fkw + sl;                    // column of this lane's slice
+        const float* fkl = fkw + lane;            // element i*L+g of this lane: fkl[i*32]
+        int* fksi = reinterpret_cast<int*>(fks);
         int cn[PREFETCH_COLS ? NC : 1];
-        if constexpr (PREFETCH_COLS) fsw_pk_cols<NC, HAS_COL>(a.col, nx1.e0, nx1.n, lane, cn);
-        PkMeta nx2;
-        nx2.s = s2;
-        fsw_pk_range(a, s2, nx2.e0, nx2.n);
-        const int s3 = fsw_pk_order(a, q + 3, last);
+        if constexpr (ASYNC) {
+            fsw_cp_async_wait_all();
+            __syncwarp();
+            // the next segment's rows start to arrive while this one is sorted
+            if (q + 1 < last) fill(kbase + (pb ^ 1) * SM::KEYS, nx1, c);
+            if constexpr (PREFETCH_COLS) fsw_pk_cols<NC, HAS_COL>(a.col, nx2.e0, nx2.n, lane, cn);
+        } else {
+            fill(fkw, cur, c);
+            if constexpr (!CLOUD && PREFETCH_COLS) fsw_pk_cols<NC, HAS_COL>(a.col, nx1.e0, nx1.n, lane, cn);
+        }
+        PkMeta nx3;
+        nx3.s = s3;
+        fsw_pk_range(a, s3, nx3.e0, nx3.n);
+        const int s4 = fsw_pk_order(a, q + 4, last);
 
         if (n != n_prev) {
             const double u = xid / (double)n;
@@ -295,14 +402,26 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
             tc = tck + (int64_t)(n - tab_n0) * tab_ld4 * tstride;
             tt = ttk + (int64_t)(n - tab_n0) * tab_ld4 * tstride;
             n_prev = n;
+            if constexpr (TABS) {
+                // this lane's R coefficients (and d/dxi companions) of size class n: shared memory, lane-private rows
+#pragma unroll
+                for (int i4 = 0; i4 < R; i4 += 4) {
+                    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), tv = cv;
+                    const bool live = g * R + i4 < n;
+                    if (live) cv = __ldg(reinterpret_cast<const float4*>(tc + fsw_rowoff(i4 / 4, tstride)));
+                    if (want_dxi && live) tv = __ldg(reinterpret_cast<const float4*>(tt + fsw_rowoff(i4 / 4, tstride)));
+                    tabC[(i4 / 4) * 32] = cv;
+                    if (SAVE_RANK) tabT[(i4 / 4) * 32] = tv;
+                }
+            }
         }
-        __syncwarp();
+        if constexpr (!ASYNC) __syncwarp();
 
         // ---- pack: lane (g, sl) takes elements e = i L + g of its slice: sortable image | element index ----
         int s[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            const int b = __float_as_int(fkl[i * 32]);  // = fkw[(i L + g) SW + sl]
+            const int b = __float_as_int(fkl[i * 32] + 0.0f);  // = fkw[(i L + g) SW + sl]; -0 becomes +0
             const int t = b ^ ((b >> 31) & 0x7fffffff);
             s[i] = ((t & ~IMASK) | g) + i * L;
         }
@@ -332,19 +451,8 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
                         s[i] = upper ? max(s[i], y) : min(s[i], y);
                     }
                 });
-                // the lane now holds a bitonic run: half-cleaners at distance R/2 .. 1
-                if constexpr ((R & (R - 1)) == 0) {
-                    fsw_static_for<fsw_clog2(R)>([&](auto hc) {
-                        constexpr int h = R >> (decltype(hc)::value + 1);
-                        fsw_static_for<R / 2>([&](auto ic) {
-                            constexpr int t = decltype(ic)::value;
-                            constexpr int i = (t / h) * 2 * h + (t % h);
-                            FSW_PK_CMPX(s[i], s[i + h]);
-                        });
-                    });
-                } else {  // run length not a power of two: any sorting network orders the bitonic run
-                    fsw_sort_network<R>([&](int i, int l) { FSW_PK_CMPX(s[i], s[l]); });
-                }
+                // the lane now holds a bitonic run
+                fsw_bitonic_merge<0, R>([&](int i, int l) { FSW_PK_CMPX(s[i], s[l]); });
             });
         } else {
             // many lanes per slice or long runs: the same steps as loops over the merge level and the lane distance
@@ -372,18 +480,7 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
                         s[i] = upper ? max(s[i], y) : min(s[i], y);
                     }
                 }
-                if constexpr ((R & (R - 1)) == 0) {
-                    fsw_static_for<fsw_clog2(R)>([&](auto hc) {
-                        constexpr int h = R >> (decltype(hc)::value + 1);
-                        fsw_static_for<R / 2>([&](auto ic) {
-                            constexpr int t = decltype(ic)::value;
-                            constexpr int i = (t / h) * 2 * h + (t % h);
-                            FSW_PK_CMPX(s[i], s[i + h]);
-                        });
-                    });
-                } else {  // run length not a power of two: any sorting network orders the bitonic run
-                    fsw_sort_network<R>([&](int i, int l) { FSW_PK_CMPX(s[i], s[l]); });
-                }
+                fsw_bitonic_merge<0, R>([&](int i, int l) { FSW_PK_CMPX(s[i], s[l]); });
             }
         }
         // sorted position of s[i] in lane g: p = g R + i
@@ -467,9 +564,14 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
 #pragma unroll
         for (int i4 = 0; i4 < R; i4 += 4) {
             float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), tv = cv;
-            const bool live = p0 + i4 < n;
-            if (live) cv = __ldg(reinterpret_cast<const float4*>(tc + fsw_rowoff(i4 / 4, tstride)));
-            if (want_dxi && live) tv = __ldg(reinterpret_cast<const float4*>(tt + fsw_rowoff(i4 / 4, tstride)));
+            if constexpr (TABS) {
+                cv = tabC[(i4 / 4) * 32];
+                if (want_dxi) tv = tabT[(i4 / 4) * 32];
+            } else {
+                const bool live = p0 + i4 < n;
+                if (live) cv = __ldg(reinterpret_cast<const float4*>(tc + fsw_rowoff(i4 / 4, tstride)));
+                if (want_dxi && live) tv = __ldg(reinterpret_cast<const float4*>(tt + fsw_rowoff(i4 / 4, tstride)));
+            }
             const float cq[4] = {cv.x, cv.y, cv.z, cv.w};
             const float tq[4] = {tv.x, tv.y, tv.z, tv.w};
 #pragma unroll
@@ -506,25 +608,32 @@ __global__ void __launch_bounds__(128, R <= 16 ? 8 : 5) fsw_coop_fwd_kernel(
                     }
                 }
             } else {
-                // row-wise again: lane l writes the SW ranks of elements 32 t + l with one vector store
+                // row-wise again: lane l writes the SW ranks of elements 32 t + l with one vector store; one 64-bit base
+                // per segment, 32-bit offsets per row
+                char* rbase = reinterpret_cast<char*>(ranks + k0) + 2 * fsw_rowoff(cur.e0, ldr);
+                const unsigned rstep = 2u * (unsigned)ldr;
 #pragma unroll
                 for (int t = 0; t < NC; ++t) {
                     const int e = t * 32 + lane;
-                    if (e < n) fsw_store_ranks<SW>(ranks + fsw_rowoff(cur.e0 + e, ldr) + k0, reinterpret_cast<const int*>(fkw) + e * SW);
+                    if (e < n) fsw_store_ranks<SW>(reinterpret_cast<unsigned short*>(rbase + (unsigned)e * rstep), reinterpret_cast<const int*>(fkw) + e * SW);
                 }
             }
-            __syncwarp();  // the next segment's gather overwrites the slots
+            __syncwarp();  // the gather after next overwrites the slots
         }
         // rotate the pipeline
         cur = nx1;
-        if constexpr (PREFETCH_COLS) {
-#pragma unroll
-            for (int m = 0; m < NC; ++m) c[m] = cn[m];
-        } else {
-            fsw_pk_cols<NC, HAS_COL>(a.col, cur.e0, cur.n, lane, c);
-        }
         nx1 = nx2;
-        s2 = s3;
+        nx2 = nx3;
+        s3 = s4;
+        if constexpr (!CLOUD) {
+            if constexpr (PREFETCH_COLS) {
+#pragma unroll
+                for (int m = 0; m < NC; ++m) c[m] = cn[m];
+            } else {
+                fsw_pk_cols<NC, HAS_COL>(a.col, ASYNC ? nx1.e0 : cur.e0, ASYNC ? nx1.n : cur.n, lane, c);
+            }
+            if constexpr (ASYNC) pb ^= 1;
+        }
     }
 }
 
@@ -564,7 +673,7 @@ int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
     constexpr int WPB = 4;
     const int64_t blocks = fsw_cdiv(warps, WPB);
-    const size_t smem = (size_t)WPB * R * 32 * sizeof(float);
+    const size_t smem = (size_t)WPB * FswCoopSmem<R, SAVE_RANK, CLOUD>::PER_WARP * sizeof(float);
     auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK, CLOUD>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const std::string label = std::string(SAVE_RANK ? "fwdr_" : "fwd_") + (CLOUD ? "cloud_u" : "coop_u") + std::to_string(R * L) + "_f32";  // R x L slots
@@ -582,7 +691,8 @@ int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_
     const bool has_col = a.col != nullptr;
     if (a.projX != nullptr) {   // point-cloud mode: dense batches only, keys formed on the fly
         if (has_col) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: point-cloud mode needs a dense batch");
-        return ranks ? launch_coop_fwd<R, L, false, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
+        if constexpr (R >= 24 && L <= 8) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: no point-cloud instance of %d x %d", R, L);
+        else return ranks ? launch_coop_fwd<R, L, false, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
                      : launch_coop_fwd<R, L, false, false, true>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st);
     }
     if constexpr (R * L > 512) {
@@ -618,6 +728,16 @@ int fsw_packed_forward_u(const SegArgs<float>& a, int np, int lo, int hi, float*
     if (gtab_c == nullptr) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: coefficient table missing");
 #define FSW_COOP_CASE(NP_, R_, L_) \
     case NP_: return launch_coop<R_, L_>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);
+    // run-length / lanes-per-slice choice per class: fewer lanes per slice = fewer cross-lane (shuffle) merge steps per element
+    static const bool wide = [] { const char* e = getenv("FSW_COOP_WIDE"); return e == nullptr || atoi(e) != 0; }();
+    if (wide && a.projX == nullptr) {
+        switch (np) {
+            FSW_COOP_CASE(96, 24, 4)
+            FSW_COOP_CASE(128, 32, 4)
+            FSW_COOP_CASE(192, 24, 8)
+            FSW_COOP_CASE(256, 32, 8)
+        }
+    }
     switch (np) {
         FSW_COOP_CASE(48, 12, 4)
         FSW_COOP_CASE(64, 16, 4)

@@ -46,6 +46,23 @@ __device__ __forceinline__ void fsw_ld_range(const SegArgs<T>& a, int s, int64_t
     }
 }
 
+#ifndef FSW_SMALL_ASYNC
+#define FSW_SMALL_ASYNC(NP) ((NP) <= 32)   // fp32 training path: asynchronous gather (LDGSTS) of the next segment's keys
+#endif
+
+// shared memory of one warp of fsw_small_fwd_kernel
+template <typename T, int NP, bool SAVE_RANK>
+struct FswSmallSmem {
+    static constexpr bool ASYNC = SAVE_RANK && sizeof(T) == 4 && FSW_SMALL_ASYNC(NP);
+    static constexpr size_t PER_WARP = (size_t)NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + (ASYNC ? 2 : 1) * sizeof(int) : 0));
+};
+
+__device__ __forceinline__ void fsw_cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fsw_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int NP, bool HAS_COL, bool SAVE_RANK>
 __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks,
@@ -56,11 +73,13 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // per warp: coefficient table [NP][32] T; when SAVE_RANK (training) also the d/dxi table [NP][32] T and the
-    // rank scratch [NP][32] int
-    constexpr size_t kWarpBytes = (size_t)NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + sizeof(int) : 0));
+    // key / rank scratch [NP][32] int (two of them when the gather of the next segment is asynchronous)
+    constexpr bool ASYNC = FswSmallSmem<T, NP, SAVE_RANK>::ASYNC;
+    constexpr size_t kWarpBytes = FswSmallSmem<T, NP, SAVE_RANK>::PER_WARP;
     T* tab = reinterpret_cast<T*>(fsw_smem_raw + warp * kWarpBytes);
     T* tabt = tab + NP * 32;
-    int* srank = reinterpret_cast<int*>(tabt + NP * 32);
+    int* srank0 = reinterpret_cast<int*>(tabt + NP * 32);
+    int* srank = srank0;
     (void)srank;
     (void)tabt;
 
@@ -81,8 +100,9 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
     const char* xp_bytes = reinterpret_cast<const char*>(a.Xp + kk);
     const char* ep_bytes = a.Ep ? reinterpret_cast<const char*>(a.Ep + kk) : nullptr;
 
-    // ---- software pipeline over segments: order two ahead, row range one ahead, column ids one ahead ----
-    SegMeta cur, nx1;
+    // ---- software pipeline over segments: order two ahead, row range one ahead, column ids one ahead (asynchronous gather:
+    //      everything one segment further ahead, and the keys of the next segment in flight into the other key buffer) ----
+    SegMeta cur, nx1, nx2;
     int s2;
     int c0, c1;
     cur.s = fsw_ld_order(a, first, last);
@@ -91,6 +111,33 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
     nx1.s = fsw_ld_order(a, first + 1, last);
     fsw_ld_range(a, nx1.s, nx1.e0, nx1.n);
     s2 = fsw_ld_order(a, first + 2, last);
+    nx2 = nx1;
+    // keys of segment m (column ids cc0 / cc1) -> key buffer: one 4-byte LDGSTS per element and lane, nothing waits here.
+    // With edge features (rare) the two projections are added on the way, synchronously.
+    auto fill = [&](int* buf, const SegMeta& m, int cc0, int cc1) {
+        float* dst = reinterpret_cast<float*>(buf) + lane;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            int row = 0;
+            if (HAS_COL) row = __shfl_sync(FSW_FULL, (j < 32) ? cc0 : cc1, j & 31);
+            if (j < m.n) {
+                const char* src = HAS_COL ? xp_bytes + fsw_rowoff(row, ldb) : xp_bytes + (m.e0 + j) * ldb;
+                if (ep_bytes == nullptr) {
+                    fsw_cp_async4(dst + j * 32, src);
+                } else {
+                    dst[j * 32] = __ldg(reinterpret_cast<const float*>(src)) + __ldg(reinterpret_cast<const float*>(ep_bytes + (m.e0 + j) * ldb));
+                }
+            }
+        }
+    };
+    int pb = 0;
+    if constexpr (ASYNC) {
+        fill(srank0, cur, c0, c1);
+        fsw_load_cols<NP, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c0, c1);   // from here on: the column ids of the NEXT segment
+        nx2.s = s2;
+        fsw_ld_range(a, s2, nx2.e0, nx2.n);
+        s2 = fsw_ld_order(a, first + 3, last);                           // and the order entry three ahead
+    }
 
     int n_prev = -1;
     T A = (T)0, A0 = (T)0, A0p = (T)0;
@@ -99,15 +146,27 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
 
     for (int q = first; q < last; ++q) {
         const int n = cur.n;
-        T key[NP];
-        fsw_gather_lean<T, NP, HAS_COL>(xp_bytes, ldb, ep_bytes, cur.e0, n, c0, c1, key);
-        // prefetches for the following segments (their addresses were loaded one iteration ago)
+        T key[ASYNC ? 1 : NP];
         int c0n, c1n;
-        fsw_load_cols<NP, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c0n, c1n);
-        SegMeta nx2;
-        nx2.s = s2;
-        fsw_ld_range(a, s2, nx2.e0, nx2.n);
-        const int s3 = fsw_ld_order(a, q + 3, last);
+        SegMeta nxn;   // the segment entering the pipeline
+        int s3;
+        if constexpr (ASYNC) {
+            // every lane reads back only what it copied itself (its own slice column): no warp barrier
+            fsw_cp_async_wait();
+            srank = srank0 + pb * (NP * 32);
+            if (q + 1 < last) fill(srank0 + (pb ^ 1) * (NP * 32), nx1, c0, c1);
+            fsw_load_cols<NP, HAS_COL>(a.col, nx2.e0, nx2.n, lane, c0n, c1n);
+            nxn.s = s2;
+            fsw_ld_range(a, s2, nxn.e0, nxn.n);
+            s3 = fsw_ld_order(a, q + 4, last);
+        } else {
+            fsw_gather_lean<T, NP, HAS_COL>(xp_bytes, ldb, ep_bytes, cur.e0, n, c0, c1, key);
+            // prefetches for the following segments (their addresses were loaded one iteration ago)
+            fsw_load_cols<NP, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c0n, c1n);
+            nxn.s = s2;
+            fsw_ld_range(a, s2, nxn.e0, nxn.n);
+            s3 = fsw_ld_order(a, q + 3, last);
+        }
 
         if (n != n_prev) {
             const double u = xid / (double)n;
@@ -136,8 +195,15 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
             int p[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                const float v = (j < n) ? key[j] + 0.0f : __int_as_float(0x7f000000 | (j << IB));  // -0 -> +0; padding: own groups
-                fk[j * 32] = v;
+                float v;
+                if constexpr (ASYNC) {
+                    // the keys wait in shared memory already (a -0 stays there: it compares and multiplies like +0)
+                    v = (j < n) ? fk[j * 32] + 0.0f : __int_as_float(0x7f000000 | (j << IB));
+                    if (j >= n) fk[j * 32] = v;
+                } else {
+                    v = (j < n) ? key[j] + 0.0f : __int_as_float(0x7f000000 | (j << IB));  // -0 -> +0; padding: own groups
+                    fk[j * 32] = v;
+                }
                 const int b = __float_as_int(v);
                 const int t = b ^ ((b >> 31) & 0x7fffffff);
                 p[j] = (t & ~IM) | j;
@@ -229,7 +295,13 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
         cur = nx1;
         c0 = c0n;
         c1 = c1n;
-        nx1 = nx2;
+        if constexpr (ASYNC) {
+            nx1 = nx2;
+            nx2 = nxn;
+            pb ^= 1;
+        } else {
+            nx1 = nxn;
+        }
         s2 = s3;
     }
 }
@@ -1049,7 +1121,7 @@ int launch_small_fwd(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out
     const int G = pick_G(hi - lo, nchunks, 148 * 32, 128);
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
-    const size_t smem = (size_t)4 * NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + sizeof(int) : 0));
+    const size_t smem = (size_t)4 * FswSmallSmem<T, NP, SAVE_RANK>::PER_WARP;
     auto kern = fsw_small_fwd_kernel<T, NP, HAS_COL, SAVE_RANK>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const std::string label = std::string(SAVE_RANK ? "fwdr_small_u" : "fwd_small_u") + std::to_string(NP) + (sizeof(T) == 4 ? "_f32" : "_f64");

@@ -144,14 +144,14 @@ __device__ __forceinline__ void fsw_gather_lean(const char* __restrict__ xp_byte
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             const int row = __shfl_sync(FSW_FULL, (j < 32) ? c0 : c1, j & 31);
-            key[j] = __ldg(reinterpret_cast<const T*>(xp_bytes + (int64_t)row * ldb));
+            key[j] = __ldg(reinterpret_cast<const T*>(xp_bytes + fsw_rowoff(row, ldb)));   // one IMAD.WIDE per gathered row
         }
     } else {
         const char* __restrict__ base = xp_bytes + ebase * ldb;
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             T v = (T)0;
-            if (j < cnt) v = __ldg(reinterpret_cast<const T*>(base + (int64_t)j * ldb));
+            if (j < cnt) v = __ldg(reinterpret_cast<const T*>(base + fsw_rowoff(j, ldb)));
             key[j] = v;
         }
     }
@@ -160,7 +160,7 @@ __device__ __forceinline__ void fsw_gather_lean(const char* __restrict__ xp_byte
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             T v = (T)0;
-            if (j < cnt) v = __ldg(reinterpret_cast<const T*>(eb + (int64_t)j * ldb));
+            if (j < cnt) v = __ldg(reinterpret_cast<const T*>(eb + fsw_rowoff(j, ldb)));
             key[j] += v;
         }
     }
