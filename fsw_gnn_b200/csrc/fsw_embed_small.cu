@@ -46,23 +46,6 @@ __device__ __forceinline__ void fsw_ld_range(const SegArgs<T>& a, int s, int64_t
     }
 }
 
-#ifndef FSW_SMALL_ASYNC
-#define FSW_SMALL_ASYNC(NP) ((NP) <= 32)   // fp32 training path: asynchronous gather (LDGSTS) of the next segment's keys
-#endif
-
-// shared memory of one warp of fsw_small_fwd_kernel
-template <typename T, int NP, bool SAVE_RANK>
-struct FswSmallSmem {
-    static constexpr bool ASYNC = SAVE_RANK && sizeof(T) == 4 && FSW_SMALL_ASYNC(NP);
-    static constexpr size_t PER_WARP = (size_t)NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + (ASYNC ? 2 : 1) * sizeof(int) : 0));
-};
-
-__device__ __forceinline__ void fsw_cp_async4(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void fsw_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int NP, bool HAS_COL, bool SAVE_RANK>
 __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int seg_lo, int seg_hi, int G, int nchunks,
@@ -73,13 +56,11 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     // per warp: coefficient table [NP][32] T; when SAVE_RANK (training) also the d/dxi table [NP][32] T and the
-    // key / rank scratch [NP][32] int (two of them when the gather of the next segment is asynchronous)
-    constexpr bool ASYNC = FswSmallSmem<T, NP, SAVE_RANK>::ASYNC;
-    constexpr size_t kWarpBytes = FswSmallSmem<T, NP, SAVE_RANK>::PER_WARP;
+    // rank scratch [NP][32] int
+    constexpr size_t kWarpBytes = (size_t)NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + sizeof(int) : 0));
     T* tab = reinterpret_cast<T*>(fsw_smem_raw + warp * kWarpBytes);
     T* tabt = tab + NP * 32;
-    int* srank0 = reinterpret_cast<int*>(tabt + NP * 32);
-    int* srank = srank0;
+    int* srank = reinterpret_cast<int*>(tabt + NP * 32);
     (void)srank;
     (void)tabt;
 
@@ -100,9 +81,8 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
     const char* xp_bytes = reinterpret_cast<const char*>(a.Xp + kk);
     const char* ep_bytes = a.Ep ? reinterpret_cast<const char*>(a.Ep + kk) : nullptr;
 
-    // ---- software pipeline over segments: order two ahead, row range one ahead, column ids one ahead (asynchronous gather:
-    //      everything one segment further ahead, and the keys of the next segment in flight into the other key buffer) ----
-    SegMeta cur, nx1, nx2;
+    // ---- software pipeline over segments: order two ahead, row range one ahead, column ids one ahead ----
+    SegMeta cur, nx1;
     int s2;
     int c0, c1;
     cur.s = fsw_ld_order(a, first, last);
@@ -111,33 +91,6 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
     nx1.s = fsw_ld_order(a, first + 1, last);
     fsw_ld_range(a, nx1.s, nx1.e0, nx1.n);
     s2 = fsw_ld_order(a, first + 2, last);
-    nx2 = nx1;
-    // keys of segment m (column ids cc0 / cc1) -> key buffer: one 4-byte LDGSTS per element and lane, nothing waits here.
-    // With edge features (rare) the two projections are added on the way, synchronously.
-    auto fill = [&](int* buf, const SegMeta& m, int cc0, int cc1) {
-        float* dst = reinterpret_cast<float*>(buf) + lane;
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-            int row = 0;
-            if (HAS_COL) row = __shfl_sync(FSW_FULL, (j < 32) ? cc0 : cc1, j & 31);
-            if (j < m.n) {
-                const char* src = HAS_COL ? xp_bytes + fsw_rowoff(row, ldb) : xp_bytes + (m.e0 + j) * ldb;
-                if (ep_bytes == nullptr) {
-                    fsw_cp_async4(dst + j * 32, src);
-                } else {
-                    dst[j * 32] = __ldg(reinterpret_cast<const float*>(src)) + __ldg(reinterpret_cast<const float*>(ep_bytes + (m.e0 + j) * ldb));
-                }
-            }
-        }
-    };
-    int pb = 0;
-    if constexpr (ASYNC) {
-        fill(srank0, cur, c0, c1);
-        fsw_load_cols<NP, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c0, c1);   // from here on: the column ids of the NEXT segment
-        nx2.s = s2;
-        fsw_ld_range(a, s2, nx2.e0, nx2.n);
-        s2 = fsw_ld_order(a, first + 3, last);                           // and the order entry three ahead
-    }
 
     int n_prev = -1;
     T A = (T)0, A0 = (T)0, A0p = (T)0;
@@ -146,27 +99,15 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
 
     for (int q = first; q < last; ++q) {
         const int n = cur.n;
-        T key[ASYNC ? 1 : NP];
+        T key[NP];
+        fsw_gather_lean<T, NP, HAS_COL>(xp_bytes, ldb, ep_bytes, cur.e0, n, c0, c1, key);
+        // prefetches for the following segments (their addresses were loaded one iteration ago)
         int c0n, c1n;
-        SegMeta nxn;   // the segment entering the pipeline
-        int s3;
-        if constexpr (ASYNC) {
-            // every lane reads back only what it copied itself (its own slice column): no warp barrier
-            fsw_cp_async_wait();
-            srank = srank0 + pb * (NP * 32);
-            if (q + 1 < last) fill(srank0 + (pb ^ 1) * (NP * 32), nx1, c0, c1);
-            fsw_load_cols<NP, HAS_COL>(a.col, nx2.e0, nx2.n, lane, c0n, c1n);
-            nxn.s = s2;
-            fsw_ld_range(a, s2, nxn.e0, nxn.n);
-            s3 = fsw_ld_order(a, q + 4, last);
-        } else {
-            fsw_gather_lean<T, NP, HAS_COL>(xp_bytes, ldb, ep_bytes, cur.e0, n, c0, c1, key);
-            // prefetches for the following segments (their addresses were loaded one iteration ago)
-            fsw_load_cols<NP, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c0n, c1n);
-            nxn.s = s2;
-            fsw_ld_range(a, s2, nxn.e0, nxn.n);
-            s3 = fsw_ld_order(a, q + 3, last);
-        }
+        fsw_load_cols<NP, HAS_COL>(a.col, nx1.e0, nx1.n, lane, c0n, c1n);
+        SegMeta nx2;
+        nx2.s = s2;
+        fsw_ld_range(a, s2, nx2.e0, nx2.n);
+        const int s3 = fsw_ld_order(a, q + 3, last);
 
         if (n != n_prev) {
             const double u = xid / (double)n;
@@ -195,15 +136,8 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
             int p[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                float v;
-                if constexpr (ASYNC) {
-                    // the keys wait in shared memory already (a -0 stays there: it compares and multiplies like +0)
-                    v = (j < n) ? fk[j * 32] + 0.0f : __int_as_float(0x7f000000 | (j << IB));
-                    if (j >= n) fk[j * 32] = v;
-                } else {
-                    v = (j < n) ? key[j] + 0.0f : __int_as_float(0x7f000000 | (j << IB));  // -0 -> +0; padding: own groups
-                    fk[j * 32] = v;
-                }
+                const float v = (j < n) ? key[j] + 0.0f : __int_as_float(0x7f000000 | (j << IB));  // -0 -> +0; padding: own groups
+                fk[j * 32] = v;
                 const int b = __float_as_int(v);
                 const int t = b ^ ((b >> 31) & 0x7fffffff);
                 p[j] = (t & ~IM) | j;
@@ -295,13 +229,7 @@ __global__ void __launch_bounds__(128) fsw_small_fwd_kernel(SegArgs<T> a, int se
         cur = nx1;
         c0 = c0n;
         c1 = c1n;
-        if constexpr (ASYNC) {
-            nx1 = nx2;
-            nx2 = nxn;
-            pb ^= 1;
-        } else {
-            nx1 = nxn;
-        }
+        nx1 = nx2;
         s2 = s3;
     }
 }
@@ -1081,6 +1009,208 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdT_kernel(SegArgs<float>
         reinterpret_cast<float4*>(op)[h] = make_float4(acc2[2 * h].x, acc2[2 * h].y, acc2[2 * h + 1].x, acc2[2 * h + 1].y);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Source-major rank backward, streaming version: the (segment, slot) pairs of a run of consecutive source rows are ONE stream
+// per warp, and the rank row and the pre-scaled gradient row of every pair travel global -> shared memory as asynchronous
+// copies (LDGSTS, 16 bytes per lane) into a ring of D pairs per warp.  Nothing is staged in registers, so D - 1 pairs
+// (~1.2 KB each at K = 199) are in flight per warp whatever the register budget - the register-staged kernel above holds 2 to 4
+// and is bound by the DRAM round trip (profiles/r2/README.md).  Every lane reads back only the bytes it copied itself
+// (its own 8 slices), so no barrier is needed; row boundaries only matter to the consumer, the copies run ahead across them.
+// ---------------------------------------------------------------------------------------------------
+template <int BYTES>
+__device__ __forceinline__ void fsw_ldgsts(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+template <>
+__device__ __forceinline__ void fsw_ldgsts<8>(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fsw_ldgsts_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fsw_ldgsts_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int V, int D>
+struct FswRankStream {
+    static constexpr int RB = V * 2;                          // rank bytes per lane and pair
+    static constexpr int SLOT = 32 * RB + 32 * V * 4;         // ranks [32][RB] + gradient planes [V / 4][32][16]
+    static constexpr int PER_WARP = D * SLOT;
+};
+
+template <int V, int D, int MINB>
+__global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float> a, int64_t Nrows, int nchunks, int rpw,
+                                                            const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
+                                                            const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
+                                                            const unsigned short* __restrict__ ranks, int64_t ldr,
+                                                            const float* __restrict__ GA, float* __restrict__ dXp,
+                                                            float* __restrict__ dEp) {
+    using RS = FswRankStream<V, D>;
+    constexpr int P = V / 4;
+    static_assert(V == 4 || V == 8, "4 or 8 slices per lane");
+    extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
+    const int lane = threadIdx.x & 31;
+    unsigned char* ring = fsw_smem_raw + (size_t)(threadIdx.x >> 5) * RS::PER_WARP + lane * 16;
+    const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t item = wglobal / nchunks;
+    const int chunk = (int)(wglobal - item * nchunks);
+    const int64_t j0 = item * rpw;
+    if (j0 >= Nrows) return;
+    const int nrows = (int)((j0 + rpw < Nrows) ? rpw : Nrows - j0);   // <= 32
+    const int k0 = (chunk * 32 + lane) * V;
+    const int ldp = (int)a.ldp, ldri = (int)ldr;
+    const bool lane_on = k0 < ldp;
+    float2 acc2[V / 2], xi2[V / 2];
+#pragma unroll
+    for (int q = 0; q < V / 2; ++q) {
+        acc2[q] = make_float2(0.f, 0.f);
+        const int ka = k0 + 2 * q;
+        xi2[q] = make_float2(ka < a.K ? __ldg(a.freqs + ka) : 0.f, ka + 1 < a.K ? __ldg(a.freqs + ka + 1) : 0.f);
+    }
+    // lane l: end of the pair list of row j0 + l
+    const int my_end = __ldg(tptr + j0 + min(lane + 1, nrows));
+    const int T0 = __ldg(tptr + j0);
+    const int T1 = __shfl_sync(FSW_FULL, my_end, nrows - 1);
+    const unsigned short* rbase = ranks + k0;
+    const float* gbase = GA + k0;
+
+    // blocks of 32 (segment, slot, n) triples, one per lane: `cur` serves the copies being issued, `prv` the pairs still
+    // being consumed behind a block boundary, `nxt` is in flight
+    const int tlast = max(T1 - 1, 0);
+    int bs = T0;
+    int cur_seg = __ldg(tseg + min(bs + lane, tlast)), cur_slot = __ldg(tslot + min(bs + lane, tlast)), cur_n = __ldg(tn + min(bs + lane, tlast));
+    int nxt_seg = __ldg(tseg + min(bs + 32 + lane, tlast)), nxt_slot = __ldg(tslot + min(bs + 32 + lane, tlast)), nxt_n = __ldg(tn + min(bs + 32 + lane, tlast));
+    int prv_slot = 0, prv_n = 0;
+
+    int issued = T0;
+    int islot = 0;   // ring slot of the next copy
+    auto issue = [&]() {
+        if (issued < T1) {
+            if (issued - bs == 32) {
+                prv_slot = cur_slot;
+                prv_n = cur_n;
+                cur_seg = nxt_seg;
+                cur_slot = nxt_slot;
+                cur_n = nxt_n;
+                bs += 32;
+                nxt_seg = __ldg(tseg + min(bs + 32 + lane, tlast));
+                nxt_slot = __ldg(tslot + min(bs + 32 + lane, tlast));
+                nxt_n = __ldg(tn + min(bs + 32 + lane, tlast));
+            }
+            const int src = issued - bs;
+            const int seg = __shfl_sync(FSW_FULL, cur_seg, src);
+            const int slot = __shfl_sync(FSW_FULL, cur_slot, src);
+            unsigned char* sb = ring + islot * RS::SLOT;
+            if (lane_on) {
+                if constexpr (V == 8) fsw_ldgsts<16>(sb, rbase + fsw_rowoff(slot, ldri));
+                else fsw_ldgsts<8>(sb - lane * 8, rbase + fsw_rowoff(slot, ldri));   // 8-byte pieces: lane * 8
+                const float* gp = gbase + fsw_rowoff(seg, ldp);
+#pragma unroll
+                for (int h = 0; h < P; ++h) fsw_ldgsts<16>(sb + 32 * RS::RB + h * 512, gp + 4 * h);
+            }
+            ++issued;
+            islot = (islot + 1 == D) ? 0 : islot + 1;
+        }
+        fsw_ldgsts_commit();
+    };
+    auto f2c = [](float c) { return make_float2(c, c); };
+
+#pragma unroll 1
+    for (int i = 0; i < D - 1; ++i) issue();
+
+    int jr = 0;
+    int row_end = __shfl_sync(FSW_FULL, my_end, 0);
+    int cslot = 0;
+    auto flush_row = [&]() {
+        if (lane_on) {
+            float* op = dXp + fsw_rowoff(j0 + jr, ldp) + k0;
+#pragma unroll
+            for (int h = 0; h < P; ++h)
+                reinterpret_cast<float4*>(op)[h] = make_float4(acc2[2 * h].x, acc2[2 * h].y, acc2[2 * h + 1].x, acc2[2 * h + 1].y);
+        }
+#pragma unroll
+        for (int q = 0; q < V / 2; ++q) acc2[q] = make_float2(0.f, 0.f);
+        ++jr;
+        row_end = __shfl_sync(FSW_FULL, my_end, min(jr, 31));
+    };
+#pragma unroll 1
+    for (int tc = T0; tc < T1; ++tc) {
+        issue();                    // pair tc + D - 1 (or an empty group): D groups are outstanding
+        fsw_ldgsts_wait<D - 1>();   // all but the newest D - 1: the copies of pair tc have landed
+        while (tc >= row_end) flush_row();   // warp-uniform; also steps over rows without pairs
+        const int src = tc - bs;    // >= -32: the consumer trails the copies by less than D <= 32 pairs
+        const int n_c = __shfl_sync(FSW_FULL, cur_n, src & 31), n_p = __shfl_sync(FSW_FULL, prv_n, src & 31);
+        const int n = src >= 0 ? n_c : n_p;
+        const unsigned char* sb = ring + cslot * RS::SLOT;
+        cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+        if (n <= 0) continue;       // pair of a segment that is not served here (general weights, more than nmax elements)
+        unsigned w[V / 2];
+        float ga[V];
+        if constexpr (V == 8) {
+            const uint4 t = *reinterpret_cast<const uint4*>(sb);
+            w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+        } else {
+            const uint2 t = *reinterpret_cast<const uint2*>(sb - lane * 8);
+            w[0] = t.x; w[1] = t.y;
+        }
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            const float4 t = *reinterpret_cast<const float4*>(sb + 32 * RS::RB + h * 512);
+            ga[4 * h] = t.x; ga[4 * h + 1] = t.y; ga[4 * h + 2] = t.z; ga[4 * h + 3] = t.w;
+        }
+        // the arithmetic of fsw_rank_bwdT_kernel (see there): cos(pi (2r+1) xi / n) on pairs of slices, packed fp32
+        const float nf = (float)n;                         // exact: n <= 32768
+        const float ih = __frcp_rn(nf);
+        const float il = fmaf(-nf, ih, 1.0f) * ih;         // 1/n = ih + il
+        const float2 ih2 = f2c(ih), nih2 = f2c(-ih), nil2 = f2c(-il);
+        float v[V];
+        (void)v;
+#pragma unroll
+        for (int pr = 0; pr < V / 2; ++pr) {
+            const float2 uh = __fmul2_rn(xi2[pr], ih2);
+            const float2 nue = __ffma2_rn(xi2[pr], nih2, uh);          // -(xi ih - uh), exact
+            const float2 nul = __ffma2_rn(xi2[pr], nil2, nue);         // -ul
+            const float2 mb = make_float2(__uint_as_float(0x4B000001u | ((w[pr] << 1) & 0x1fffeu)),
+                                          __uint_as_float(0x4B000001u | ((w[pr] >> 15) & 0x1fffeu)));
+            const float2 m = __fadd2_rn(mb, f2c(-8388608.0f));         // 2r+1, exact below 2^23
+            const float2 nm = __ffma2_rn(mb, f2c(-1.0f), f2c(8388608.0f));
+            const float2 ph = __fmul2_rn(m, uh);
+            const float2 nqe = __ffma2_rn(nm, uh, ph);                 // ph - m uh, exact
+            const float2 npl = __ffma2_rn(m, nul, nqe);                // -(m ul + m uh - ph)
+            const float2 t = __fadd2_rn(ph, f2c(12582912.0f));
+            const float2 kk = __fadd2_rn(t, f2c(-12582912.0f));        // rint(ph)
+            const float2 red = __ffma2_rn(kk, f2c(-1.0f), ph);         // exact
+            const float2 x = __ffma2_rn(npl, f2c(-1.0f), red);
+            const float2 y2 = __fmul2_rn(x, x);
+            float2 c = __ffma2_rn(y2, f2c(1.929574e-3f), f2c(-2.580689e-2f));
+            c = __ffma2_rn(y2, c, f2c(2.353306e-1f));
+            c = __ffma2_rn(y2, c, f2c(-1.335263f));
+            c = __ffma2_rn(y2, c, f2c(4.058712f));
+            c = __ffma2_rn(y2, c, f2c(-4.934802f));
+            c = __ffma2_rn(y2, c, f2c(1.0f));
+            const float2 gs = make_float2(__uint_as_float(__float_as_uint(ga[2 * pr]) ^ (__float_as_uint(t.x) << 31)),
+                                          __uint_as_float(__float_as_uint(ga[2 * pr + 1]) ^ (__float_as_uint(t.y) << 31)));
+            if (dEp) {
+                const float2 vv = __fmul2_rn(gs, c);
+                v[2 * pr] = vv.x;
+                v[2 * pr + 1] = vv.y;
+                acc2[pr] = __fadd2_rn(acc2[pr], vv);
+            } else {
+                acc2[pr] = __ffma2_rn(gs, c, acc2[pr]);
+            }
+        }
+        if (dEp) {
+            const int s_c = __shfl_sync(FSW_FULL, cur_slot, src & 31), s_p = __shfl_sync(FSW_FULL, prv_slot, src & 31);
+            if (lane_on) {
+                float* ep = dEp + fsw_rowoff(src >= 0 ? s_c : s_p, ldp) + k0;
+#pragma unroll
+                for (int h = 0; h < P; ++h) reinterpret_cast<float4*>(ep)[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+            }
+        }
+    }
+    while (jr < nrows) flush_row();   // the last row with pairs and the rows without any
+}
+
 template <bool HAS_COL, bool NEED_DXI>
 int launch_rank_bwdg(const SegArgs<float>& a, int lo, int hi, const unsigned short* ranks, int64_t ldr, const float* g, int64_t ld_g,
                      int64_t g_col0, float* dXp, float* dEp, double* dfreqs, float* tables, cudaStream_t st) {
@@ -1121,7 +1251,7 @@ int launch_small_fwd(const SegArgs<T>& a, int lo, int hi, T* out, int64_t ld_out
     const int G = pick_G(hi - lo, nchunks, 148 * 32, 128);
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
-    const size_t smem = (size_t)4 * FswSmallSmem<T, NP, SAVE_RANK>::PER_WARP;
+    const size_t smem = (size_t)4 * NP * 32 * (sizeof(T) + (SAVE_RANK ? sizeof(T) + sizeof(int) : 0));
     auto kern = fsw_small_fwd_kernel<T, NP, HAS_COL, SAVE_RANK>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const std::string label = std::string(SAVE_RANK ? "fwdr_small_u" : "fwd_small_u") + std::to_string(NP) + (sizeof(T) == 4 ? "_f32" : "_f64");
@@ -1263,6 +1393,34 @@ int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, int n
     const int64_t warps = Nrows * nchunks;
     const int64_t blocks = fsw_cdiv(warps, 4);
     fsw_prof_begin("bwd_rankT_u32768_f32", st);
+    // default: the streaming kernel (asynchronous copies into a shared-memory ring, 16 source rows per warp);
+    // FSW_RANKT_STREAM=0 selects the register-staged kernel
+    static const int stream_mode = [] { const char* e = getenv("FSW_RANKT_STREAM"); return e ? atoi(e) : 1; }();
+    if (stream_mode != 0) {
+        static const int rpw_env = [] { const char* e = getenv("FSW_RANKT_RPW"); return e ? atoi(e) : 16; }();
+        const int rpw = rpw_env < 1 ? 1 : (rpw_env > 32 ? 32 : rpw_env);
+        const int64_t swarps = fsw_cdiv(Nrows, rpw) * nchunks;
+        const int64_t sblocks = fsw_cdiv(swarps, 4);
+#define FSW_RANKS_LAUNCH(V_, D_, MINB_)                                                                                              \
+    do {                                                                                                                             \
+        auto kern = fsw_rank_bwdS_kernel<V_, D_, MINB_>;                                                                             \
+        const size_t smem = (size_t)4 * FswRankStream<V_, D_>::PER_WARP;                                                             \
+        FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                \
+        kern<<<(unsigned)sblocks, 128, smem, st>>>(a, Nrows, nchunks, rpw, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp);     \
+    } while (0)
+        if (wide) {
+            // measured at configs[3] (ms per launch; register-staged kernel 22.35): ring of 6 pairs x 5 CTAs 17.97,
+            // 8 x 4 CTAs 18.74, 5 x 6 CTAs 18.28, 12 x 3 CTAs 20.66; 8 / 16 / 32 rows per warp within 0.3 %
+            if (stream_mode == 2) FSW_RANKS_LAUNCH(8, 8, 4);
+            else FSW_RANKS_LAUNCH(8, 6, 5);
+        } else {
+            FSW_RANKS_LAUNCH(4, 8, 6);
+        }
+#undef FSW_RANKS_LAUNCH
+        fsw_prof_end(st);
+        FSW_CHECK_LAUNCH("fsw_rank_bwdS_kernel");
+        return FSW_OK;
+    }
     // 4 CTAs per SM: 125 registers, no spills (5 CTAs at 96 registers spill inside the pair loop: 28.2 vs 22.9 ms per launch)
     // L2 prefetch of every pair row of a block of triples: measured SLOWER (25.2 vs 22.9 ms per launch at configs[3]) - the
     // kernel is not waiting on those loads; kept behind a knob for other shapes

@@ -444,8 +444,8 @@ def test_config3_pointcloud_gradients_k256():
 @pytest.mark.parametrize("n,d,K", [(33, 1, 9), (100, 3, 37), (512, 4, 64), (777, 2, 40), (1024, 3, 256)])
 def test_cloud_mode_equals_projected_path(n, d, K):
     """point-cloud mode (keys formed inside the sort kernel, slice-major ranks, dL/dp evaluated where it is consumed) against the
-    general dense path (projected matrix + row-major ranks + contractions): identical keys, so the values are bit-identical and
-    the gradients agree to fp32 summation order"""
+    general dense path (projected matrix + row-major ranks + contractions): identical keys, so values and gradients agree
+    to fp32 summation order"""
     from fsw_gnn_b200 import FSW_embedding, ops, _lib
     rng = np.random.default_rng(n + d)
     B = 7
@@ -473,7 +473,9 @@ def test_cloud_mode_equals_projected_path(n, d, K):
             ops.CLOUD_MODE = True
     assert "bwd_cloud_dx" in res[True][4] and "bwd_cloud_dx" not in res[False][4]
     assert not any(k.startswith(("gemm", "project", "umma")) for k in res[True][4]), sorted(res[True][4])
-    assert torch.equal(res[True][0], res[False][0])
+    # identical keys and ranks; the Fourier sums may be split over a different number of lanes in the two paths (the projected
+    # path takes the longer-run instances of the packed-key kernel), so the values agree to fp32 summation order, STRICT
+    check("cloud vs projected n=%d d=%d K=%d values" % (n, d, K), res[True][0].cpu().numpy(), res[False][0].cpu().numpy().astype(np.float64), mode="strict")
     for name, i_ in (("dX", 1), ("dtheta", 2), ("dxi", 3)):
         a, b = res[True][i_], res[False][i_]
         check("cloud vs projected n=%d d=%d K=%d %s" % (n, d, K, name), a.cpu().numpy(), b.cpu().numpy().astype(np.float64), mode="scaled", grad=True)
