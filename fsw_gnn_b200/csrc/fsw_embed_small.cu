@@ -1017,16 +1017,6 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdT_kernel(SegArgs<float>
 // and is bound by the DRAM round trip (profiles/r2/README.md).  Every lane reads back only the bytes it copied itself
 // (its own 8 slices), so no barrier is needed; row boundaries only matter to the consumer, the copies run ahead across them.
 // ---------------------------------------------------------------------------------------------------
-template <int BYTES>
-__device__ __forceinline__ void fsw_ldgsts(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
-}
-template <>
-__device__ __forceinline__ void fsw_ldgsts<8>(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void fsw_ldgsts_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void fsw_ldgsts_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1038,7 +1028,26 @@ struct FswRankStream {
     static constexpr int PER_WARP = D * SLOT;
 };
 
-template <int V, int D, int MINB>
+// predicated asynchronous copy (no branch around it) to a 32-bit shared-memory address: BYTES = 8 or 16
+template <int BYTES>
+__device__ __forceinline__ void fsw_ldgsts_if(unsigned on, unsigned sdst, const void* gsrc) {
+    if constexpr (BYTES == 16)
+        asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }" ::"r"(sdst), "l"(gsrc), "r"(on) : "memory");
+    else
+        asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 8; }" ::"r"(sdst), "l"(gsrc), "r"(on) : "memory");
+}
+__device__ __forceinline__ uint4 fsw_lds128(unsigned saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 fsw_lds64(unsigned saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
+
+template <int V, int D, int MINB, bool HAS_EP>
 __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float> a, int64_t Nrows, int nchunks, int rpw,
                                                             const int32_t* __restrict__ tptr, const int32_t* __restrict__ tseg,
                                                             const int32_t* __restrict__ tslot, const int32_t* __restrict__ tn,
@@ -1050,7 +1059,10 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
     static_assert(V == 4 || V == 8, "4 or 8 slices per lane");
     extern __shared__ __align__(16) unsigned char fsw_smem_raw[];
     const int lane = threadIdx.x & 31;
-    unsigned char* ring = fsw_smem_raw + (size_t)(threadIdx.x >> 5) * RS::PER_WARP + lane * 16;
+    // this lane's bytes of a ring slot: ranks at lane * RB, gradient plane h at 32 RB + 512 h + lane * 16
+    // (32-bit shared-window addresses, formed once: generic pointers cost an address conversion per access)
+    const unsigned ring_r = (unsigned)__cvta_generic_to_shared(fsw_smem_raw) + (threadIdx.x >> 5) * RS::PER_WARP + lane * RS::RB;
+    const unsigned ring_g = (unsigned)__cvta_generic_to_shared(fsw_smem_raw) + (threadIdx.x >> 5) * RS::PER_WARP + 32 * RS::RB + lane * 16;
     const int64_t wglobal = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t item = wglobal / nchunks;
     const int chunk = (int)(wglobal - item * nchunks);
@@ -1060,6 +1072,7 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
     const int k0 = (chunk * 32 + lane) * V;
     const int ldp = (int)a.ldp, ldri = (int)ldr;
     const bool lane_on = k0 < ldp;
+    const unsigned on = lane_on ? 1u : 0u;
     float2 acc2[V / 2], xi2[V / 2];
 #pragma unroll
     for (int q = 0; q < V / 2; ++q) {
@@ -1071,8 +1084,8 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
     const int my_end = __ldg(tptr + j0 + min(lane + 1, nrows));
     const int T0 = __ldg(tptr + j0);
     const int T1 = __shfl_sync(FSW_FULL, my_end, nrows - 1);
-    const unsigned short* rbase = ranks + k0;
-    const float* gbase = GA + k0;
+    const unsigned short* rbase = ranks + (lane_on ? k0 : 0);
+    const float* gbase = GA + (lane_on ? k0 : 0);
 
     // blocks of 32 (segment, slot, n) triples, one per lane: `cur` serves the copies being issued, `prv` the pairs still
     // being consumed behind a block boundary, `nxt` is in flight
@@ -1081,46 +1094,36 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
     int cur_seg = __ldg(tseg + min(bs + lane, tlast)), cur_slot = __ldg(tslot + min(bs + lane, tlast)), cur_n = __ldg(tn + min(bs + lane, tlast));
     int nxt_seg = __ldg(tseg + min(bs + 32 + lane, tlast)), nxt_slot = __ldg(tslot + min(bs + 32 + lane, tlast)), nxt_n = __ldg(tn + min(bs + 32 + lane, tlast));
     int prv_slot = 0, prv_n = 0;
+    (void)prv_slot;
 
     int issued = T0;
-    int islot = 0;   // ring slot of the next copy
-    auto issue = [&]() {
-        if (issued < T1) {
-            if (issued - bs == 32) {
-                prv_slot = cur_slot;
-                prv_n = cur_n;
-                cur_seg = nxt_seg;
-                cur_slot = nxt_slot;
-                cur_n = nxt_n;
-                bs += 32;
-                nxt_seg = __ldg(tseg + min(bs + 32 + lane, tlast));
-                nxt_slot = __ldg(tslot + min(bs + 32 + lane, tlast));
-                nxt_n = __ldg(tn + min(bs + 32 + lane, tlast));
-            }
-            const int src = issued - bs;
-            const int seg = __shfl_sync(FSW_FULL, cur_seg, src);
-            const int slot = __shfl_sync(FSW_FULL, cur_slot, src);
-            unsigned char* sb = ring + islot * RS::SLOT;
-            if (lane_on) {
-                if constexpr (V == 8) fsw_ldgsts<16>(sb, rbase + fsw_rowoff(slot, ldri));
-                else fsw_ldgsts<8>(sb - lane * 8, rbase + fsw_rowoff(slot, ldri));   // 8-byte pieces: lane * 8
-                const float* gp = gbase + fsw_rowoff(seg, ldp);
-#pragma unroll
-                for (int h = 0; h < P; ++h) fsw_ldgsts<16>(sb + 32 * RS::RB + h * 512, gp + 4 * h);
-            }
-            ++issued;
-            islot = (islot + 1 == D) ? 0 : islot + 1;
+    unsigned ioff = 0, coff = 0;   // byte offsets of the ring slots of the next copy / the next pair to consume
+    auto issue = [&]() {           // needs issued < T1
+        if (issued - bs == 32) {
+            if (HAS_EP) prv_slot = cur_slot;
+            prv_n = cur_n;
+            cur_seg = nxt_seg;
+            cur_slot = nxt_slot;
+            cur_n = nxt_n;
+            bs += 32;
+            nxt_seg = __ldg(tseg + min(bs + 32 + lane, tlast));
+            nxt_slot = __ldg(tslot + min(bs + 32 + lane, tlast));
+            nxt_n = __ldg(tn + min(bs + 32 + lane, tlast));
         }
-        fsw_ldgsts_commit();
+        const int src = issued - bs;
+        const int seg = __shfl_sync(FSW_FULL, cur_seg, src);
+        const int slot = __shfl_sync(FSW_FULL, cur_slot, src);
+        fsw_ldgsts_if<RS::RB>(on, ring_r + ioff, rbase + fsw_rowoff(slot, ldri));
+        const float* gp = gbase + fsw_rowoff(seg, ldp);
+#pragma unroll
+        for (int h = 0; h < P; ++h) fsw_ldgsts_if<16>(on, ring_g + ioff + h * 512, gp + 4 * h);
+        ++issued;
+        ioff = (ioff + RS::SLOT == D * RS::SLOT) ? 0u : ioff + RS::SLOT;
     };
     auto f2c = [](float c) { return make_float2(c, c); };
 
-#pragma unroll 1
-    for (int i = 0; i < D - 1; ++i) issue();
-
     int jr = 0;
     int row_end = __shfl_sync(FSW_FULL, my_end, 0);
-    int cslot = 0;
     auto flush_row = [&]() {
         if (lane_on) {
             float* op = dXp + fsw_rowoff(j0 + jr, ldp) + k0;
@@ -1133,34 +1136,33 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
         ++jr;
         row_end = __shfl_sync(FSW_FULL, my_end, min(jr, 31));
     };
-#pragma unroll 1
-    for (int tc = T0; tc < T1; ++tc) {
-        issue();                    // pair tc + D - 1 (or an empty group): D groups are outstanding
-        fsw_ldgsts_wait<D - 1>();   // all but the newest D - 1: the copies of pair tc have landed
+    // one pair: its copies have landed.  The arithmetic is that of fsw_rank_bwdT_kernel (see there): cos(pi (2r+1) xi / n) on
+    // pairs of slices in packed fp32.  A pair of a segment that is not served here (tn = 0: general weights, more than nmax
+    // elements) carries a zero gradient row (fsw_scale_grad_kernel), so it runs through with n = 1 and adds exactly 0.
+    auto consume = [&](int tc) {
         while (tc >= row_end) flush_row();   // warp-uniform; also steps over rows without pairs
-        const int src = tc - bs;    // >= -32: the consumer trails the copies by less than D <= 32 pairs
+        const int src = tc - bs;             // >= -32: the consumer trails the copies by less than D <= 32 pairs
         const int n_c = __shfl_sync(FSW_FULL, cur_n, src & 31), n_p = __shfl_sync(FSW_FULL, prv_n, src & 31);
-        const int n = src >= 0 ? n_c : n_p;
-        const unsigned char* sb = ring + cslot * RS::SLOT;
-        cslot = (cslot + 1 == D) ? 0 : cslot + 1;
-        if (n <= 0) continue;       // pair of a segment that is not served here (general weights, more than nmax elements)
+        const int n_raw = src >= 0 ? n_c : n_p;
+        const int n = max(n_raw, 1);
         unsigned w[V / 2];
         float ga[V];
         if constexpr (V == 8) {
-            const uint4 t = *reinterpret_cast<const uint4*>(sb);
+            const uint4 t = fsw_lds128(ring_r + coff);
             w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
         } else {
-            const uint2 t = *reinterpret_cast<const uint2*>(sb - lane * 8);
+            const uint2 t = fsw_lds64(ring_r + coff);
             w[0] = t.x; w[1] = t.y;
         }
 #pragma unroll
         for (int h = 0; h < P; ++h) {
-            const float4 t = *reinterpret_cast<const float4*>(sb + 32 * RS::RB + h * 512);
-            ga[4 * h] = t.x; ga[4 * h + 1] = t.y; ga[4 * h + 2] = t.z; ga[4 * h + 3] = t.w;
+            const uint4 t = fsw_lds128(ring_g + coff + h * 512);
+            ga[4 * h] = __uint_as_float(t.x); ga[4 * h + 1] = __uint_as_float(t.y); ga[4 * h + 2] = __uint_as_float(t.z); ga[4 * h + 3] = __uint_as_float(t.w);
         }
-        // the arithmetic of fsw_rank_bwdT_kernel (see there): cos(pi (2r+1) xi / n) on pairs of slices, packed fp32
+        coff = (coff + RS::SLOT == D * RS::SLOT) ? 0u : coff + RS::SLOT;
         const float nf = (float)n;                         // exact: n <= 32768
-        const float ih = __frcp_rn(nf);
+        float ih;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ih) : "f"(nf));   // any ih within a few ulp of 1/n: il carries the rest
         const float il = fmaf(-nf, ih, 1.0f) * ih;         // 1/n = ih + il
         const float2 ih2 = f2c(ih), nih2 = f2c(-ih), nil2 = f2c(-il);
         float v[V];
@@ -1170,10 +1172,10 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
             const float2 uh = __fmul2_rn(xi2[pr], ih2);
             const float2 nue = __ffma2_rn(xi2[pr], nih2, uh);          // -(xi ih - uh), exact
             const float2 nul = __ffma2_rn(xi2[pr], nil2, nue);         // -ul
-            const float2 mb = make_float2(__uint_as_float(0x4B000001u | ((w[pr] << 1) & 0x1fffeu)),
-                                          __uint_as_float(0x4B000001u | ((w[pr] >> 15) & 0x1fffeu)));
-            const float2 m = __fadd2_rn(mb, f2c(-8388608.0f));         // 2r+1, exact below 2^23
-            const float2 nm = __ffma2_rn(mb, f2c(-1.0f), f2c(8388608.0f));
+            // the two uint16 ranks of w as floats 2^23 + r (one byte permute each), then 2r+1 and -(2r+1) by one FMA each (exact)
+            const float2 mb = make_float2(__uint_as_float(__byte_perm(w[pr], 0x4B00u, 0x5410)), __uint_as_float(__byte_perm(w[pr], 0x4B00u, 0x5432)));
+            const float2 m = __ffma2_rn(mb, f2c(2.0f), f2c(-16777215.0f));
+            const float2 nm = __ffma2_rn(mb, f2c(-2.0f), f2c(16777215.0f));
             const float2 ph = __fmul2_rn(m, uh);
             const float2 nqe = __ffma2_rn(nm, uh, ph);                 // ph - m uh, exact
             const float2 npl = __ffma2_rn(m, nul, nqe);                // -(m ul + m uh - ph)
@@ -1190,7 +1192,7 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
             c = __ffma2_rn(y2, c, f2c(1.0f));
             const float2 gs = make_float2(__uint_as_float(__float_as_uint(ga[2 * pr]) ^ (__float_as_uint(t.x) << 31)),
                                           __uint_as_float(__float_as_uint(ga[2 * pr + 1]) ^ (__float_as_uint(t.y) << 31)));
-            if (dEp) {
+            if constexpr (HAS_EP) {
                 const float2 vv = __fmul2_rn(gs, c);
                 v[2 * pr] = vv.x;
                 v[2 * pr + 1] = vv.y;
@@ -1199,15 +1201,35 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
                 acc2[pr] = __ffma2_rn(gs, c, acc2[pr]);
             }
         }
-        if (dEp) {
+        if constexpr (HAS_EP) {
             const int s_c = __shfl_sync(FSW_FULL, cur_slot, src & 31), s_p = __shfl_sync(FSW_FULL, prv_slot, src & 31);
-            if (lane_on) {
+            if (lane_on && n_raw > 0) {
                 float* ep = dEp + fsw_rowoff(src >= 0 ? s_c : s_p, ldp) + k0;
 #pragma unroll
                 for (int h = 0; h < P; ++h) reinterpret_cast<float4*>(ep)[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
             }
         }
+    };
+
+    // prologue: D - 1 groups (the copies of the first D - 1 pairs, or empty groups behind a short list)
+#pragma unroll 1
+    for (int i = 0; i < D - 1; ++i) {
+        if (issued < T1) issue();
+        fsw_ldgsts_commit();
     }
+    // steady state: issue pair tc + D - 1, wait for all but the newest D - 1 groups (the copies of pair tc have landed)
+    int tc = T0;
+#pragma unroll 1
+    for (; tc < T1 - (D - 1); ++tc) {
+        issue();
+        fsw_ldgsts_commit();
+        fsw_ldgsts_wait<D - 1>();
+        consume(tc);
+    }
+    // tail: everything has been issued
+    fsw_ldgsts_wait<0>();
+#pragma unroll 1
+    for (; tc < T1; ++tc) consume(tc);
     while (jr < nrows) flush_row();   // the last row with pairs and the rows without any
 }
 
@@ -1403,7 +1425,7 @@ int fsw_rank_backward_T(const SegArgs<float>& a, int64_t S, int64_t Nrows, int n
         const int64_t sblocks = fsw_cdiv(swarps, 4);
 #define FSW_RANKS_LAUNCH(V_, D_, MINB_)                                                                                              \
     do {                                                                                                                             \
-        auto kern = fsw_rank_bwdS_kernel<V_, D_, MINB_>;                                                                             \
+        auto kern = dEp ? fsw_rank_bwdS_kernel<V_, D_, MINB_, true> : fsw_rank_bwdS_kernel<V_, D_, MINB_, false>;                    \
         const size_t smem = (size_t)4 * FswRankStream<V_, D_>::PER_WARP;                                                             \
         FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                \
         kern<<<(unsigned)sblocks, 128, smem, st>>>(a, Nrows, nchunks, rpw, tptr, tseg, tslot, tn, ranks, ldr, ga_buf, dXp, dEp);     \

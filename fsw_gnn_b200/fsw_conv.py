@@ -183,6 +183,9 @@ class FSW_conv(_Base):
                                         emb_mod.total_mass_pad_thresh, vertex_features.dtype, use_cache=self.cache_graph,
                                         coalesce=(edge_features is not None))
         E_feat = csr.edge_features_in_slot_order(edge_features) if edge_features is not None else None
+        if torch.is_grad_enabled() and vertex_features.dtype == torch.float32 and \
+                (vertex_features.requires_grad or any(p.requires_grad for p in emb_mod.parameters())):
+            plan.transpose_async(n)   # training: the backward's transposed structure is built under the forward kernels
         emb = emb_mod.embed_plan(vertex_features, plan, E_feat)
         return self._combine(emb, vertex_features)
 

@@ -22,6 +22,17 @@ def round_up(x, m):
 RANKT_NMAX = 32768   # FSW_RANKT_NMAX (include/fsw_embedding.h): largest segment served by the source-major backward
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for work that is not on the critical path (fsw_csr_transpose under the forward)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class SegmentPlan:
     """CSR description of a batch of weighted multisets + the launch plan of the fused kernels.
 
@@ -74,23 +85,57 @@ class SegmentPlan:
             self._scratch[key] = _ws(nbytes, self.device) if nbytes > 0 else None
         return self._scratch[key]
 
+    def _build_transpose(self, key, side):
+        lib = _lib.load()
+        dev = self.device
+        tptr = torch.empty(key + 1, dtype=torch.int32, device=dev)
+        tseg = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+        tslot = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+        tn = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
+        ws = _ws(lib.fsw_transpose_workspace_bytes(key), dev)
+
+        def launch():
+            _lib.call(dev, "fsw_csr_transpose", ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E,
+                      RANKT_NMAX if self.max_n_eff <= RANKT_NMAX else 4096,   # FSW_RANKT_ELIGIBLE
+                      ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev))
+
+        self._transpose_event = None
+        if side is None:
+            launch()
+        else:
+            # the buffers were allocated on the current stream; the side stream starts after everything queued so far
+            # (rowptr / col / info are ready there) and every buffer is told about its second stream
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                launch()
+                ev = torch.cuda.Event()
+                ev.record(side)
+            for t in (tptr, tseg, tslot, tn, ws):
+                t.record_stream(side)
+            self._transpose_event = ev
+        self._transpose = (key, tptr, tseg, tslot, tn)
+
+    def transpose_async(self, nrows):
+        """Start fsw_csr_transpose on a side stream: the transposition is first read by the BACKWARD of the last layer, a whole
+        forward pass after the graph arrives, so its ~9 ms (configs[3]) need not sit between the graph and the first sort.
+        `transpose()` makes the consuming stream wait for it."""
+        if self.col is None or self.rowptr is None or self.dtype != torch.float32:
+            return
+        key = int(nrows)
+        if getattr(self, "_transpose", None) is None or self._transpose[0] != key:
+            self._build_transpose(key, _side_stream(self.device))
+
     def transpose(self, nrows):
         """(tptr, tseg, tslot, tn) of fsw_csr_transpose, built lazily and cached (graphs with explicit columns)."""
         if self.col is None or self.rowptr is None:
             return None
         key = int(nrows)
         if getattr(self, "_transpose", None) is None or self._transpose[0] != key:
-            lib = _lib.load()
-            dev = self.device
-            tptr = torch.empty(key + 1, dtype=torch.int32, device=dev)
-            tseg = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
-            tslot = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
-            tn = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
-            ws = _ws(lib.fsw_transpose_workspace_bytes(key), dev)
-            _lib.call(dev, "fsw_csr_transpose", ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E,
-                      RANKT_NMAX if self.max_n_eff <= RANKT_NMAX else 4096,   # FSW_RANKT_ELIGIBLE
-                      ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev))
-            self._transpose = (key, tptr, tseg, tslot, tn)
+            self._build_transpose(key, None)
+        ev = getattr(self, "_transpose_event", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._transpose_event = None
         return self._transpose[1:]
 
     def any_deficient(self):

@@ -8,11 +8,11 @@
 set -e
 mkdir -p gpurun_out
 python profiles/prof_conv.py 1.0 3 > gpurun_out/r2_full_plain.log 2>&1 &&
-ncu --set full --clock-control none -k regex:'fsw_(rank_bwdT|coop_fwd|small_fwd|medium|umma|scale_grad)' \
+ncu --set full --clock-control none -k regex:'fsw_(rank_bwdS|rank_bwdT|coop_fwd|small_fwd|medium|umma|scale_grad)' \
     -s 30 -c 40 -o /tmp/r2_full -f python profiles/prof_conv.py 1.0 3 > gpurun_out/r2_full_ncu.log 2>&1
 ncu -i /tmp/r2_full.ncu-rep --page raw --csv > gpurun_out/r2_full_raw.csv
 python profiles/ncu_summary.py gpurun_out/r2_full_raw.csv > gpurun_out/r2_full_summary.txt
-ncu -i /tmp/r2_full.ncu-rep --page source --csv -k regex:fsw_rank_bwdT > gpurun_out/r2_src_rank_bwdT.csv 2>/dev/null || true
+ncu -i /tmp/r2_full.ncu-rep --page source --csv -k regex:fsw_rank_bwd > gpurun_out/r2_src_rank_bwdS.csv 2>/dev/null || true
 ncu -i /tmp/r2_full.ncu-rep --page source --csv -k regex:fsw_umma --launch-count 1 > gpurun_out/r2_src_umma.csv 2>/dev/null || true
 ls -la /tmp/r2_full.ncu-rep gpurun_out | tail -12
 tail -3 gpurun_out/r2_full_ncu.log

@@ -1,6 +1,6 @@
 """Per-kernel DRAM traffic of the full-size capture (profiles/r2/ncu_fullscale.sh) -> profiles/r2/ncu_traffic.json, the file
 bench.py reads `roofline.traffic` from.  Kernel names are mapped to the library's profile labels:
-    fsw_rank_bwdT_kernel                      -> bwd_rankT_u32768_f32
+    fsw_rank_bwdS_kernel / fsw_rank_bwdT_kernel -> bwd_rankT_u32768_f32
     fsw_coop_fwd_kernel<R, L, col, rank>      -> fwd[r]_coop_u{R*L}_f32
     fsw_small_fwd_kernel<float, NP, col, rank>-> fwd[r]_small_u{NP}_f32
     fsw_umma_kernel<MODE>                     -> umma_nt / umma_nn / umma_tn (average over the launches captured)
@@ -25,13 +25,13 @@ def unit_scale(k):
 
 
 def label(name):
-    m = re.search(r"fsw_coop_fwd_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\w+), (?:\(bool\))?(\w+)>", name)
+    m = re.search(r"fsw_coop_fwd_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\w+), (?:\(bool\))?(\w+)(?:, (?:\(bool\))?\w+)?>", name)
     if m:
         return ("fwdr" if m.group(4) in ("1", "true") else "fwd") + "_coop_u%d_f32" % (int(m.group(1)) * int(m.group(2)))
     m = re.search(r"fsw_small_fwd_kernel<float, (?:\(int\))?(\d+), (?:\(bool\))?(\w+), (?:\(bool\))?(\w+)>", name)
     if m:
         return ("fwdr" if m.group(3) in ("1", "true") else "fwd") + "_small_u%d_f32" % int(m.group(1))
-    if "fsw_rank_bwdT_kernel" in name:
+    if "fsw_rank_bwdT_kernel" in name or "fsw_rank_bwdS_kernel" in name:
         return "bwd_rankT_u32768_f32"
     m = re.search(r"fsw_umma_kernel<(?:\(int\))?(\d)>", name)
     if m:

@@ -526,9 +526,9 @@ def test_no_grad_allocates_no_rank_buffer():
     seen = []
     orig = ops.embed_forward
 
-    def spy(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks=None, dxi_out=None):
+    def spy(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks=None, dxi_out=None, **kw):
         seen.append((ranks is not None, dxi_out is not None))
-        return orig(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks, dxi_out)
+        return orig(plan, Xp, ldp, Ep, freqs, out, ld_out, out_col0, bias, ranks, dxi_out, **kw)
     ops.embed_forward = spy
     try:
         with torch.no_grad():
