@@ -1098,25 +1098,31 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
 
     int issued = T0;
     unsigned ioff = 0, coff = 0;   // byte offsets of the ring slots of the next copy / the next pair to consume
-    auto issue = [&]() {           // needs issued < T1
-        if (issued - bs == 32) {
-            if (HAS_EP) prv_slot = cur_slot;
-            prv_n = cur_n;
-            cur_seg = nxt_seg;
-            cur_slot = nxt_slot;
-            cur_n = nxt_n;
-            bs += 32;
-            nxt_seg = __ldg(tseg + min(bs + 32 + lane, tlast));
-            nxt_slot = __ldg(tslot + min(bs + 32 + lane, tlast));
-            nxt_n = __ldg(tn + min(bs + 32 + lane, tlast));
-        }
+    const char* rbase_b = reinterpret_cast<const char*>(rbase);
+    const char* gbase_b = reinterpret_cast<const char*>(gbase);
+    const int ldr_b = ldri * 2, ldp_b = ldp * 4;   // row pitches in bytes (< 2^31 / rows by the int32 CSR contract)
+    auto rotate = [&]() {          // the copies move on to the next block of 32 triples
+        if (HAS_EP) prv_slot = cur_slot;
+        prv_n = cur_n;
+        cur_seg = nxt_seg;
+        cur_slot = nxt_slot;
+        cur_n = nxt_n;
+        bs += 32;
+        nxt_seg = __ldg(tseg + min(bs + 32 + lane, tlast));
+        nxt_slot = __ldg(tslot + min(bs + 32 + lane, tlast));
+        nxt_n = __ldg(tn + min(bs + 32 + lane, tlast));
+    };
+    auto issue = [&]() {           // needs issued < T1 and issued < bs + 32
         const int src = issued - bs;
         const int seg = __shfl_sync(FSW_FULL, cur_seg, src);
         const int slot = __shfl_sync(FSW_FULL, cur_slot, src);
-        fsw_ldgsts_if<RS::RB>(on, ring_r + ioff, rbase + fsw_rowoff(slot, ldri));
-        const float* gp = gbase + fsw_rowoff(seg, ldp);
+        const char* rp;            // base + row * pitch as one IMAD.WIDE each
+        const char* gp;
+        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(rp) : "r"(slot), "r"(ldr_b), "l"(rbase_b));
+        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(gp) : "r"(seg), "r"(ldp_b), "l"(gbase_b));
+        fsw_ldgsts_if<RS::RB>(on, ring_r + ioff, rp);
 #pragma unroll
-        for (int h = 0; h < P; ++h) fsw_ldgsts_if<16>(on, ring_g + ioff + h * 512, gp + 4 * h);
+        for (int h = 0; h < P; ++h) fsw_ldgsts_if<16>(on, ring_g + ioff + h * 512, gp + 16 * h);
         ++issued;
         ioff = (ioff + RS::SLOT == D * RS::SLOT) ? 0u : ioff + RS::SLOT;
     };
@@ -1214,17 +1220,27 @@ __global__ void __launch_bounds__(128, MINB) fsw_rank_bwdS_kernel(SegArgs<float>
     // prologue: D - 1 groups (the copies of the first D - 1 pairs, or empty groups behind a short list)
 #pragma unroll 1
     for (int i = 0; i < D - 1; ++i) {
-        if (issued < T1) issue();
+        if (issued < T1) {
+            if (issued - bs == 32) rotate();
+            issue();
+        }
         fsw_ldgsts_commit();
     }
-    // steady state: issue pair tc + D - 1, wait for all but the newest D - 1 groups (the copies of pair tc have landed)
+    // steady state: issue pair tc + D - 1, wait for all but the newest D - 1 groups (the copies of pair tc have landed);
+    // runs of pairs up to the next triple-block boundary, so that the per-pair path carries no block bookkeeping
     int tc = T0;
+    const int Tsteady = T1 - (D - 1);
 #pragma unroll 1
-    for (; tc < T1 - (D - 1); ++tc) {
-        issue();
-        fsw_ldgsts_commit();
-        fsw_ldgsts_wait<D - 1>();
-        consume(tc);
+    while (tc < Tsteady) {
+        if (issued - bs == 32) rotate();
+        const int run_end = min(Tsteady, tc + (bs + 32 - issued));
+#pragma unroll 1
+        for (; tc < run_end; ++tc) {
+            issue();
+            fsw_ldgsts_commit();
+            fsw_ldgsts_wait<D - 1>();
+            consume(tc);
+        }
     }
     // tail: everything has been issued
     fsw_ldgsts_wait<0>();
