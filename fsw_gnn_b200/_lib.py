@@ -61,6 +61,7 @@ _SIGNATURES = {
                                         c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp, c_vp, c_i64, c_vp]),
     "fsw_embed_backward_cloud": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp,
                                          c_vp, c_i64, c_vp]),
+    "fsw_column_dot": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "fsw_embed_weight_grad_scratch_bytes": (c_sz, [c_i32, c_i64]),
     "fsw_embed_backward_weights": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_dbl, c_i32,
                                            c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),

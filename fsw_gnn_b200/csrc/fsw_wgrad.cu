@@ -261,3 +261,76 @@ extern "C" int fsw_embed_weight_grad_finish(int dtype, const int32_t* rowptr, in
     FSW_CHECK_LAUNCH("fsw_wgrad_finish_kernel");
     return FSW_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// dL/dxi of the segments whose d out / d xi the forward produced: acc[k] += sum_s g[s, k] dxi_out[s, k]  (float64 accumulators).
+// One pass over the two [S, K] matrices (2 x 1.9 GB at configs[3]) instead of an elementwise product written back to memory and
+// a column reduction over it.  A warp takes 64 rows (lanes = columns), fp32 partial sums of 64 terms, then the 8 warps of a block
+// meet in shared memory and one float64 atomic per column and block lands in `acc`.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) fsw_column_dot_kernel(const T* __restrict__ g, int64_t ld_g, const T* __restrict__ d, int64_t ld_d,
+                                                             int64_t S, int K, double* __restrict__ acc) {
+    constexpr int ROWS = 64;
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * ROWS;
+    const int64_t r1 = (r0 + ROWS < S) ? r0 + ROWS : S;
+    for (int kb = 0; kb < K; kb += 32) {   // block-uniform
+        const int k = kb + lane;
+        T part = (T)0;
+        if (k < K) {
+            const T* gp = g + r0 * ld_g + k;
+            const T* dp = d + r0 * ld_d + k;
+            const int nr = (int)(r1 - r0);
+            T p1 = (T)0, p2 = (T)0, p3 = (T)0;   // four chains, eight rows in flight per lane
+            int r = 0;
+            for (; r + 8 <= nr; r += 8) {
+                T a[8], b[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    a[u] = __ldg(gp + (int64_t)(r + u) * ld_g);
+                    b[u] = __ldg(dp + (int64_t)(r + u) * ld_d);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u += 4) {
+                    part = fma(a[u], b[u], part);
+                    p1 = fma(a[u + 1], b[u + 1], p1);
+                    p2 = fma(a[u + 2], b[u + 2], p2);
+                    p3 = fma(a[u + 3], b[u + 3], p3);
+                }
+            }
+            for (; r < nr; ++r) part = fma(__ldg(gp + (int64_t)r * ld_g), __ldg(dp + (int64_t)r * ld_d), part);
+            part += p1 + p2 + p3;
+        }
+        red[warp][lane] = (double)part;
+        __syncthreads();
+        if (warp == 0 && k < K) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][lane];
+            atomicAdd(acc + k, t);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+extern "C" int fsw_column_dot(int dtype, const void* g, int64_t ld_g, const void* d, int64_t ld_d, int64_t S, int64_t K, double* acc,
+                              void* stream) {
+    if (S == 0 || K == 0) return FSW_OK;
+    if (!g || !d || !acc) return fsw_fail(FSW_ERR_INVALID, "fsw_column_dot: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)fsw_cdiv(S, 8 * 64);
+    fsw_prof_begin("bwd_dxi_dot", st);
+    if (dtype == FSW_F32)
+        fsw_column_dot_kernel<float><<<blocks, 256, 0, st>>>((const float*)g, ld_g, (const float*)d, ld_d, S, (int)K, acc);
+    else if (dtype == FSW_F64)
+        fsw_column_dot_kernel<double><<<blocks, 256, 0, st>>>((const double*)g, ld_g, (const double*)d, ld_d, S, (int)K, acc);
+    else
+        return fsw_fail(FSW_ERR_INVALID, "fsw_column_dot: dtype %d", dtype);
+    fsw_prof_end(st);
+    FSW_CHECK_LAUNCH("fsw_column_dot_kernel");
+    return FSW_OK;
+}

@@ -11,6 +11,8 @@ exchange at all (shard the batch dimension; see bench.py).
 One process per GPU; torch.distributed provides the communicator (backend nccl on GPUs, gloo in the
 CPU tests of the host-side logic).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -140,7 +142,8 @@ class ShardedGraph:
         self.num_edges = int(ei.shape[1])
         self.csr = _graph.GraphCSR(ei, self.n_local, 0, "unit", dtype, num_sources=len(self.row_ranges) * self.max_rows)
         self.plan = self.csr.plan(thresh, dtype)
-        self.plan.exchange = RowExchange(self.max_rows, group)   # project locally, all-gather the projected rows
+        # project locally, all-gather the projected rows; FSW_EXCHANGE_CHUNKS: column chunks whose exchange overlaps the kernels
+        self.plan.exchange = RowExchange(self.max_rows, group, chunks=int(os.environ.get("FSW_EXCHANGE_CHUNKS", "1")))
 
 
 def sharded_conv_forward(conv, x_local, sg):

@@ -470,7 +470,10 @@ class FSWEmbedFunction(torch.autograd.Function):
             # with learnable frequencies the forward also emits d out / d xi per (segment, slice)
             dxi_out = None
             if ranks is not None and ctx.needs_input_grad[2]:
-                dxi_out = torch.zeros((plan.S, k1 - k0), dtype=X.dtype, device=X.device)
+                # the rank-recording forward writes every (segment, slice) of the uniform segments of up to 32768 elements;
+                # only a plan with other segments needs the zero fill (1.9 GB per layer at configs[3])
+                covered = X.dtype == torch.float32 and plan.uniform_fraction() == 1.0 and plan.max_n_eff <= RANKT_NMAX
+                dxi_out = (torch.empty if covered else torch.zeros)((plan.S, k1 - k0), dtype=X.dtype, device=X.device)
             embed_forward(plan, xp, ldc, Ep, freqs[k0:k1], out, d_out, tm_dim + k0,
                           None if bias_core is None else bias_core[k0:k1], ranks, dxi_out)
             ch[5], ch[6] = ranks, dxi_out
@@ -531,10 +534,11 @@ class FSWEmbedFunction(torch.autograd.Function):
                 embed_backward(plan, Xp, ldc, ctx.Ep, freqs[k0:k1], g, g.stride(0), tm_dim + k0, dXp, dEp, dxi_acc, ranks,
                                dxi_from_forward=(dxi_fwd or not need_xi), transpose=transpose, nrows=Nrows)
                 if need_xi:
-                    dxi_c = dxi_acc.to(X.dtype)
-                    if dxi_fwd:
-                        dxi_c = dxi_c + (g[:, tm_dim + k0:tm_dim + k1] * dxi_out).sum(dim=0)
-                    dxi[k0:k1] = dxi_c
+                    if dxi_fwd:   # + sum_s g[s, k] d out[s, k] / d xi_k of the segments the forward covered: one fused pass
+                        gk = g[:, tm_dim + k0:tm_dim + k1]
+                        _lib.call(X.device, "fsw_column_dot", dtype_code(X.dtype), ptr(gk), gk.stride(0), ptr(dxi_out), dxi_out.stride(0),
+                                  plan.S, k1 - k0, ptr(dxi_acc), stream_ptr(X.device))
+                    dxi[k0:k1] = dxi_acc.to(X.dtype)
                 work = None
                 if exch is not None:
                     # sum over ranks, keep this rank's rows: runs under the next chunk's kernels

@@ -245,6 +245,11 @@ int fsw_embed_backward_cloud(int dtype, const void* X, int64_t d, const void* th
  *  max_n: the largest number of elements of a segment.  scratch: fsw_embed_weight_grad_scratch_bytes(dtype, max_n)
  *     (0 when every tile fits shared memory).  Xp / Ep / rowptr / n_fixed / col / W / mass / freqs / g as in section 6.
  * ---------------------------------------------------------------------------------------------- */
+/* acc[k] += sum_s g[s, k] * d[s, k] for k < K, float64 accumulators: the frequency gradient of the segments whose d out / d xi
+ * the forward wrote (dxi_out of fsw_embed_forward; replaces the reference's autograd through the frequency multiply,
+ * fsw_embedding.py:1037-1045), in one pass over the two [S, K] matrices. */
+int fsw_column_dot(int dtype, const void* g, int64_t ld_g, const void* d, int64_t ld_d, int64_t S, int64_t K, double* acc,
+                   void* stream);
 size_t fsw_embed_weight_grad_scratch_bytes(int dtype, int64_t max_n);
 int fsw_embed_backward_weights(int dtype, const void* Xp, int64_t ldp, const void* Ep, const int32_t* rowptr, int64_t n_fixed,
                                const int32_t* col, const void* W, const double* mass, int64_t S, int64_t K, const void* freqs,
