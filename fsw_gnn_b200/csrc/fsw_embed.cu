@@ -912,7 +912,7 @@ int embed_backward_t(const SegArgs<T>& a, const int32_t* bo, const T* g, int64_t
             if (hi <= lo) continue;
             if constexpr (sizeof(T) == 4) {
                 if (kind == 0 && cap >= 128 && cap <= 512 && have_ranks) continue;  // done by the rank kernels
-                if (kind == 0 && source_major && (cap <= 4096 || tnmax == FSW_RANKT_NMAX)) continue;  // source-major rank backward
+                if (kind == 0 && source_major && cap <= tnmax) continue;  // source-major rank backward (hubs beyond: re-sorted below)
                 if (kind == 0 && cap >= 128) {
                     // re-sorting backward; the forward produced d/dxi for these when it recorded ranks (cap <= 32768)
                     double* df = (have_ranks && cap <= 32768) ? dfreqs_cov : dfreqs;

@@ -96,7 +96,7 @@ class SegmentPlan:
 
         def launch():
             _lib.call(dev, "fsw_csr_transpose", ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E,
-                      RANKT_NMAX if self.max_n_eff <= RANKT_NMAX else 4096,   # FSW_RANKT_ELIGIBLE
+                      RANKT_NMAX,   # FSW_RANKT_ELIGIBLE
                       ptr(tptr), ptr(tseg), ptr(tslot), ptr(tn), ptr(ws), ws.numel(), stream_ptr(dev))
 
         self._transpose_event = None

@@ -117,10 +117,10 @@ int fsw_edge_weights(int dtype, const int32_t* rowptr, const int32_t* col, const
  * that segment when it is eligible for the source-major backward (uniform weights, n <= nmax_eligible), else 0.
  * `info` comes from fsw_segment_plan.  workspace: fsw_transpose_workspace_bytes(Nrows).
  * A transposition handed to fsw_embed_backward must be built with nmax_eligible = FSW_RANKT_ELIGIBLE(max n_eff of
- * the plan): the backward serves exactly those segments through it (all uniform segments when none exceeds
- * FSW_RANKT_NMAX; otherwise those of up to 4096 elements, so that the open-ended last size bucket stays whole). */
+ * the plan): the backward serves exactly those segments through it - every uniform segment of up to FSW_RANKT_NMAX
+ * elements (the plan has a closed size bucket that ends there); hubs beyond are re-sorted and added with atomics. */
 #define FSW_RANKT_NMAX 32768
-#define FSW_RANKT_ELIGIBLE(max_n_eff) ((max_n_eff) <= FSW_RANKT_NMAX ? FSW_RANKT_NMAX : 4096)
+#define FSW_RANKT_ELIGIBLE(max_n_eff) (FSW_RANKT_NMAX)
 size_t fsw_transpose_workspace_bytes(int64_t Nrows);
 int fsw_csr_transpose(const int32_t* rowptr, const int32_t* col, const int32_t* info, int64_t S, int64_t Nrows, int64_t E,
                       int nmax_eligible, int32_t* tptr, int32_t* tseg, int32_t* tslot, int32_t* tn, void* workspace,

@@ -394,7 +394,7 @@ def test_config2_graph_gradients_k127():
 @pytest.mark.parametrize("K", [199, 257])
 @pytest.mark.parametrize("learn_freqs", [True, False])
 def test_mixed_hub_gradients(K, learn_freqs):
-    """A hub above 32768 elements drops the source-major limit to 4096: plain stores and atomics then hit the same dXp rows,
+    """A hub above 32768 elements is re-sorted and added with atomics after the source-major kernel has written every row with plain stores (segments of up to 32768 elements): plain stores and atomics then hit the same dXp rows,
     the re-sorting backward serves the hub.  K = 199 (one 256-slice chunk) and K = 257 (two chunks); frequencies learnable
     (d/dxi from the forward) and frozen."""
     from fsw_gnn_b200 import FSW_embedding
