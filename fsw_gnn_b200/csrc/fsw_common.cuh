@@ -203,7 +203,9 @@ size_t fsw_rank_tables_bytes(int64_t ldp);
 // forward scratch (fsw_embed_packed.cu)
 #define FSW_FWD_TAB_NMAX 512
 // extent of the tables for a plan: the largest uniform segment size in 33..FSW_FWD_TAB_NMAX that occurs (0: none)
+#define FSW_FWD_TAB_GRAPH_NMAX 1024   // graphs: the 513..1024 bucket (not resolved by size) takes tables up to 1024
 static inline int fsw_fwd_tables_nmax(const int32_t* bo) {
+    if (bo[FSW_PLAN_EXACT] < bo[FSW_PLAN_EXACT + 1]) return FSW_FWD_TAB_GRAPH_NMAX;
     for (int n = FSW_FWD_TAB_NMAX; n > 32; --n)
         if (bo[n] < bo[n + 1]) return n;
     return 0;

@@ -758,7 +758,7 @@ int embed_forward_t(const SegArgs<T>& a, const int32_t* bo, T* out, int64_t ld_o
                 // 65..512 elements (and dense batches of up to 1024): packed keys, cooperating lanes.  The graph tables
                 // (tab_n0 == 0) reach the largest size <= 512 that occurs; a dense single-size table serves its own class.
                 if (kind == 0 && gtab_c != nullptr && cap <= 1024 &&
-                    (tab_n0 == 0 ? cap <= FSW_FWD_TAB_NMAX : (a.n_fixed > cap / 2 && a.n_fixed <= cap))) {
+                    (tab_n0 == 0 ? cap <= (tab_nmax > FSW_FWD_TAB_NMAX ? FSW_FWD_TAB_GRAPH_NMAX : FSW_FWD_TAB_NMAX) : (a.n_fixed > cap / 2 && a.n_fixed <= cap))) {
                     int rc = FSW_OK;
                     if (tab_n0 == 0 && cap <= FSW_FWD_TAB_NMAX) {
                         // two classes per power of two: 3/4 cap slots for the lower part of the range (less padding)

@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(256) fsw_build_fwd_tables_kernel(const float* 
                                                                    float* __restrict__ tab_c, float* __restrict__ tab_t) {
     const int n = n0 + blockIdx.x;
     const int jb = blockIdx.y;
-    if (n < 1) return;
+    if (n < 1 || jb * 4 >= n) return;   // position blocks beyond n are never read (the consumers test p < n per block of 4)
     for (int idx = threadIdx.x; idx < K * 4; idx += blockDim.x) {
         const int k = idx >> 2, j = jb * 4 + (idx & 3);
         float c = 0.f, t = 0.f;
@@ -695,12 +695,7 @@ int launch_coop(const SegArgs<float>& a, int lo, int hi, float* out, int64_t ld_
         else return ranks ? launch_coop_fwd<R, L, false, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
                      : launch_coop_fwd<R, L, false, false, true>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st);
     }
-    if constexpr (R * L > 512) {
-        // more than 512 slots: dense batches only (a column-id register per 32 slots would not fit)
-        if (has_col) return fsw_fail(FSW_ERR_INVALID, "fsw_packed_forward_u: %d slots need a dense batch", R * L);
-        return ranks ? launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
-                     : launch_coop_fwd<R, L, false, false>(a, lo, hi, out, ld_out, out_col0, bias, nullptr, 0, nullptr, 0, gtab_c, gtab_t, tab_n0, tab_ld4, st);
-    } else {
+    {
         if (ranks) {
             return has_col ? launch_coop_fwd<R, L, true, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st)
                            : launch_coop_fwd<R, L, false, true>(a, lo, hi, out, ld_out, out_col0, bias, ranks, ldr, dxi_out, ld_dxi, gtab_c, gtab_t, tab_n0, tab_ld4, st);

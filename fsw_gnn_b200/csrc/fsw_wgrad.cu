@@ -272,47 +272,38 @@ namespace {
 template <typename T>
 __global__ void __launch_bounds__(256) fsw_column_dot_kernel(const T* __restrict__ g, int64_t ld_g, const T* __restrict__ d, int64_t ld_d,
                                                              int64_t S, int K, double* __restrict__ acc) {
-    constexpr int ROWS = 64;
+    constexpr int ROWS = 64;   // rows per warp
+    constexpr int CB = 8;      // column chunks of 32 held per lane: a warp reads whole rows of up to 256 columns, contiguously
     __shared__ double red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * ROWS;
-    const int64_t r1 = (r0 + ROWS < S) ? r0 + ROWS : S;
-    for (int kb = 0; kb < K; kb += 32) {   // block-uniform
-        const int k = kb + lane;
-        T part = (T)0;
-        if (k < K) {
-            const T* gp = g + r0 * ld_g + k;
-            const T* dp = d + r0 * ld_d + k;
-            const int nr = (int)(r1 - r0);
-            T p1 = (T)0, p2 = (T)0, p3 = (T)0;   // four chains, eight rows in flight per lane
-            int r = 0;
-            for (; r + 8 <= nr; r += 8) {
-                T a[8], b[8];
+    const int nr = (int)((r0 + ROWS < S ? r0 + ROWS : S) - r0);   // may be <= 0 for the last warps (they still join the barriers)
+    for (int kb = 0; kb < K; kb += 32 * CB) {   // block-uniform
+        T part[CB];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    a[u] = __ldg(gp + (int64_t)(r + u) * ld_g);
-                    b[u] = __ldg(dp + (int64_t)(r + u) * ld_d);
-                }
+        for (int i = 0; i < CB; ++i) part[i] = (T)0;
+        const T* gp = g + r0 * ld_g + kb + lane;
+        const T* dp = d + r0 * ld_d + kb + lane;
+#pragma unroll 2
+        for (int r = 0; r < nr; ++r) {
 #pragma unroll
-                for (int u = 0; u < 8; u += 4) {
-                    part = fma(a[u], b[u], part);
-                    p1 = fma(a[u + 1], b[u + 1], p1);
-                    p2 = fma(a[u + 2], b[u + 2], p2);
-                    p3 = fma(a[u + 3], b[u + 3], p3);
-                }
+            for (int i = 0; i < CB; ++i)
+                if (kb + 32 * i + lane < K) part[i] = fma(__ldg(gp + (int64_t)r * ld_g + 32 * i), __ldg(dp + (int64_t)r * ld_d + 32 * i), part[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < CB; ++i) {
+            if (kb + 32 * i >= K) break;   // block-uniform
+            red[warp][lane] = (double)part[i];
+            __syncthreads();
+            const int k = kb + 32 * i + lane;
+            if (warp == 0 && k < K) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += red[w][lane];
+                atomicAdd(acc + k, t);
             }
-            for (; r < nr; ++r) part = fma(__ldg(gp + (int64_t)r * ld_g), __ldg(dp + (int64_t)r * ld_d), part);
-            part += p1 + p2 + p3;
+            __syncthreads();
         }
-        red[warp][lane] = (double)part;
-        __syncthreads();
-        if (warp == 0 && k < K) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) t += red[w][lane];
-            atomicAdd(acc + k, t);
-        }
-        __syncthreads();
     }
 }
 }  // namespace
