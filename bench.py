@@ -522,8 +522,37 @@ def main():
             b.record()
             torch.cuda.synchronize()
             ms_c2 = a.elapsed_time(b) / 20
-            extras["conv_c2"] = {"edges_per_s": 100000 / (ms_c2 * 1e-3), "ms_per_step": ms_c2,
+            l0 = _lib.launch_count()
+            c2_step()
+            c2_launches = _lib.launch_count() - l0
+            extras["conv_c2"] = {"edges_per_s": 100000 / (ms_c2 * 1e-3), "ms_per_step": ms_c2, "library_launches_per_step": c2_launches,
                                  "config": "configs[1]: FSW_conv(64,64) fwd+bwd, N=10k, E=100k (launch-latency bound)"}
+            # the same step captured in a CUDA graph and replayed: graph plan, transposition and scratch are cached before the
+            # capture, so the captured region holds kernel launches and allocator-pool memory only (profiles/r2/c2_graph.py)
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        c2_step()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg):
+                    c2_step()
+                for _ in range(3):
+                    cg.replay()
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(50):
+                    cg.replay()
+                b.record()
+                torch.cuda.synchronize()
+                ms_c2g = a.elapsed_time(b) / 50
+                extras["conv_c2"]["cuda_graph_ms_per_step"] = ms_c2g
+                extras["conv_c2"]["cuda_graph_edges_per_s"] = 100000 / (ms_c2g * 1e-3)
+                del cg
+            except Exception as ex:   # the eager number above stands
+                extras["conv_c2"]["cuda_graph_error"] = str(ex)[:200]
         if rank == 0 and world == 1:
             # C5: configs[4] - power-law graph, 1M vertices, one 100 000-edge hub, d_in = 256 -> d_out = 512 (K = 511 slices):
             # the skewed segment sort and the tensor-core projection.  One FSW_embedding layer fwd+bwd through embed_plan.
