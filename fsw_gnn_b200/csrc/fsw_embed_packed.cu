@@ -175,27 +175,30 @@ __device__ __forceinline__ void fsw_bitonic_merge(CE&& ce) {
     }
 }
 
-// Per-run-length policy, from the measurements in profiles/r2/README.md (the kernels are bound by the shared-memory data
-// pipe - shuffles cost two wavefronts each - and by the integer ALU; DRAM is < 25 % busy):
-//   R = 12: synchronous gather (all loads issued before the first use), the lane's coefficients staged in shared memory
-//   R = 16: asynchronous gather (LDGSTS) of the next segment into a second key buffer, coefficients through L1
-//   R >= 24: synchronous gather, coefficients through L1 (shared memory per warp limits the residency otherwise)
+// Per-class policy, from the measurements in profiles/r2/README.md (the kernels are bound by the shared-memory data pipe -
+// shuffles cost two wavefronts each - and by the integer ALU; DRAM is < 25 % busy):
+//   gather: synchronous (all loads issued before the first use) except R = 16, where the asynchronous copy (LDGSTS) of the
+//           next segment into a second key buffer is as fast and leaves registers for the sort;
+//   coefficients: staged per lane in shared memory (reloaded when n changes) for R = 12 and for R >= 24 with up to 8 lanes per
+//           slice (-5..11 %); through L1 for R = 16 (one CTA less per SM otherwise) and for 16 / 32 lanes per slice (+16 %);
+//   registers: 64 (8 CTAs) at R = 12, 72 (7 CTAs) at R = 16, 96 (5 CTAs) at R = 24, 128 (4 CTAs) at R = 32 - R = 24 at 80
+//           registers and R = 32 at 96 spill ~150 bytes and lose 5-15 %.
 #ifndef FSW_COOP_ASYNC
 #define FSW_COOP_ASYNC(R) ((R) == 16)
 #endif
 #ifndef FSW_COOP_TABS
-#define FSW_COOP_TABS(R) ((R) == 12)
+#define FSW_COOP_TABS(R, L) ((R) == 12 || ((R) >= 24 && (L) <= 8))
 #endif
 #ifndef FSW_COOP_MINB
-#define FSW_COOP_MINB(R) ((R) <= 16 ? 8 : ((R) <= 24 ? 5 : 4))   // resident CTAs per SM asked of the compiler (register cap: 64 / 96 / 128; R = 24 at 80 registers and R = 32 at 96 spill ~150 bytes and lose 5-15 %)
+#define FSW_COOP_MINB(R) ((R) <= 12 ? 8 : ((R) <= 16 ? 7 : ((R) <= 24 ? 5 : 4)))
 #endif
 
 // shared memory of one warp, in floats: key buffers [NBUF][R L][32 / L] + the lane-private coefficient rows [TABF][R / 4][32] float4
-template <int R, bool SAVE_RANK, bool CLOUD>
+template <int R, int L, bool SAVE_RANK, bool CLOUD>
 struct FswCoopSmem {
     static constexpr bool ASYNC = FSW_COOP_ASYNC(R) && !CLOUD;
     static constexpr int NBUF = ASYNC ? 2 : 1;                             // graphs: the gather of the next segment lands while this one is sorted
-    static constexpr int TABF = (FSW_COOP_TABS(R) && !CLOUD) ? (SAVE_RANK ? 2 : 1) : 0;  // tables staged in shared memory (reloaded when n changes)
+    static constexpr int TABF = (FSW_COOP_TABS(R, L) && !CLOUD) ? (SAVE_RANK ? 2 : 1) : 0;  // tables staged in shared memory (reloaded when n changes)
     static constexpr int KEYS = R * 32;
     static constexpr int PER_WARP = (NBUF + TABF) * KEYS;
 };
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(128, FSW_COOP_MINB(R)) fsw_coop_fwd_kernel(
     const float* __restrict__ gtab_c, const float* __restrict__ gtab_t, int tab_n0, int tab_ld4) {
     static_assert(R % 4 == 0 && R >= 4, "a lane reads its table positions as float4s");
     static_assert((L & (L - 1)) == 0 && L >= 4 && L <= 32, "lanes per slice: power of two; 32 / L <= 8 slices tile the padded width");
-    using SM = FswCoopSmem<R, SAVE_RANK, CLOUD>;
+    using SM = FswCoopSmem<R, L, SAVE_RANK, CLOUD>;
     constexpr int SW = 32 / L;            // slices per warp
     constexpr int NS = R * L;             // element slots per (segment, slice)
     constexpr int NC = (NS + 31) / 32;    // column-id registers per lane (element 32 m + lane)
@@ -673,7 +676,7 @@ int launch_coop_fwd(const SegArgs<float>& a, int lo, int hi, float* out, int64_t
     const int64_t warps = fsw_cdiv(hi - lo, G) * nchunks;
     constexpr int WPB = 4;
     const int64_t blocks = fsw_cdiv(warps, WPB);
-    const size_t smem = (size_t)WPB * FswCoopSmem<R, SAVE_RANK, CLOUD>::PER_WARP * sizeof(float);
+    const size_t smem = (size_t)WPB * FswCoopSmem<R, L, SAVE_RANK, CLOUD>::PER_WARP * sizeof(float);
     auto kern = fsw_coop_fwd_kernel<R, L, HAS_COL, SAVE_RANK, CLOUD>;
     if (smem > 40 * 1024) FSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const std::string label = std::string(SAVE_RANK ? "fwdr_" : "fwd_") + (CLOUD ? "cloud_u" : "coop_u") + std::to_string(R * L) + "_f32";  // R x L slots
