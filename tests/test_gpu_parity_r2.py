@@ -562,3 +562,26 @@ def test_module_on_other_device_than_current():
     out0.square().sum().backward()
     torch.testing.assert_close(out.detach().cpu(), out0.detach().cpu(), rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(x.grad.cpu(), x0.grad.cpu(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("S,K,col0", [(1, 1, 0), (513, 199, 1), (70001, 37, 0), (20000, 511, 1)])
+def test_column_dot_vs_fp64(S, K, col0, dtype):
+    """fsw_column_dot (frequency gradient of the forward-covered segments, fsw_embedding.py:1037-1045 through autograd in the
+    reference): acc[k] += sum_s g[s, col0 + k] d[s, k] in float64 accumulators, against the fp64 sum of the same fp32 products;
+    row-strided g (a column slice, as the backward passes it), rows that do not fill the last warp, K beyond 256"""
+    from fsw_gnn_b200 import _lib
+    from fsw_gnn_b200._lib import dtype_code, ptr, stream_ptr
+    gen = torch.Generator(device=dev()); gen.manual_seed(S + K)
+    g = torch.randn(S, K + col0 + 3, device=dev(), dtype=dtype, generator=gen)
+    d = torch.randn(S, K, device=dev(), dtype=dtype, generator=gen)
+    acc = torch.full((K,), 0.25, dtype=torch.float64, device=dev())
+    gk = g[:, col0:col0 + K]
+    _lib.call(dev(), "fsw_column_dot", dtype_code(dtype), ptr(gk), gk.stride(0), ptr(d), d.stride(0), S, K, ptr(acc), stream_ptr(dev()))
+    ref = 0.25 + (gk.double() * d.double()).sum(dim=0)
+    scale = (gk.double() * d.double()).abs().sum(dim=0).max().item() + 1.0
+    err = (acc - ref).abs().max().item()
+    tol = (1e-12 if dtype == torch.float64 else 2e-6) * scale   # fp32: 64-term fp32 partial sums, then float64
+    from parity import LOG
+    LOG.append("column_dot S=%d K=%d %s: max|err|=%.2e (tolerance %.2e = relative to the largest sum of absolute terms)" % (S, K, dtype, err, tol))
+    assert err <= tol
