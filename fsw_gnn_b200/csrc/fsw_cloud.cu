@@ -30,6 +30,31 @@ __device__ __forceinline__ float fsw_cos_rank(unsigned r, float uh, float ul) {
     return __uint_as_float(__float_as_uint(p) ^ (__float_as_uint(t) << 31));
 }
 
+// the same for two (rank, slice) pairs at once on Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2: one issue slot for
+// both); nul = -ul.  Returns cos(pi (2 r + 1) u) WITHOUT the sign; `t` carries the parity of the rounded phase in its low bit.
+__device__ __forceinline__ float2 fsw_cos_rank2(unsigned r0, unsigned r1, float2 uh, float2 nul, float2& t) {
+    auto f2c = [](float c) { return make_float2(c, c); };
+    const float2 mb = make_float2(__uint_as_float(0x4B000000u | r0), __uint_as_float(0x4B000000u | r1));   // 2^23 + r
+    const float2 m = __ffma2_rn(mb, f2c(2.0f), f2c(-16777215.0f));     // 2 r + 1, exact
+    const float2 nm = __ffma2_rn(mb, f2c(-2.0f), f2c(16777215.0f));
+    const float2 ph = __fmul2_rn(m, uh);
+    const float2 nqe = __ffma2_rn(nm, uh, ph);                         // ph - m uh, exact
+    const float2 npl = __ffma2_rn(m, nul, nqe);                        // -(m ul + m uh - ph)
+    t = __fadd2_rn(ph, f2c(12582912.0f));
+    const float2 kk = __fadd2_rn(t, f2c(-12582912.0f));                // rint(ph)
+    const float2 red = __ffma2_rn(kk, f2c(-1.0f), ph);
+    const float2 x = __ffma2_rn(npl, f2c(-1.0f), red);
+    const float2 y2 = __fmul2_rn(x, x);
+    float2 c = __ffma2_rn(y2, f2c(1.929574e-3f), f2c(-2.580689e-2f));
+    c = __ffma2_rn(y2, c, f2c(2.353306e-1f));
+    c = __ffma2_rn(y2, c, f2c(-1.335263f));
+    c = __ffma2_rn(y2, c, f2c(4.058712f));
+    c = __ffma2_rn(y2, c, f2c(-4.934802f));
+    c = __ffma2_rn(y2, c, f2c(1.0f));
+    return c;
+}
+__device__ __forceinline__ float fsw_flip(float v, float t) { return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(t) << 31)); }
+
 // per-slice constants of a cloud size n: double-float xi_k / n and the amplitude (1 + xi_k) A0(n, k)
 __device__ __forceinline__ void fsw_slice_consts(float xi, int n, float& uh, float& ul, float& amp) {
     const double u = (double)xi / (double)n;
@@ -66,8 +91,21 @@ __global__ void __launch_bounds__(256) fsw_cloud_bwd_dx_kernel(const float* __re
     float acc[D];
 #pragma unroll
     for (int dd = 0; dd < D; ++dd) acc[dd] = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
+    int k = 0;
+    for (; k + 16 <= K; k += 16) {   // 16 rank loads in flight, then two slices per packed instruction
+        unsigned r[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) r[u] = rp[(int64_t)(k + u) * n];
+#pragma unroll
+        for (int u = 0; u < 16; u += 2) {
+            float2 t;
+            const float2 c = fsw_cos_rank2(r[u], r[u + 1], make_float2(s_uh[k + u], s_uh[k + u + 1]), make_float2(-s_ul[k + u], -s_ul[k + u + 1]), t);
+            const float dp0 = fsw_flip(s_ga[k + u], t.x) * c.x, dp1 = fsw_flip(s_ga[k + u + 1], t.y) * c.y;
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) acc[dd] = fmaf(dp1, s_th[(k + u + 1) * D + dd], fmaf(dp0, s_th[(k + u) * D + dd], acc[dd]));
+        }
+    }
+    for (; k < K; ++k) {
         const unsigned r = rp[(int64_t)k * n];
         const float dp = s_ga[k] * fsw_cos_rank(r, s_uh[k], s_ul[k]);
 #pragma unroll
@@ -84,9 +122,17 @@ __global__ void __launch_bounds__(256) fsw_cloud_bwd_dtheta_kernel(const float* 
                                                                    int64_t ld_g, int64_t g_col0, const unsigned short* __restrict__ ranksT,
                                                                    float* __restrict__ dtheta, int64_t ld_dt) {
     __shared__ float red[8][D];
+    __shared__ float s_c[3];
     const int k = blockIdx.x;
-    float uh, ul, amp;
-    fsw_slice_consts(__ldg(freqs + k), n, uh, ul, amp);
+    if (threadIdx.x == 0) {   // double-precision division and the amplitude: once per block, not per thread
+        float uh0, ul0, amp0;
+        fsw_slice_consts(__ldg(freqs + k), n, uh0, ul0, amp0);
+        s_c[0] = uh0;
+        s_c[1] = ul0;
+        s_c[2] = amp0;
+    }
+    __syncthreads();
+    const float uh = s_c[0], ul = s_c[1], amp = s_c[2];
     const int64_t s0 = (int64_t)blockIdx.y * clouds_per_block;
     const int64_t s1 = min(S, s0 + clouds_per_block);
     float acc[D];
@@ -96,7 +142,17 @@ __global__ void __launch_bounds__(256) fsw_cloud_bwd_dtheta_kernel(const float* 
         const float ga = amp * __ldg(g + fsw_rowoff(s, ld_g) + g_col0 + k);
         const unsigned short* rp = ranksT + ((int64_t)s * K + k) * n;
         const float* xs = X + (int64_t)s * n * D;
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        int e = threadIdx.x;
+        for (; e + (int)blockDim.x < n; e += 2 * blockDim.x) {   // two points per packed instruction
+            const int e1 = e + blockDim.x;
+            float2 t;
+            const float2 c = fsw_cos_rank2(rp[e], rp[e1], make_float2(uh, uh), make_float2(-ul, -ul), t);
+            const float dp0 = fsw_flip(ga, t.x) * c.x, dp1 = fsw_flip(ga, t.y) * c.y;
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd)
+                acc[dd] = fmaf(dp1, __ldg(xs + (int64_t)e1 * D + dd), fmaf(dp0, __ldg(xs + (int64_t)e * D + dd), acc[dd]));
+        }
+        for (; e < n; e += blockDim.x) {
             const float dp = ga * fsw_cos_rank(rp[e], uh, ul);
 #pragma unroll
             for (int dd = 0; dd < D; ++dd) acc[dd] = fmaf(dp, __ldg(xs + (int64_t)e * D + dd), acc[dd]);
