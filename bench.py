@@ -426,12 +426,19 @@ def main():
     resident_step()   # the e2e pass cleared the graph cache: prepare the resident graph (and its side-stream transposition) untimed
     torch.cuda.synchronize()
     _lib.profile_enable(True)
+    if world > 1:
+        fdist.EXCHANGE_TIMING["on"] = True
     nprof = 2
     for _ in range(nprof):
         resident_step()
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     _lib.profile_enable(False)
+    nccl_ms = None
+    if world > 1:
+        fdist.EXCHANGE_TIMING["on"] = False
+        # time the compute stream spent between issuing a collective and having waited for it (skew between the ranks included)
+        nccl_ms = {k: round(v / nprof, 3) for k, v in fdist.exchange_timing_read().items()}
     peaks, peak_kind = measured_peaks()
     traffic = ncu_traffic()
     kern = {k: v for k, v in prof.items() if k.startswith(("fwd", "bwd"))}
@@ -480,6 +487,7 @@ def main():
         "roofline": roofline,
         "roofline_forward": roofline_forward,
         "kernel_ms_per_step": breakdown,
+        "nccl_exposed_ms_per_step": nccl_ms,
     }
 
     # ---- secondary workloads + CPU baseline (rank 0 does the printing; every rank runs its shard) ----

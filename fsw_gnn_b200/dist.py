@@ -19,6 +19,42 @@ import torch.distributed as dist
 from . import graph as _graph
 
 
+# Optional timing of the exchange as the compute stream sees it (bench.py `nccl_exposed_ms_per_step`): a CUDA event before a
+# collective is issued and one after the compute stream has waited for it.  Off by default (no events, no overhead).
+EXCHANGE_TIMING = {"on": False, "events": []}
+
+
+class _TimedWork:
+    """async work handle whose wait() also records the end event on the waiting stream"""
+
+    def __init__(self, work, start, kind):
+        self.work, self.start, self.kind = work, start, kind
+
+    def wait(self):
+        self.work.wait()
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        EXCHANGE_TIMING["events"].append((self.kind, self.start, end))
+
+
+def _timing_start():
+    if not EXCHANGE_TIMING["on"]:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def exchange_timing_read():
+    """{kind: total ms} of the collectives recorded since the last read (synchronises their events)"""
+    out = {}
+    for kind, a, b in EXCHANGE_TIMING["events"]:
+        b.synchronize()
+        out[kind] = out.get(kind, 0.0) + a.elapsed_time(b)
+    EXCHANGE_TIMING["events"] = []
+    return out
+
+
 def remap_sources(src, row_ranges, max_rows):
     """Global source id -> row of the padded all-gathered feature matrix [G * max_rows, d]
     (rank r's vertices occupy rows r*max_rows .. r*max_rows + n_r)."""
@@ -96,8 +132,9 @@ class RowExchange:
             pad = torch.zeros((self.max_rows - n,) + tuple(xp_local.shape[1:]), dtype=xp_local.dtype, device=xp_local.device)
             xp_local = torch.cat((xp_local, pad), dim=0)
         out = torch.empty((G * self.max_rows,) + tuple(xp_local.shape[1:]), dtype=xp_local.dtype, device=xp_local.device)
+        t0 = _timing_start()
         work = dist.all_gather_into_tensor(out, xp_local.contiguous(), group=self.group, async_op=True)
-        return out, work
+        return out, (work if t0 is None else _TimedWork(work, t0, "all_gather_rows"))
 
     def scatter_async(self, g_all, n_local):
         """-> (summed block [max_rows, ld] (valid after work.wait(); take [:n_local]), work)"""
@@ -109,8 +146,9 @@ class RowExchange:
             r = dist.get_rank(self.group)
             return g_all[r * rows:(r + 1) * rows], work
         out = torch.empty((rows,) + tuple(g_all.shape[1:]), dtype=g_all.dtype, device=g_all.device)
+        t0 = _timing_start()
         work = dist.reduce_scatter_tensor(out, g_all, group=self.group, async_op=True)
-        return out, work
+        return out, (work if t0 is None else _TimedWork(work, t0, "reduce_scatter_rows"))
 
     def scatter(self, g_all, n_local):
         G = dist.get_world_size(self.group)
@@ -162,7 +200,12 @@ def all_reduce_gradients(modules, group=None):
     if not params:
         return
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    t0 = _timing_start()
     dist.all_reduce(flat, group=group)
+    if t0 is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        EXCHANGE_TIMING["events"].append(("all_reduce_params", t0, end))
     off = 0
     for p in params:
         n = p.numel()
