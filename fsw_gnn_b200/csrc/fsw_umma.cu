@@ -220,22 +220,29 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
         uint32_t ph = 0;
         const int nvec = (int)((2 * UM_A_BYTES + 2 * bbytes) / 32);   // float4 count of the A tile + the B tile
         const int nvecA = UM_A_BYTES / 16;
+        const uint32_t smem_s = smem_u32(smem);   // 32-bit shared-window addresses: LDS / STS instead of generic loads and stores
+        // fp32 -> tf32, round to nearest with ties away (what cvt.rna.tf32.f32 returns for every finite input; the PTX
+        // instruction is emulated with an extra Inf / NaN test and select per value, ~40 % of the split's instructions)
+        auto rna = [](uint32_t b) { return (b + 0x1000u) & 0xffffe000u; };
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const WorkItem w = decode_item(p, item);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 mbar_wait(&full[s], ph);
-                uint8_t* st = smem + s * stage_bytes;
+                const uint32_t st = smem_s + s * stage_bytes;
 #pragma unroll 4
                 for (int i = t; i < nvec; i += 128) {
                     // the A tile is followed by its lo tile, then the B tile and its lo tile
-                    float4* src = (i < nvecA) ? (float4*)st + i : (float4*)(st + 2 * UM_A_BYTES) + (i - nvecA);
-                    float4* dst = (i < nvecA) ? (float4*)(st + UM_A_BYTES) + i : (float4*)(st + 2 * UM_A_BYTES + bbytes) + (i - nvecA);
-                    const float4 v = *src;
-                    float4 hi, lo;
-                    hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
-                    lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
-                    *src = hi;
-                    *dst = lo;
+                    const uint32_t src = (i < nvecA) ? st + 16u * i : st + 2 * UM_A_BYTES + 16u * (i - nvecA);
+                    const uint32_t dst = (i < nvecA) ? st + UM_A_BYTES + 16u * i : st + 2 * UM_A_BYTES + bbytes + 16u * (i - nvecA);
+                    uint32_t v[4], hi[4], lo[4];
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(src) : "memory");
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        hi[c] = rna(v[c]);
+                        lo[c] = rna(__float_as_uint(__uint_as_float(v[c]) - __uint_as_float(hi[c])));
+                    }
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(src), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&xfrm[s]);
