@@ -8,9 +8,9 @@
 // into TWO accumulators in tensor memory that are added in the epilogue, so the 2^-11-times smaller correction terms
 // never ride through the rounding of the large accumulator.  The dropped A_lo . B_lo term is 2^-22 relative.
 //
-// One persistent CTA per SM, 14 warps:
+// One persistent CTA per SM, 18 warps (14 in mode 2):
 //   warp 0      TMA producer   global -> shared (128-byte swizzle), ring of 2 stages, mbarrier complete_tx
-//   warps 2-5   splitter       hi/lo split of the landed tiles in place (generic proxy) + fence.proxy.async
+//   warps 2-5, 14-17  splitter  hi/lo split of the landed tiles in place (generic proxy) + fence.proxy.async
 //   warp 1      MMA issuer     one thread: 3 tcgen05.mma per k-step, tcgen05.commit releases the stage / publishes the tile
 //   warps 6-13  epilogue       tcgen05.ld -> registers (main + corr [+ bias]) -> swizzled staging -> TMA store / reduce-add
 // Modes: 0 = NT (A [M,Kd], B [N,Kd]: both K-major), 1 = NN (B [Kd,N]: MN-major), 2 = TN (A [Kd,M], B [Kd,N]: both MN-major,
@@ -34,7 +34,12 @@ constexpr int UM_BK = 16;
 constexpr int UM_ROWB = UM_BK * 4;       // bytes of one K-major tile row (64: SWIZZLE_64B)
 constexpr int UM_BOXB = 32 * UM_ROWB;    // bytes of one MN-major TMA box: [UM_BK k-rows][32 floats]
 constexpr int UM_MAX_STAGES = 8;
-constexpr int UM_THREADS = 448;
+// NT / NN: 18 warps, 8 of them splitters (warps 2-5 and 14-17: the hi/lo split is the slowest stage of the ring for long
+// contractions, C5 project 1.80 -> 1.54 ms); TN keeps 14 warps (its epilogue accumulators need the registers: 1.39 vs 1.46 ms)
+template <int MODE>
+constexpr int um_threads() { return MODE == 2 ? 448 : 576; }
+template <int MODE>
+constexpr int um_split_threads() { return MODE == 2 ? 128 : 256; }
 // The tensor core adds into the fp32 accumulator with truncation (measured: a chain of 1024 k-steps of positive terms ends
 // 5.5e-5 low, 5.4e-8 per k-step), so no chain is longer than a round: the accumulators are drained after UM_FLUSH_TN
 // k-blocks (32 k-steps) in the long reductions of mode 2, after UM_FLUSH k-blocks (contraction length 512) otherwise.
@@ -81,7 +86,7 @@ __device__ __forceinline__ WorkItem decode_item(const UmmaParams& p, int item) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(UM_THREADS, 1)
+__global__ void __launch_bounds__(um_threads<MODE>(), 1)
 fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__ CUtensorMap tB0,
                 const __grid_constant__ CUtensorMap tA1, const __grid_constant__ CUtensorMap tB1,
                 const __grid_constant__ CUtensorMap tC, const UmmaParams p) {
@@ -111,7 +116,7 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < UM_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&xfrm[s], 128);
+            mbar_init(&xfrm[s], um_split_threads<MODE>());
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -213,9 +218,9 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
+    } else if (warp < 6 || warp >= 14) {
         // ------------------------------------------------ hi / lo split -------------------------------------------------
-        const int t = threadIdx.x - 64;
+        const int t = (warp < 6) ? threadIdx.x - 64 : threadIdx.x - 448 + 128;
         int s = 0;
         uint32_t ph = 0;
         const int nvec = (int)((2 * UM_A_BYTES + 2 * bbytes) / 32);   // float4 count of the A tile + the B tile
@@ -230,7 +235,7 @@ fsw_umma_kernel(const __grid_constant__ CUtensorMap tA0, const __grid_constant__
                 mbar_wait(&full[s], ph);
                 const uint32_t st = smem_s + s * stage_bytes;
 #pragma unroll 4
-                for (int i = t; i < nvec; i += 128) {
+                for (int i = t; i < nvec; i += um_split_threads<MODE>()) {
                     // the A tile is followed by its lo tile, then the B tile and its lo tile
                     const uint32_t src = (i < nvecA) ? st + 16u * i : st + 2 * UM_A_BYTES + 16u * (i - nvecA);
                     const uint32_t dst = (i < nvecA) ? st + UM_A_BYTES + 16u * i : st + 2 * UM_A_BYTES + bbytes + 16u * (i - nvecA);
@@ -508,7 +513,7 @@ int fsw_umma_gemm(int op, int64_t M, int64_t N, int nseg, const int64_t* Kd, con
     do {                                                                                                                   \
         FSW_CUDA(cudaFuncSetAttribute(fsw_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         fsw_prof_begin(labels[MODE], st);                                                                                  \
-        fsw_umma_kernel<MODE><<<grid, UM_THREADS, smem, st>>>(tA[0], tB[0], tA[1], tB[1], tC, p);                          \
+        fsw_umma_kernel<MODE><<<grid, um_threads<MODE>(), smem, st>>>(tA[0], tB[0], tA[1], tB[1], tC, p);                          \
         fsw_prof_end(st);                                                                                                  \
     } while (0)
     if (op == 0) FSW_UMMA_LAUNCH(0);
