@@ -486,6 +486,7 @@ def main():
         "gpu_launches": int(gpu_launches),
         "roofline": roofline,
         "roofline_forward": roofline_forward,
+        "hbm_reserved_gb": round(torch.cuda.max_memory_reserved(dev) / 1e9, 1),
         "kernel_ms_per_step": breakdown,
         "nccl_exposed_ms_per_step": nccl_ms,
     }

@@ -163,7 +163,7 @@ class GraphCSR:
 # `_version` catches in-place edits.
 # ------------------------------------------------------------------------------------------------
 _GRAPH_CACHE = []
-_GRAPH_CACHE_SIZE = 4
+_GRAPH_CACHE_SIZE = 2   # the layers of a network share one graph; two entries cover alternating train / validation graphs
 
 
 def cached_graph(edge_index, num_vertices, self_loop_weight, edge_weighting, thresh, dtype, use_cache=True, coalesce=False):

@@ -15,6 +15,26 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=device)
 
 
+# Scratch of the embedding kernels (coefficient tables, pre-scaled gradient, merge tiles; up to several GB at configs[3]) is only
+# live inside one library call, and calls on one stream are ordered: every plan on a (device, stream) shares one buffer instead
+# of holding its own (a training loop that meets a new graph every step otherwise keeps one set per cached graph).  Buffers are
+# never released or resized in place - a larger request adds a new one - so pointers baked into a captured CUDA graph stay valid.
+_SCRATCH_POOL = {}
+
+
+def _shared_scratch(nbytes, device):
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    bufs = _SCRATCH_POOL.setdefault(key, [])
+    for b in bufs:
+        if b.numel() >= nbytes:
+            return b
+    b = _ws(nbytes, device)
+    bufs.append(b)
+    bufs.sort(key=lambda t: t.numel())
+    return b
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -75,15 +95,17 @@ class SegmentPlan:
         return self._mass_t
 
     def scratch(self, K, backward):
+        """scratch buffer for one fsw_embed_forward / fsw_embed_backward call (shared per device and stream, see _shared_scratch)"""
         key = (int(K), bool(backward))
-        if key not in self._scratch:
+        if key not in self._scratch:   # the SIZE is cached per plan, the buffer is shared
             lib = _lib.load()
             nbytes = lib.fsw_embed_scratch_bytes(dtype_code(self.dtype), self.bucket_offsets, int(K), self.max_n_eff,
                                                  1 if backward else 0)
             if backward and self.col is not None:
                 nbytes += lib.fsw_embed_backward_extra_bytes(dtype_code(self.dtype), self.S, int(K))
-            self._scratch[key] = _ws(nbytes, self.device) if nbytes > 0 else None
-        return self._scratch[key]
+            self._scratch[key] = int(nbytes)
+        nbytes = self._scratch[key]
+        return _shared_scratch(nbytes, self.device) if nbytes > 0 else None
 
     def _build_transpose(self, key, side):
         lib = _lib.load()
