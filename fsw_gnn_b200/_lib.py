@@ -41,7 +41,7 @@ _SIGNATURES = {
     "launch_add_block_sums_kernel_double": (None, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64]),
     "fsw_segcumsum_workspace_bytes": (c_sz, [c_i64]),
     "fsw_segcumsum": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_sz, c_vp]),
-    "fsw_csr_workspace_bytes": (c_sz, [c_i64]),
+    "fsw_csr_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "fsw_csr_from_edge_index": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "fsw_rowptr_from_sorted_rows": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "fsw_edge_weights": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_dbl, c_i32, c_vp, c_vp, c_vp]),
@@ -66,7 +66,7 @@ _SIGNATURES = {
     "fsw_embed_backward_weights": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_dbl, c_i32,
                                            c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "fsw_embed_weight_grad_finish": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_dbl, c_i32, c_vp, c_vp, c_vp, c_vp]),
-    "fsw_transpose_workspace_bytes": (c_sz, [c_i64]),
+    "fsw_transpose_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "fsw_csr_transpose": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 

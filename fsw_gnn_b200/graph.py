@@ -104,7 +104,7 @@ class GraphCSR:
         self.rowptr = torch.empty(N + 1, dtype=torch.int32, device=device)
         self.col = torch.empty(max(Etot, 1), dtype=torch.int32, device=device)[:Etot]
         self.eid = torch.empty(max(Etot, 1), dtype=torch.int32, device=device)[:Etot]
-        ws = _ws(lib.fsw_csr_workspace_bytes(N), device)
+        ws = _ws(lib.fsw_csr_workspace_bytes(N, E), device)
         _lib.call(device, "fsw_csr_from_edge_index", ptr(ei), E, N, self_loops, ptr(self.rowptr), ptr(self.col), ptr(self.eid),
                   ptr(ws), ws.numel(), stream_ptr(device))
         gcn = 1 if edge_weighting == "gcn" else 0

@@ -114,7 +114,7 @@ class SegmentPlan:
         tseg = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
         tslot = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
         tn = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)
-        ws = _ws(lib.fsw_transpose_workspace_bytes(key), dev)
+        ws = _ws(lib.fsw_transpose_workspace_bytes(key, self.E), dev)
 
         def launch():
             _lib.call(dev, "fsw_csr_transpose", ptr(self.rowptr), ptr(self.col), ptr(self.info), self.S, key, self.E,

@@ -97,8 +97,9 @@ int fsw_segcumsum(int dtype, const void* values_in, void* values_out, const void
  * Duplicate (dst, src) pairs are kept as separate elements: the embedding of a multiset is
  * unchanged by splitting a weight over two copies of the same point, so this equals the
  * reference's `coalesce()` sum (fsw_conv.py:397-398) in value and in gradient.
- * workspace: fsw_csr_workspace_bytes(N).  `counts` is scratch [N+1] int32 inside it. */
-size_t fsw_csr_workspace_bytes(int64_t N);
+ * workspace: fsw_csr_workspace_bytes(N, E).  The elements of a segment keep the order of the edge list (stable sort by
+ * destination), so the CSR of a graph - and with it the order in which exact key ties are resolved - is reproducible. */
+size_t fsw_csr_workspace_bytes(int64_t N, int64_t E);
 int fsw_csr_from_edge_index(const int64_t* edge_index, int64_t E, int64_t N, int self_loops, int32_t* rowptr,
                             int32_t* col, int32_t* eid, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -115,13 +116,14 @@ int fsw_edge_weights(int dtype, const int32_t* rowptr, const int32_t* col, const
 /* Transpose of a CSR segment structure with explicit columns: for every point row j (0 <= j < Nrows) the
  * (segment, slot) pairs that reference it: tptr [Nrows+1], tseg [E], tslot [E], tn [E] = number of elements of
  * that segment when it is eligible for the source-major backward (uniform weights, n <= nmax_eligible), else 0.
- * `info` comes from fsw_segment_plan.  workspace: fsw_transpose_workspace_bytes(Nrows).
+ * `info` comes from fsw_segment_plan.  workspace: fsw_transpose_workspace_bytes(Nrows, E).  The pairs of a source row are
+ * listed in element order (stable sort), so the source-major backward sums them in the same order in every run.
  * A transposition handed to fsw_embed_backward must be built with nmax_eligible = FSW_RANKT_ELIGIBLE(max n_eff of
  * the plan): the backward serves exactly those segments through it - every uniform segment of up to FSW_RANKT_NMAX
  * elements (the plan has a closed size bucket that ends there); hubs beyond are re-sorted and added with atomics. */
 #define FSW_RANKT_NMAX 32768
 #define FSW_RANKT_ELIGIBLE(max_n_eff) (FSW_RANKT_NMAX)
-size_t fsw_transpose_workspace_bytes(int64_t Nrows);
+size_t fsw_transpose_workspace_bytes(int64_t Nrows, int64_t E);
 int fsw_csr_transpose(const int32_t* rowptr, const int32_t* col, const int32_t* info, int64_t S, int64_t Nrows, int64_t E,
                       int nmax_eligible, int32_t* tptr, int32_t* tseg, int32_t* tslot, int32_t* tn, void* workspace,
                       size_t workspace_bytes, void* stream);
