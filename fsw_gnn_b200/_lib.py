@@ -43,6 +43,8 @@ _SIGNATURES = {
     "fsw_segcumsum": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp, c_sz, c_vp]),
     "fsw_csr_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "fsw_csr_from_edge_index": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "fsw_csr_coalesce_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "fsw_csr_coalesce": (c_i32, [c_i32, c_vp, c_i64, c_i64, c_i32, c_dbl, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "fsw_rowptr_from_sorted_rows": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "fsw_edge_weights": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_dbl, c_i32, c_vp, c_vp, c_vp]),
     "fsw_plan_workspace_bytes": (c_sz, [c_i64]),

@@ -328,6 +328,77 @@ __global__ void __launch_bounds__(256) transpose_lookup(const int32_t* __restric
     tn[t] = elig_of_elem[e];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Coalescing CSR (graphs with edge features, fsw_conv.py:397-398, :438-439): duplicate (dst, src) pairs become ONE element that
+// carries the sum of their base weights; every input edge learns the slot it was merged into (the caller sums the edge
+// features per slot).  Stable radix sort of 64-bit keys dst * N + src, head flags, scan.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) coal_keys(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int64_t N,
+                                                 int self_loops, unsigned long long* __restrict__ keys, int32_t* __restrict__ ids) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tot = E + (self_loops ? N : 0);
+    if (i >= tot) return;
+    const int64_t d = (i < E) ? dst[i] : i - E, c = (i < E) ? src[i] : i - E;
+    keys[i] = (d >= 0 && d < N && c >= 0 && c < N) ? (unsigned long long)d * (unsigned long long)N + (unsigned long long)c
+                                                  : (unsigned long long)N * (unsigned long long)N;   // invalid: behind everything
+    ids[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256) coal_heads(const unsigned long long* __restrict__ keys, int64_t tot, int64_t N, int* __restrict__ head) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= tot) return;
+    const unsigned long long k = keys[p];
+    const bool valid = k < (unsigned long long)N * (unsigned long long)N;
+    head[p] = (valid && (p == 0 || keys[p - 1] != k)) ? 1 : 0;
+}
+
+// one thread per sorted position: the slot of its input edge; the head of a run writes the element (column, summed base weight,
+// destination count).  Runs are short (duplicates are rare), so the head walks its run - a deterministic sum.
+template <typename T>
+__global__ void __launch_bounds__(256) coal_emit(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ ids,
+                                                 const int* __restrict__ head, const int* __restrict__ excl, int64_t tot, int64_t E,
+                                                 int64_t N, double slw, int32_t* __restrict__ col, T* __restrict__ W,
+                                                 int32_t* __restrict__ slot_of_elem, int* __restrict__ counts, int32_t* __restrict__ nslots) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= tot) return;
+    const unsigned long long k = keys[p];
+    const bool valid = k < (unsigned long long)N * (unsigned long long)N;
+    const int slot = excl[p] + head[p] - 1;   // exclusive scan of the heads + own head - 1 = index of the run this position is in
+    slot_of_elem[ids[p]] = valid ? slot : -1;
+    if (head[p]) {
+        double w = 0.0;
+        for (int64_t q = p; q < tot && keys[q] == k; ++q) w += (ids[q] < E) ? 1.0 : slw;
+        col[slot] = (int32_t)(k % (unsigned long long)N);
+        W[slot] = (T)w;
+        atomicAdd(counts + (int64_t)(k / (unsigned long long)N), 1);
+    }
+    if (p == tot - 1) *nslots = excl[p] + head[p];
+}
+
+// in-degrees (sum of the element weights of a row) and, with gcn weighting, w / sqrt(deg[dst]) / sqrt(deg[src])
+template <typename T>
+__global__ void __launch_bounds__(256) coal_weights(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N,
+                                                    T* __restrict__ deg, T* __restrict__ W, int phase) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N) return;
+    const int lo = rowptr[v], hi = rowptr[v + 1];
+    if (phase == 0) {
+        double d = 0.0;
+        for (int p = lo; p < hi; ++p) d += (double)W[p];
+        deg[v] = (T)d;
+    } else {
+        const double dv = (double)deg[v];
+        for (int p = lo; p < hi; ++p) W[p] = (T)((double)W[p] / sqrt(dv) / sqrt((double)deg[col[p]]));
+    }
+}
+
+size_t sort64_temp_bytes(int64_t n) {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)(n > 0 ? n : 1));
+    return (tb + 255) & ~(size_t)255;
+}
+
 }  // namespace
 
 extern "C" size_t fsw_transpose_workspace_bytes(int64_t Nrows, int64_t E) {
@@ -372,6 +443,76 @@ extern "C" int fsw_csr_transpose(const int32_t* rowptr, const int32_t* col, cons
         FSW_CHECK_LAUNCH("transpose_segids");
         transpose_lookup<<<(unsigned)fsw_cdiv(E, 256), 256, 0, st>>>(tslot, segid, elig, E, tseg, tn);
         FSW_CHECK_LAUNCH("transpose_lookup");
+    }
+    return FSW_OK;
+}
+
+extern "C" size_t fsw_csr_coalesce_workspace_bytes(int64_t N, int64_t E) {
+    // counts [N+1] + block sums | keys, sorted keys (8 B) | ids, sorted ids, heads, scanned heads (4 B) [E + N] each | cub temp
+    const int64_t tot = E + N;
+    const size_t head = ((size_t)((N + 1) + fsw_cdiv(tot + 1, SCAN_BLOCK) + fsw_cdiv(N + 1, SCAN_BLOCK) + 128) * sizeof(int) + 255) & ~(size_t)255;
+    const size_t a4 = ((size_t)(tot > 0 ? tot : 1) * 4 + 255) & ~(size_t)255;
+    const size_t a8 = ((size_t)(tot > 0 ? tot : 1) * 8 + 255) & ~(size_t)255;
+    return head + 2 * a8 + 4 * a4 + sort64_temp_bytes(tot);
+}
+
+// edge_index [2, E] int64 -> coalesced destination-major CSR: rowptr [N+1], col [cap], W [cap] (`dtype`; cap >= E (+ N with self
+// loops): the first *nslots entries are written), slot_of_elem [E (+ N)] = CSR slot of every input edge (then of every self
+// loop), deg [N] in-degrees, nslots (device int32).  gcn != 0: W = base / sqrt(deg[dst]) / sqrt(deg[src]).
+extern "C" int fsw_csr_coalesce(int dtype, const int64_t* edge_index, int64_t E, int64_t N, int self_loops, double self_loop_weight,
+                                int gcn, int32_t* rowptr, int32_t* col, void* W, int32_t* slot_of_elem, void* deg, int32_t* nslots,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    if (N < 0 || E < 0) return fsw_fail(FSW_ERR_INVALID, "fsw_csr_coalesce: negative size");
+    if (E + N >= (int64_t)INT32_MAX) return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_csr_coalesce: more than 2^31 elements");
+    if (N >= ((int64_t)1 << 31)) return fsw_fail(FSW_ERR_UNSUPPORTED, "fsw_csr_coalesce: more than 2^31 vertices");
+    if (!rowptr || !col || !W || !slot_of_elem || !deg || !nslots) return fsw_fail(FSW_ERR_INVALID, "fsw_csr_coalesce: null argument");
+    if (dtype != FSW_F32 && dtype != FSW_F64) return fsw_fail(FSW_ERR_INVALID, "fsw_csr_coalesce: dtype %d", dtype);
+    if (workspace_bytes < fsw_csr_coalesce_workspace_bytes(N, E)) return fsw_fail(FSW_ERR_WORKSPACE, "fsw_csr_coalesce: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t totmax = E + N, tot = E + (self_loops ? N : 0);
+    const size_t head_b = ((size_t)((N + 1) + fsw_cdiv(totmax + 1, SCAN_BLOCK) + fsw_cdiv(N + 1, SCAN_BLOCK) + 128) * sizeof(int) + 255) & ~(size_t)255;
+    const size_t a4 = ((size_t)(totmax > 0 ? totmax : 1) * 4 + 255) & ~(size_t)255;
+    const size_t a8 = ((size_t)(totmax > 0 ? totmax : 1) * 8 + 255) & ~(size_t)255;
+    unsigned char* wsb = (unsigned char*)workspace;
+    int* counts = (int*)wsb;
+    int* btmp = counts + (N + 1);
+    unsigned long long* keys = (unsigned long long*)(wsb + head_b);
+    unsigned long long* keys_s = (unsigned long long*)(wsb + head_b + a8);
+    int32_t* ids = (int32_t*)(wsb + head_b + 2 * a8);
+    int32_t* ids_s = (int32_t*)(wsb + head_b + 2 * a8 + a4);
+    int* heads = (int*)(wsb + head_b + 2 * a8 + 2 * a4);
+    int* excl = (int*)(wsb + head_b + 2 * a8 + 3 * a4);
+    void* temp = wsb + head_b + 2 * a8 + 4 * a4;
+    FSW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(N + 1) * sizeof(int), st));
+    FSW_CUDA(cudaMemsetAsync(nslots, 0, sizeof(int32_t), st));
+    if (tot > 0) {
+        const unsigned blocks = (unsigned)fsw_cdiv(tot, 256);
+        coal_keys<<<blocks, 256, 0, st>>>(edge_index, edge_index + E, E, N, self_loops, keys, ids);
+        FSW_CHECK_LAUNCH("coal_keys");
+        size_t tb = sort64_temp_bytes(totmax);
+        int bits = 2 * key_bits(N) + 1;
+        if (bits > 64) bits = 64;
+        FSW_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys_s, ids, ids_s, (int)tot, 0, bits, st));
+        fsw_count_launch(4);
+        coal_heads<<<blocks, 256, 0, st>>>(keys_s, tot, N, heads);
+        FSW_CHECK_LAUNCH("coal_heads");
+        int rc = exclusive_scan_i32(heads, tot, excl, btmp, st);
+        if (rc) return rc;
+        if (dtype == FSW_F32)
+            coal_emit<float><<<blocks, 256, 0, st>>>(keys_s, ids_s, heads, excl, tot, E, N, self_loop_weight, col, (float*)W, slot_of_elem, counts, nslots);
+        else
+            coal_emit<double><<<blocks, 256, 0, st>>>(keys_s, ids_s, heads, excl, tot, E, N, self_loop_weight, col, (double*)W, slot_of_elem, counts, nslots);
+        FSW_CHECK_LAUNCH("coal_emit");
+    }
+    int rc = exclusive_scan_i32(counts, N + 1, rowptr, btmp, st);
+    if (rc) return rc;
+    if (N > 0) {
+        const unsigned nb = (unsigned)fsw_cdiv(N, 256);
+        for (int phase = 0; phase < (gcn ? 2 : 1); ++phase) {
+            if (dtype == FSW_F32) coal_weights<float><<<nb, 256, 0, st>>>(rowptr, col, N, (float*)deg, (float*)W, phase);
+            else coal_weights<double><<<nb, 256, 0, st>>>(rowptr, col, N, (double*)deg, (double*)W, phase);
+            FSW_CHECK_LAUNCH("coal_weights");
+        }
     }
     return FSW_OK;
 }

@@ -114,30 +114,34 @@ class GraphCSR:
                   float(self_loop_weight), gcn, ptr(self.in_degrees), ptr(self.W), stream_ptr(device))
 
     def _init_coalesced(self, edge_index, num_vertices, self_loop_weight, edge_weighting, dtype):
+        """fsw_csr_coalesce: stable 64-bit radix sort of dst * N + src, one element per distinct pair with the summed base weight
+        (replaces the reference's sparse_coo_tensor(...).coalesce(), fsw_conv.py:397-398); one small D2H read for the element count"""
         _lib.require_cuda(edge_index, "edge_index")
         assert edge_weighting in {"unit", "gcn"}, "invalid value passed in argument <edge_weighting>"
+        lib = _lib.load()
         device = edge_index.device
         N, E = int(num_vertices), int(edge_index.shape[1])
-        src, dst = edge_index[0].to(torch.int64), edge_index[1].to(torch.int64)
-        base = torch.ones(E, dtype=dtype, device=device)
-        if self_loop_weight > 0:
-            loops = torch.arange(N, device=device, dtype=torch.int64)
-            src, dst = torch.cat((src, loops)), torch.cat((dst, loops))
-            base = torch.cat((base, torch.full((N,), float(self_loop_weight), dtype=dtype, device=device)))
-        uniq, inverse = torch.unique(dst * N + src, sorted=True, return_inverse=True)
-        nslots = int(uniq.numel())
-        rows, cols = uniq // N, uniq % N
-        W = torch.zeros(nslots, dtype=dtype, device=device).index_add_(0, inverse, base)
-        deg = torch.zeros(N, dtype=dtype, device=device).index_add_(0, rows, W)
-        if edge_weighting == "gcn":
-            W = W / torch.sqrt(deg[rows]) / torch.sqrt(deg[cols])
+        ei = edge_index.contiguous()
+        if ei.dtype != torch.int64:
+            ei = ei.to(torch.int64)
+        self_loops = 1 if self_loop_weight > 0 else 0
+        cap = max(E + (N if self_loops else 0), 1)
+        self.rowptr = torch.empty(N + 1, dtype=torch.int32, device=device)
+        col = torch.empty(cap, dtype=torch.int32, device=device)
+        W = torch.empty(cap, dtype=dtype, device=device)
+        slot_of_elem = torch.empty(cap, dtype=torch.int32, device=device)
+        self.in_degrees = torch.empty(N, dtype=dtype, device=device)
+        nslots_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        ws = _ws(lib.fsw_csr_coalesce_workspace_bytes(N, E), device)
+        _lib.call(device, "fsw_csr_coalesce", dtype_code(dtype), ptr(ei), E, N, self_loops, float(self_loop_weight),
+                  1 if edge_weighting == "gcn" else 0, ptr(self.rowptr), ptr(col), ptr(W), ptr(slot_of_elem), ptr(self.in_degrees),
+                  ptr(nslots_dev), ptr(ws), ws.numel(), stream_ptr(device))
+        nslots = int(nslots_dev.item())
         self.N, self.E, self.Etot = N, E, nslots
-        self.rowptr = rowptr_from_sorted_rows(rows, N)
-        self.col = cols.to(torch.int32)
+        self.col = col[:nslots]
+        self.W = W[:nslots]
         self.eid = None
-        self.slot_of_edge = inverse[:E]
-        self.in_degrees = deg
-        self.W = W.contiguous()
+        self.slot_of_edge = slot_of_elem[:E].to(torch.int64)
 
     def plan(self, thresh, dtype):
         return SegmentPlan(self.N, self.Etot, self.rowptr, 0, self.col, self.W, thresh, dtype, self.rowptr.device)

@@ -103,6 +103,16 @@ size_t fsw_csr_workspace_bytes(int64_t N, int64_t E);
 int fsw_csr_from_edge_index(const int64_t* edge_index, int64_t E, int64_t N, int self_loops, int32_t* rowptr,
                             int32_t* col, int32_t* eid, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Coalescing variant (graphs with edge features: the reference's coalesce() sums the feature vectors of duplicate edges,
+ * fsw_conv.py:397-398, :438-439): duplicate (dst, src) pairs become ONE element with the summed base weight (1 per edge,
+ * self_loop_weight per self loop).  col / W have room for E (+ N) elements, the first *nslots (device int32) are written;
+ * slot_of_elem [E (+ N)] = CSR slot of every input edge, then of every self loop; deg [N] = in-degrees (`dtype`);
+ * gcn != 0: W = base / sqrt(deg[dst]) / sqrt(deg[src]).  Stable 64-bit radix sort: deterministic. */
+size_t fsw_csr_coalesce_workspace_bytes(int64_t N, int64_t E);
+int fsw_csr_coalesce(int dtype, const int64_t* edge_index, int64_t E, int64_t N, int self_loops, double self_loop_weight, int gcn,
+                     int32_t* rowptr, int32_t* col, void* W, int32_t* slot_of_elem, void* deg, int32_t* nslots, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* rows [nnz] int64 sorted ascending (a coalesced COO tensor, fsw_embedding.py:664-668) -> rowptr [S+1] int32 */
 int fsw_rowptr_from_sorted_rows(const int64_t* rows, int64_t nnz, int64_t S, int32_t* rowptr, void* stream);
 

@@ -585,3 +585,34 @@ def test_column_dot_vs_fp64(S, K, col0, dtype):
     from parity import LOG
     LOG.append("column_dot S=%d K=%d %s: max|err|=%.2e (tolerance %.2e = relative to the largest sum of absolute terms)" % (S, K, dtype, err, tol))
     assert err <= tol
+
+
+@pytest.mark.parametrize("self_loops", [0.0, 0.3])
+@pytest.mark.parametrize("weighting", ["unit", "gcn"])
+def test_coalesced_csr_matches_numpy(self_loops, weighting):
+    """fsw_csr_coalesce (graphs with edge features; the reference's sparse_coo_tensor(...).coalesce(), fsw_conv.py:397-398): index
+    work bit-exact against numpy's unique over dst * N + src - one element per distinct (dst, src) pair in sorted order, every
+    input edge mapped to its element, weights = summed base weights (gcn: / sqrt(deg dst) / sqrt(deg src)), in-degrees"""
+    from fsw_gnn_b200.graph import GraphCSR
+    rng = np.random.default_rng(5)
+    N, E = 200, 5000   # 5000 edges over 40 000 pairs: plenty of duplicates
+    ei = rng.integers(0, N, (2, E))
+    ei[1][ei[1] == 7] = 8     # an empty row
+    if weighting == "gcn" and self_loops == 0.0:
+        ei[0][ei[0] == 7] = 9
+    csr = GraphCSR(torch.as_tensor(ei, device=dev()), N, self_loops, weighting, torch.float64, coalesce=True)
+    src = np.concatenate([ei[0], np.arange(N)]) if self_loops > 0 else ei[0]
+    dst = np.concatenate([ei[1], np.arange(N)]) if self_loops > 0 else ei[1]
+    base = np.concatenate([np.ones(E), np.full(N, self_loops)]) if self_loops > 0 else np.ones(E)
+    uniq, inverse = np.unique(dst * N + src, return_inverse=True)
+    W = np.zeros(len(uniq)); np.add.at(W, inverse, base)
+    rows, cols = uniq // N, uniq % N
+    deg = np.zeros(N); np.add.at(deg, rows, W)
+    if weighting == "gcn":
+        W = W / np.sqrt(deg[rows]) / np.sqrt(deg[cols])
+    assert csr.Etot == len(uniq)
+    assert np.array_equal(csr.col.cpu().numpy(), cols)
+    assert np.array_equal(np.diff(csr.rowptr.cpu().numpy()), np.bincount(rows, minlength=N))
+    assert np.array_equal(csr.slot_of_edge.cpu().numpy(), inverse[:E])
+    np.testing.assert_allclose(csr.in_degrees.cpu().numpy(), deg, rtol=1e-14)
+    np.testing.assert_allclose(csr.W.cpu().numpy(), W, rtol=1e-14)
