@@ -495,7 +495,8 @@ class FSWEmbedFunction(torch.autograd.Function):
                 # the rank-recording forward writes every (segment, slice) of the uniform segments of up to 32768 elements;
                 # only a plan with other segments needs the zero fill (1.9 GB per layer at configs[3])
                 covered = X.dtype == torch.float32 and plan.uniform_fraction() == 1.0 and plan.max_n_eff <= RANKT_NMAX
-                dxi_out = (torch.empty if covered else torch.zeros)((plan.S, k1 - k0), dtype=X.dtype, device=X.device)
+                # (rows padded to the projected width: 32-byte aligned rows for the kernels that write and read it)
+                dxi_out = (torch.empty if covered else torch.zeros)((plan.S, ldc), dtype=X.dtype, device=X.device)[:, :k1 - k0]
             embed_forward(plan, xp, ldc, Ep, freqs[k0:k1], out, d_out, tm_dim + k0,
                           None if bias_core is None else bias_core[k0:k1], ranks, dxi_out)
             ch[5], ch[6] = ranks, dxi_out
